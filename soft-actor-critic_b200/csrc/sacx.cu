@@ -1,0 +1,786 @@
+// libsacx.so -- C ABI (include/sacx.h) over the B200-native SAC update engine.
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/sacx.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sacx_engine.cuh"
+
+namespace sacx {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------ ring
+constexpr int STAGE_ROWS = 4096;
+
+struct Ring {
+  int O, A, n_agents, W;
+  i64 cap, stride;                      // float words per agent block
+  i64 off_s, off_a, off_r, off_s2, off_d;
+  float* dev = nullptr;
+  bool own = false;
+  float* h_rows = nullptr;              // pinned staging [STAGE_ROWS, W]
+  StageHdr* h_hdr = nullptr;
+  float* d_rows = nullptr;
+  StageHdr* d_hdr = nullptr;
+  int staged = 0;
+  int stage_limit = STAGE_ROWS;          // <= capacity: two staged rows never target the same slot
+  std::vector<i64> pushes;              // host mirror of RingMeta.pushes (includes staged rows)
+  cudaStream_t stream = 0;
+  cudaEvent_t stage_free = nullptr;     // staging block may be overwritten once this event has fired
+  bool stage_busy = false;
+  // scratch for the host gather
+  void* scr_dev = nullptr; size_t scr_dev_bytes = 0;
+  void* scr_host = nullptr; size_t scr_host_bytes = 0;
+  long long launches = 0;
+
+  static void offsets(int O, int A, i64 cap, i64& s, i64& a, i64& r, i64& s2, i64& d, i64& total) {
+    i64 c = (i64)(sizeof(RingMeta) / 4);
+    s = c; c = align4(c + cap * O);
+    a = c; c = align4(c + cap * A);
+    r = c; c = align4(c + cap);
+    s2 = c; c = align4(c + cap * O);
+    d = c; c = align4(c + cap);
+    total = (c + 127) & ~(i64)127;
+  }
+  i64 len(int agent) const { return std::min(pushes[agent], cap); }
+  float* block(int agent) const { return dev + (i64)agent * stride; }
+
+  int wait_stage() {
+    if (stage_busy) {
+      SACX_CUDA(cudaEventSynchronize(stage_free));
+      stage_busy = false;
+    }
+    return SACX_OK;
+  }
+  int flush() {
+    if (staged == 0) return SACX_OK;
+    SACX_CUDA(cudaMemcpyAsync(d_rows, h_rows, (size_t)staged * W * sizeof(float), cudaMemcpyHostToDevice, stream));
+    SACX_CUDA(cudaMemcpyAsync(d_hdr, h_hdr, (size_t)staged * sizeof(StageHdr), cudaMemcpyHostToDevice, stream));
+    ring_scatter_kernel<<<(staged + 7) / 8, 256, 0, stream>>>(dev, stride, cap, off_s, off_a, off_r, off_s2, off_d, O, A,
+                                                              d_rows, d_hdr, staged);
+    ++launches;
+    SACX_CUDA(cudaGetLastError());
+    SACX_CUDA(cudaEventRecord(stage_free, stream));
+    stage_busy = true;
+    staged = 0;
+    return SACX_OK;
+  }
+  int push(int agent, const float* s, const float* a, float r, const float* s2, float d) {
+    if (agent < 0 || agent >= n_agents) return fail(SACX_ERR_INVALID, "ring push: agent out of range");
+    if (staged == 0) { int rc = wait_stage(); if (rc) return rc; }
+    float* row = h_rows + (size_t)staged * W;
+    memcpy(row, s, O * sizeof(float));
+    memcpy(row + O, a, A * sizeof(float));
+    row[O + A] = r;
+    memcpy(row + O + A + 1, s2, O * sizeof(float));
+    row[2 * O + A + 1] = d;
+    h_hdr[staged].agent = agent;
+    h_hdr[staged].pad = 0;
+    h_hdr[staged].push_no = pushes[agent]++;
+    if (++staged >= stage_limit) return flush();
+    return SACX_OK;
+  }
+  int ensure_scratch(size_t bytes) {
+    if (bytes > scr_dev_bytes) {
+      if (scr_dev) cudaFree(scr_dev);
+      if (scr_host) cudaFreeHost(scr_host);
+      scr_dev = scr_host = nullptr; scr_dev_bytes = scr_host_bytes = 0;
+      SACX_CUDA(cudaMalloc(&scr_dev, bytes));
+      SACX_CUDA(cudaMallocHost(&scr_host, bytes));
+      scr_dev_bytes = scr_host_bytes = bytes;
+    }
+    return SACX_OK;
+  }
+};
+
+// ------------------------------------------------------------------------------------------ engine runtime
+static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, const RunArgs& proto, bool per_phase) {
+  const Plan& hp = e->h_plans[plan_id];
+  if (pe < 0) pe = hp.n_phases;
+  RunArgs a = proto;
+  a.arena = e->arena; a.agent_stride = e->stride; a.scal_off = e->scal_off; a.hp = e->hp;
+  a.n_agents = e->cfg.n_agents; a.barrier = e->d_barrier; a.ctas_per_agent = e->grid_x;
+  if (e->ring) {
+    Ring* r = e->ring;
+    a.ring = r->dev; a.ring_stride = r->stride; a.ring_capacity = r->cap;
+    a.ring_s = r->off_s; a.ring_a = r->off_a; a.ring_r = r->off_r; a.ring_s2 = r->off_s2; a.ring_d = r->off_d;
+  }
+  const Plan* dplan = e->d_plans + plan_id;
+  auto launch = [&](int p0, int p1, int steps, dim3 grid, bool coop) -> int {
+    a.phase_begin = p0; a.phase_end = p1; a.n_steps = steps;
+    void* args[] = {(void*)&dplan, (void*)&a};
+    const void* fn = e->large ? (const void*)sacx_run_kernel<true> : (const void*)sacx_run_kernel<false>;
+    if (coop) {
+      SACX_CUDA(cudaMemsetAsync(e->d_barrier, 0, sizeof(unsigned) * (size_t)std::max(1, (int)grid.y), e->stream));
+      SACX_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(256), args, (size_t)e->smem_bytes, e->stream));
+    } else {
+      SACX_CUDA(cudaLaunchKernel(fn, grid, dim3(256), args, (size_t)e->smem_bytes, e->stream));
+    }
+    ++e->launches;
+    return SACX_OK;
+  };
+  if (per_phase) {
+    // one launch per phase, no in-kernel barrier: grid.x covers the phase's tiles, grid.y the agents
+    for (int s = 0; s < n_steps; ++s) {
+      RunArgs keep = a;
+      // external per-step arrays advance on the host
+      const i64 nb = (i64)e->cfg.n_agents * e->cfg.batch_size;
+      if (proto.idx_ext) a.idx_ext = proto.idx_ext + s * nb;
+      if (proto.eps1_ext) a.eps1_ext = proto.eps1_ext + s * nb * e->cfg.act_dim;
+      if (proto.eps2_ext) a.eps2_ext = proto.eps2_ext + s * nb * e->cfg.act_dim;
+      for (int p = pb; p < pe; ++p) {
+        const int tiles = std::max(1, hp.phases[p].ntiles);
+        int rc = launch(p, p + 1, 1, dim3(std::min(tiles, 65535), std::min(e->cfg.n_agents, 65535)), false);
+        if (rc) return rc;
+      }
+      a = keep;
+    }
+    return SACX_OK;
+  }
+  const bool coop = e->grid_x > 1;
+  const bool single_pass = (pe - pb == 1) && n_steps == 1 && e->grid_y >= e->cfg.n_agents;
+  return launch(pb, pe, n_steps, dim3(e->grid_x, e->grid_y), coop && !single_pass);
+}
+
+static int engine_init_scalars(Engine* e) {
+  AgentScalars s;
+  memset(&s, 0, sizeof s);
+  s.log_alpha = std::log(e->cfg.alpha);
+  // auto: alpha = exp(log_alpha) in f64 (agent.py:50); fixed: torch.tensor(alpha) is f32 (agent.py:55)
+  s.alpha = e->cfg.auto_entropy_tuning ? std::exp(s.log_alpha) : (double)(float)e->cfg.alpha;
+  s.alpha_f32 = (float)s.alpha;
+  s.metrics[4] = (float)s.alpha;
+  s.metrics[5] = (float)s.log_alpha;
+  for (int ag = 0; ag < e->cfg.n_agents; ++ag)
+    SACX_CUDA(cudaMemcpyAsync(e->arena + (i64)ag * e->stride + e->scal_off, &s, sizeof s, cudaMemcpyHostToDevice, e->stream));
+  SACX_CUDA(cudaStreamSynchronize(e->stream));
+  return SACX_OK;
+}
+
+static int validate(const sacx_config* c) {
+  if (!c) return fail(SACX_ERR_INVALID, "null config");
+  if (c->n_hidden_pi <= 0 || c->n_hidden_q <= 0) return fail(SACX_ERR_EMPTY_HIDDEN, "hidden_sizes cannot be empty");
+  if (c->n_hidden_pi > SACX_MAX_HIDDEN || c->n_hidden_q > SACX_MAX_HIDDEN)
+    return fail(SACX_ERR_INVALID, "more than SACX_MAX_HIDDEN hidden layers");
+  if (c->obs_dim <= 0 || c->act_dim <= 0 || c->act_dim > SACX_MAX_ACT) return fail(SACX_ERR_INVALID, "obs_dim/act_dim out of range (act_dim <= 32)");
+  if (c->batch_size <= 0 || c->n_agents <= 0) return fail(SACX_ERR_INVALID, "batch_size and n_agents must be positive");
+  for (int i = 0; i < c->n_hidden_pi; ++i) if (c->hidden_pi[i] <= 0 || c->hidden_pi[i] > 8192) return fail(SACX_ERR_INVALID, "policy hidden size out of range");
+  for (int i = 0; i < c->n_hidden_q; ++i) if (c->hidden_q[i] <= 0 || c->hidden_q[i] > 8192) return fail(SACX_ERR_INVALID, "q hidden size out of range");
+  const int acts[4] = {c->act_hidden_pi, c->act_out_pi, c->act_hidden_q, c->act_out_q};
+  for (int a : acts) if (a < 0 || a > SACX_ACT_SELU) return fail(SACX_ERR_ACTIVATION, "unknown activation id");
+  if (!(c->alpha > 0.0)) return fail(SACX_ERR_INVALID, "alpha must be positive");
+  return SACX_OK;
+}
+
+}  // namespace sacx
+
+using namespace sacx;
+
+struct sacx_ring_s { Ring r; };
+struct sacx_agent_s { Engine e; };
+
+extern "C" {
+
+const char* sacx_last_error(void) { return g_err.c_str(); }
+int sacx_version(void) { return SACX_VERSION; }
+int sacx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int sacx_sizeof_config(void) { return (int)sizeof(sacx_config); }
+int sacx_sizeof_metrics(void) { return (int)sizeof(sacx_metrics); }
+int sacx_sizeof_tensor_desc(void) { return (int)sizeof(sacx_tensor_desc); }
+
+int sacx_activation_id(const char* name) {
+  if (!name) return SACX_ERR_ACTIVATION;
+  static const char* names[] = {"identity", "relu", "tanh", "elu", "leaky_relu", "gelu", "selu"};
+  for (int i = 0; i < 7; ++i) if (strcmp(name, names[i]) == 0) return i;
+  return fail(SACX_ERR_ACTIVATION, std::string("unknown activation: ") + name);
+}
+
+// ---------------------------------------------------------------------------------------- ring API
+int64_t sacx_ring_bytes(int32_t O, int32_t A, int64_t cap, int32_t n_agents) {
+  i64 s, a, r, s2, d, total;
+  Ring::offsets(O, A, cap, s, a, r, s2, d, total);
+  return total * 4 * (int64_t)n_agents;
+}
+
+int sacx_ring_create(int32_t O, int32_t A, int64_t cap, int32_t n_agents, void* dev_mem, sacx_ring_t* out) {
+  if (!out || O <= 0 || A <= 0 || cap <= 0 || n_agents <= 0) return fail(SACX_ERR_INVALID, "ring_create: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SACX_ERR_CUDA, "no CUDA device: the replay ring is device-resident and has no CPU fallback");
+  }
+  sacx_ring_s* h = new sacx_ring_s();
+  Ring& r = h->r;
+  r.O = O; r.A = A; r.cap = cap; r.n_agents = n_agents; r.W = 2 * O + A + 2;
+  i64 total;
+  Ring::offsets(O, A, cap, r.off_s, r.off_a, r.off_r, r.off_s2, r.off_d, total);
+  r.stride = total;
+  r.pushes.assign(n_agents, 0);
+  r.stage_limit = (int)std::min<i64>(STAGE_ROWS, cap);
+  if (dev_mem) r.dev = (float*)dev_mem;
+  else {
+    SACX_CUDA(cudaMalloc((void**)&r.dev, (size_t)total * 4 * n_agents));
+    r.own = true;
+  }
+  for (int ag = 0; ag < n_agents; ++ag) SACX_CUDA(cudaMemset(r.block(ag), 0, sizeof(RingMeta)));
+  SACX_CUDA(cudaMallocHost((void**)&r.h_rows, (size_t)STAGE_ROWS * r.W * sizeof(float)));
+  SACX_CUDA(cudaMallocHost((void**)&r.h_hdr, (size_t)STAGE_ROWS * sizeof(StageHdr)));
+  SACX_CUDA(cudaMalloc((void**)&r.d_rows, (size_t)STAGE_ROWS * r.W * sizeof(float)));
+  SACX_CUDA(cudaMalloc((void**)&r.d_hdr, (size_t)STAGE_ROWS * sizeof(StageHdr)));
+  SACX_CUDA(cudaEventCreateWithFlags(&r.stage_free, cudaEventDisableTiming));
+  *out = h;
+  return SACX_OK;
+}
+
+int sacx_ring_destroy(sacx_ring_t h) {
+  if (!h) return SACX_OK;
+  Ring& r = h->r;
+  cudaStreamSynchronize(r.stream);
+  if (r.own && r.dev) cudaFree(r.dev);
+  if (r.h_rows) cudaFreeHost(r.h_rows);
+  if (r.h_hdr) cudaFreeHost(r.h_hdr);
+  if (r.d_rows) cudaFree(r.d_rows);
+  if (r.d_hdr) cudaFree(r.d_hdr);
+  if (r.scr_dev) cudaFree(r.scr_dev);
+  if (r.scr_host) cudaFreeHost(r.scr_host);
+  if (r.stage_free) cudaEventDestroy(r.stage_free);
+  delete h;
+  return SACX_OK;
+}
+
+int sacx_ring_set_stream(sacx_ring_t h, void* stream) {
+  if (!h) return fail(SACX_ERR_INVALID, "null ring");
+  int rc = h->r.flush();
+  if (rc) return rc;
+  h->r.stream = (cudaStream_t)stream;
+  return SACX_OK;
+}
+
+int sacx_ring_push_host(sacx_ring_t h, int32_t agent, const float* s, const float* a, float reward, const float* s2, float done) {
+  if (!h || !s || !a || !s2) return fail(SACX_ERR_INVALID, "ring_push: null pointer");
+  return h->r.push(agent, s, a, reward, s2, done);
+}
+
+int sacx_ring_push_n_host(sacx_ring_t h, int32_t agent, int64_t n, const float* s, const float* a, const float* reward,
+                          const float* s2, const float* done) {
+  if (!h || !s || !a || !s2 || !reward || !done || n < 0) return fail(SACX_ERR_INVALID, "ring_push_n: bad arguments");
+  Ring& r = h->r;
+  for (int64_t i = 0; i < n; ++i) {
+    int rc = r.push(agent, s + i * r.O, a + i * r.A, reward[i], s2 + i * r.O, done[i]);
+    if (rc) return rc;
+  }
+  return SACX_OK;
+}
+
+int sacx_ring_push_n_dev(sacx_ring_t h, int32_t agent, int64_t n, const float* s, const float* a, const float* reward,
+                         const float* s2, const float* done) {
+  if (!h || !s || !a || !s2 || !reward || !done || n < 0) return fail(SACX_ERR_INVALID, "ring_push_n_dev: bad arguments");
+  Ring& r = h->r;
+  if (agent < 0 || agent >= r.n_agents) return fail(SACX_ERR_INVALID, "ring push: agent out of range");
+  if (n > r.cap) return fail(SACX_ERR_INVALID, "ring_push_n_dev: n exceeds capacity");
+  if (n == 0) return SACX_OK;
+  int rc = r.flush();
+  if (rc) return rc;
+  ring_scatter_dev_kernel<<<(unsigned)((n + 7) / 8), 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2,
+                                                                         r.off_d, r.O, r.A, s, a, reward, s2, done, r.pushes[agent], (int)n);
+  ++r.launches;
+  SACX_CUDA(cudaGetLastError());
+  r.pushes[agent] += n;
+  return SACX_OK;
+}
+
+int sacx_ring_flush(sacx_ring_t h) { return h ? h->r.flush() : fail(SACX_ERR_INVALID, "null ring"); }
+int64_t sacx_ring_len(sacx_ring_t h, int32_t agent) { return (h && agent >= 0 && agent < h->r.n_agents) ? h->r.len(agent) : -1; }
+int64_t sacx_ring_pushes(sacx_ring_t h, int32_t agent) { return (h && agent >= 0 && agent < h->r.n_agents) ? h->r.pushes[agent] : -1; }
+
+int sacx_ring_gather(sacx_ring_t h, int32_t agent, const int64_t* idx_dev, int32_t B, float* s, float* a, float* rr, float* s2, float* d) {
+  if (!h || !idx_dev || B <= 0) return fail(SACX_ERR_INVALID, "ring_gather: bad arguments");
+  Ring& r = h->r;
+  if (agent < 0 || agent >= r.n_agents) return fail(SACX_ERR_INVALID, "ring_gather: agent out of range");
+  if (r.len(agent) < B)
+    return fail(SACX_ERR_UNDERFILLED, "Not enough samples in the replay buffer to sample " + std::to_string(B) +
+                                          " transitions. Current size: " + std::to_string(r.len(agent)));
+  int rc = r.flush();
+  if (rc) return rc;
+  ring_gather_kernel<<<(B + 7) / 8, 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2, r.off_d, r.O, r.A,
+                                                        (const i64*)idx_dev, B, s, a, rr, s2, d);
+  ++r.launches;
+  SACX_CUDA(cudaGetLastError());
+  return SACX_OK;
+}
+
+int sacx_ring_gather_host(sacx_ring_t h, int32_t agent, const int64_t* idx, int32_t B, float* s, float* a, float* rr, float* s2, float* d) {
+  if (!h || !idx || B <= 0) return fail(SACX_ERR_INVALID, "ring_gather_host: bad arguments");
+  Ring& r = h->r;
+  if (agent < 0 || agent >= r.n_agents) return fail(SACX_ERR_INVALID, "ring_gather: agent out of range");
+  const i64 n = r.len(agent);
+  if (n < B)
+    return fail(SACX_ERR_UNDERFILLED, "Not enough samples in the replay buffer to sample " + std::to_string(B) +
+                                          " transitions. Current size: " + std::to_string(n));
+  for (int i = 0; i < B; ++i)
+    if (idx[i] < 0 || idx[i] >= n) return fail(SACX_ERR_INVALID, "ring_gather_host: logical index out of range");
+  const size_t rowf = (size_t)r.W;
+  const size_t bytes = (size_t)B * (sizeof(i64) + rowf * sizeof(float));
+  int rc = r.ensure_scratch(bytes);
+  if (rc) return rc;
+  i64* d_idx = (i64*)r.scr_dev;
+  float* d_out = (float*)((char*)r.scr_dev + (size_t)B * sizeof(i64));
+  float* ds = d_out, *da = ds + (size_t)B * r.O, *dr = da + (size_t)B * r.A, *ds2 = dr + B, *dd = ds2 + (size_t)B * r.O;
+  memcpy(r.scr_host, idx, (size_t)B * sizeof(i64));
+  SACX_CUDA(cudaMemcpyAsync(d_idx, r.scr_host, (size_t)B * sizeof(i64), cudaMemcpyHostToDevice, r.stream));
+  rc = sacx_ring_gather(h, agent, (const int64_t*)d_idx, B, ds, da, dr, ds2, dd);
+  if (rc) return rc;
+  float* hout = (float*)((char*)r.scr_host + (size_t)B * sizeof(i64));
+  SACX_CUDA(cudaMemcpyAsync(hout, d_out, (size_t)B * rowf * sizeof(float), cudaMemcpyDeviceToHost, r.stream));
+  SACX_CUDA(cudaStreamSynchronize(r.stream));
+  const float* hs = hout, *ha = hs + (size_t)B * r.O, *hr = ha + (size_t)B * r.A, *hs2 = hr + B, *hd = hs2 + (size_t)B * r.O;
+  if (s) memcpy(s, hs, (size_t)B * r.O * 4);
+  if (a) memcpy(a, ha, (size_t)B * r.A * 4);
+  if (rr) memcpy(rr, hr, (size_t)B * 4);
+  if (s2) memcpy(s2, hs2, (size_t)B * r.O * 4);
+  if (d) memcpy(d, hd, (size_t)B * 4);
+  return SACX_OK;
+}
+
+int sacx_ring_sample_indices(sacx_ring_t h, int32_t agent, uint64_t seed, uint64_t counter, int32_t B, int64_t* out_dev) {
+  if (!h || !out_dev || B <= 0) return fail(SACX_ERR_INVALID, "ring_sample_indices: bad arguments");
+  Ring& r = h->r;
+  if (agent < 0 || agent >= r.n_agents) return fail(SACX_ERR_INVALID, "agent out of range");
+  if (r.len(agent) < B)
+    return fail(SACX_ERR_UNDERFILLED, "Not enough samples in the replay buffer to sample " + std::to_string(B) +
+                                          " transitions. Current size: " + std::to_string(r.len(agent)));
+  int rc = r.flush();
+  if (rc) return rc;
+  ring_indices_kernel<<<(B + 255) / 256, 256, 0, r.stream>>>(r.block(agent), r.cap, seed, counter, agent, B, (i64*)out_dev);
+  ++r.launches;
+  SACX_CUDA(cudaGetLastError());
+  return SACX_OK;
+}
+
+// ---------------------------------------------------------------------------------------- agent API
+int sacx_agent_arena_floats(const sacx_config* cfg, int64_t* out) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!out) return fail(SACX_ERR_INVALID, "null out");
+  Engine e;
+  e.cfg = *cfg;
+  e.build_layout();
+  *out = e.stride;
+  return SACX_OK;
+}
+
+int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* out) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!out) return fail(SACX_ERR_INVALID, "null out");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SACX_ERR_CUDA, "no CUDA device: the SAC update engine is CUDA-only (sm_100a) and has no CPU fallback");
+  }
+  sacx_agent_s* h = new sacx_agent_s();
+  Engine& e = h->e;
+  e.cfg = *cfg;
+  if (e.cfg.dp_world <= 0) { e.cfg.dp_world = 1; e.cfg.dp_rank = 0; }
+  int dev = 0;
+  SACX_CUDA(cudaGetDevice(&dev));
+  SACX_CUDA(cudaDeviceGetAttribute(&e.n_sms, cudaDevAttrMultiProcessorCount, dev));
+  const char* tile_env = getenv("SACX_TILE");
+  e.large = (cfg->n_agents > 1) || (cfg->batch_size >= 1024);
+  if (tile_env && !strcmp(tile_env, "small")) e.large = false;
+  if (tile_env && !strcmp(tile_env, "large")) e.large = true;
+  e.build_layout();
+  Hyper& hp = e.hp;
+  memset(&hp, 0, sizeof hp);
+  hp.gamma = (float)cfg->gamma; hp.tau = (float)cfg->tau; hp.one_minus_tau = (float)(1.0 - cfg->tau);
+  hp.log_std_min = cfg->log_std_min; hp.log_std_max = cfg->log_std_max; hp.action_scale = cfg->action_scale;
+  hp.lr[OPT_PI] = cfg->actor_lr; hp.lr[OPT_Q1] = hp.lr[OPT_Q2] = cfg->critic_lr;
+  hp.alpha_lr = cfg->alpha_lr; hp.alpha_init = cfg->alpha;
+  hp.target_entropy = -(float)cfg->act_dim;                 // agent.py:43
+  hp.auto_alpha = cfg->auto_entropy_tuning;
+  hp.obs = cfg->obs_dim; hp.act = cfg->act_dim; hp.B = cfg->batch_size;
+  hp.B_global = cfg->batch_size * e.cfg.dp_world; hp.row0_global = cfg->batch_size * e.cfg.dp_rank;
+  hp.seed = cfg->seed;
+  if ((rc = e.build_plans())) { delete h; return rc; }
+  // launch geometry: one CTA per SM; a single agent spreads over the chip, a population gets one CTA per agent
+  const size_t gemm_floats = e.large ? CfgLarge::SMEM_FLOATS : CfgSmall::SMEM_FLOATS;
+  e.smem_bytes = (int)(SMEM_OPS * sizeof(Op) + WSM_FLOATS * 4 + gemm_floats * 4);
+  const void* fn = e.large ? (const void*)sacx_run_kernel<true> : (const void*)sacx_run_kernel<false>;
+  SACX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e.smem_bytes));
+  int per_sm = 0;
+  if (e.large) SACX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sacx_run_kernel<true>, 256, e.smem_bytes));
+  else SACX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sacx_run_kernel<false>, 256, e.smem_bytes));
+  if (per_sm < 1) { delete h; return fail(SACX_ERR_CUDA, "update kernel does not fit on an SM"); }
+  e.max_ctas = e.n_sms;                                      // one CTA per SM (persistent)
+  if (cfg->n_agents == 1) {
+    e.grid_x = cfg->ctas_per_agent > 0 ? cfg->ctas_per_agent : std::min(e.max_ctas, e.max_phase_tiles());
+    e.grid_x = std::max(1, std::min(e.grid_x, e.max_ctas));
+    e.grid_y = 1;
+  } else {
+    e.grid_x = std::max(1, std::min(cfg->ctas_per_agent > 0 ? cfg->ctas_per_agent : 1, e.max_ctas));
+    e.grid_y = std::max(1, std::min(cfg->n_agents, e.max_ctas / e.grid_x));
+  }
+  const size_t total = (size_t)e.stride * 4 * cfg->n_agents;
+  if (arena_dev) e.arena = arena_dev;
+  else {
+    SACX_CUDA(cudaMalloc((void**)&e.arena, total));
+    SACX_CUDA(cudaMemset(e.arena, 0, total));
+    e.own_arena = true;
+  }
+  SACX_CUDA(cudaMalloc((void**)&e.d_plans, sizeof(Plan) * N_PLANS));
+  SACX_CUDA(cudaMemcpy(e.d_plans, e.h_plans.data(), sizeof(Plan) * N_PLANS, cudaMemcpyHostToDevice));
+  SACX_CUDA(cudaMalloc((void**)&e.d_barrier, sizeof(unsigned) * 65536));
+  SACX_CUDA(cudaMemset(e.d_barrier, 0, sizeof(unsigned) * 65536));
+  SACX_CUDA(cudaMallocHost((void**)&e.pinned_metrics, sizeof(sacx_metrics)));
+  if ((rc = engine_init_scalars(&e))) { delete h; return rc; }
+  *out = h;
+  return SACX_OK;
+}
+
+int sacx_agent_destroy(sacx_agent_t h) {
+  if (!h) return SACX_OK;
+  Engine& e = h->e;
+  cudaStreamSynchronize(e.stream);
+  if (e.own_arena && e.arena) cudaFree(e.arena);
+  if (e.d_plans) cudaFree(e.d_plans);
+  if (e.d_barrier) cudaFree(e.d_barrier);
+  if (e.pinned_metrics) cudaFreeHost(e.pinned_metrics);
+  if (e.pinned_io) cudaFreeHost(e.pinned_io);
+  if (e.dev_io) cudaFree(e.dev_io);
+  delete h;
+  return SACX_OK;
+}
+
+int sacx_agent_set_stream(sacx_agent_t h, void* stream) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  h->e.stream = (cudaStream_t)stream;
+  return SACX_OK;
+}
+int sacx_agent_attach_ring(sacx_agent_t h, sacx_ring_t r) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  if (r) {
+    if (r->r.O != h->e.cfg.obs_dim || r->r.A != h->e.cfg.act_dim) return fail(SACX_ERR_INVALID, "ring/agent dimension mismatch");
+    if (r->r.n_agents != h->e.cfg.n_agents) return fail(SACX_ERR_INVALID, "ring/agent population mismatch");
+  }
+  h->e.ring = r ? &r->r : nullptr;
+  return SACX_OK;
+}
+float* sacx_agent_arena(sacx_agent_t h) { return h ? h->e.arena : nullptr; }
+int64_t sacx_agent_stride(sacx_agent_t h) { return h ? h->e.stride : 0; }
+
+int sacx_agent_layout(sacx_agent_t h, sacx_tensor_desc* out, int32_t capacity, int32_t* n_out) {
+  if (!h || !n_out) return fail(SACX_ERR_INVALID, "layout: bad arguments");
+  const auto& lay = h->e.lay;
+  *n_out = (int32_t)lay.size();
+  if (out) for (int i = 0; i < (int)lay.size() && i < capacity; ++i) out[i] = lay[i];
+  return SACX_OK;
+}
+
+int sacx_agent_grid(sacx_agent_t h, int32_t* gx, int32_t* gy, int32_t* smem) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  if (gx) *gx = h->e.grid_x;
+  if (gy) *gy = h->e.grid_y;
+  if (smem) *smem = h->e.smem_bytes;
+  return SACX_OK;
+}
+
+int sacx_agent_reset_state(sacx_agent_t h) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  Engine& e = h->e;
+  for (int ag = 0; ag < e.cfg.n_agents; ++ag) {
+    float* base = e.arena + (i64)ag * e.stride;
+    SACX_CUDA(cudaMemcpyAsync(base + e.T0, base + e.q1.begin, (size_t)e.n_critic * 4, cudaMemcpyDeviceToDevice, e.stream));
+    SACX_CUDA(cudaMemsetAsync(base + e.P0 + e.blk, 0, (size_t)e.blk * 3 * 4, e.stream));
+  }
+  return engine_init_scalars(&e);
+}
+
+int sacx_agent_refresh_alpha(sacx_agent_t h) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  Engine& e = h->e;
+  SACX_CUDA(cudaStreamSynchronize(e.stream));
+  for (int ag = 0; ag < e.cfg.n_agents; ++ag) {
+    AgentScalars s;
+    float* p = e.arena + (i64)ag * e.stride + e.scal_off;
+    SACX_CUDA(cudaMemcpy(&s, p, sizeof s, cudaMemcpyDeviceToHost));
+    if (e.cfg.auto_entropy_tuning) s.alpha = std::exp(s.log_alpha);
+    s.alpha_f32 = (float)s.alpha;
+    s.metrics[4] = (float)s.alpha; s.metrics[5] = (float)s.log_alpha;
+    SACX_CUDA(cudaMemcpy(p, &s, sizeof s, cudaMemcpyHostToDevice));
+  }
+  return SACX_OK;
+}
+
+static int need_ring(Engine& e, bool device_sampling) {
+  if (!e.ring) return fail(SACX_ERR_INVALID, "no replay ring attached to the agent");
+  for (int ag = 0; ag < e.cfg.n_agents; ++ag)
+    if (e.ring->len(ag) < (i64)e.cfg.batch_size * (device_sampling ? e.cfg.dp_world : 1))
+      return fail(SACX_ERR_UNDERFILLED, "Not enough samples in the replay buffer to sample " + std::to_string(e.cfg.batch_size) +
+                                            " transitions. Current size: " + std::to_string(e.ring->len(ag)));
+  int rc = e.ring->flush();
+  if (rc) return rc;
+  if (e.ring->stream != e.stream) {   // order the ring's writes before the update
+    SACX_CUDA(cudaStreamSynchronize(e.ring->stream));
+  }
+  return SACX_OK;
+}
+
+static int do_update(sacx_agent_t h, const int64_t* idx, const float* e1, const float* e2, int n_steps, bool staged) {
+  if (!h || n_steps <= 0) return fail(SACX_ERR_INVALID, "update: bad arguments");
+  Engine& e = h->e;
+  int rc = need_ring(e, idx == nullptr);
+  if (rc) return rc;
+  RunArgs a;
+  memset(&a, 0, sizeof a);
+  a.idx_ext = (const i64*)idx; a.eps1_ext = e1; a.eps2_ext = e2;
+  return engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, staged);
+}
+
+int sacx_update(sacx_agent_t h, const int64_t* idx, const float* e1, const float* e2, int32_t n_steps) {
+  return do_update(h, idx, e1, e2, n_steps, false);
+}
+int sacx_update_staged(sacx_agent_t h, const int64_t* idx, const float* e1, const float* e2, int32_t n_steps) {
+  return do_update(h, idx, e1, e2, n_steps, true);
+}
+
+static int read_metrics(Engine& e, int agent, sacx_metrics* out) {
+  AgentScalars s;
+  SACX_CUDA(cudaMemcpyAsync(e.pinned_io ? e.pinned_io : (void*)&s, e.arena + (i64)agent * e.stride + e.scal_off, sizeof s,
+                            cudaMemcpyDeviceToHost, e.stream));
+  SACX_CUDA(cudaStreamSynchronize(e.stream));
+  if (e.pinned_io) memcpy(&s, e.pinned_io, sizeof s);
+  out->q1_loss = s.metrics[0]; out->q2_loss = s.metrics[1]; out->policy_loss = s.metrics[2]; out->alpha_loss = s.metrics[3];
+  out->alpha = s.metrics[4]; out->log_alpha = s.metrics[5]; out->q1_mean = s.metrics[6]; out->q2_mean = s.metrics[7];
+  out->logpi_mean = s.metrics[8]; out->y_mean = s.metrics[9];
+  out->nonfinite = s.nonfinite; out->reserved = 0; out->updates = s.updates;
+  return SACX_OK;
+}
+
+static int ensure_io(Engine& e, size_t bytes) {
+  bytes = std::max(bytes, sizeof(AgentScalars));
+  if (bytes > e.pinned_io_bytes) {
+    if (e.pinned_io) cudaFreeHost(e.pinned_io);
+    if (e.dev_io) cudaFree(e.dev_io);
+    e.pinned_io = e.dev_io = nullptr;
+    e.pinned_io_bytes = e.dev_io_bytes = 0;
+    SACX_CUDA(cudaMallocHost(&e.pinned_io, bytes));
+    SACX_CUDA(cudaMalloc(&e.dev_io, bytes));
+    e.pinned_io_bytes = e.dev_io_bytes = bytes;
+  }
+  return SACX_OK;
+}
+
+int sacx_update_host(sacx_agent_t h, const int64_t* idx, const float* e1, const float* e2, int32_t n_steps, sacx_metrics* m) {
+  if (!h || n_steps <= 0) return fail(SACX_ERR_INVALID, "update_host: bad arguments");
+  Engine& e = h->e;
+  const size_t nb = (size_t)n_steps * e.cfg.n_agents * e.cfg.batch_size;
+  const size_t b_idx = idx ? nb * sizeof(i64) : 0;
+  const size_t b_eps = nb * e.cfg.act_dim * sizeof(float);
+  const size_t total = b_idx + (e1 ? b_eps : 0) + (e2 ? b_eps : 0);
+  int rc = ensure_io(e, total + 256);
+  if (rc) return rc;
+  char* hp = (char*)e.pinned_io;
+  char* dp = (char*)e.dev_io;
+  size_t off = 0;
+  const i64* d_idx = nullptr; const float* d_e1 = nullptr; const float* d_e2 = nullptr;
+  if (idx) { memcpy(hp + off, idx, b_idx); d_idx = (const i64*)(dp + off); off += b_idx; }
+  if (e1) { memcpy(hp + off, e1, b_eps); d_e1 = (const float*)(dp + off); off += b_eps; }
+  if (e2) { memcpy(hp + off, e2, b_eps); d_e2 = (const float*)(dp + off); off += b_eps; }
+  if (off) SACX_CUDA(cudaMemcpyAsync(dp, hp, off, cudaMemcpyHostToDevice, e.stream));
+  rc = do_update(h, (const int64_t*)d_idx, d_e1, d_e2, n_steps, false);
+  if (rc) return rc;
+  if (m) return read_metrics(e, 0, m);
+  SACX_CUDA(cudaStreamSynchronize(e.stream));
+  return SACX_OK;
+}
+
+int sacx_sample_batch(sacx_agent_t h, const int64_t* idx) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  int rc = need_ring(h->e, idx == nullptr);
+  if (rc) return rc;
+  RunArgs a; memset(&a, 0, sizeof a);
+  a.idx_ext = (const i64*)idx;
+  return engine_launch(&h->e, PLAN_SAMPLE, 0, -1, 1, a, false);
+}
+
+int sacx_load_batch(sacx_agent_t h, const float* s, const float* a_, const float* r, const float* s2, const float* d) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  Engine& e = h->e;
+  const int B = e.cfg.batch_size;
+  load_batch_kernel<<<(B + 7) / 8, 256, 0, e.stream>>>(e.arena, e.x_sa, e.x_s2, e.x_pi, e.b_r, e.b_d, e.ldx, e.cfg.obs_dim,
+                                                       e.cfg.act_dim, B, s, a_, r, s2, d);
+  ++e.launches;
+  SACX_CUDA(cudaGetLastError());
+  return SACX_OK;
+}
+
+static int copy_out(Engine& e, i64 off, float* dst, int n) {
+  if (!dst) return SACX_OK;
+  SACX_CUDA(cudaMemcpyAsync(dst, e.arena + off, (size_t)n * 4, cudaMemcpyDeviceToDevice, e.stream));
+  return SACX_OK;
+}
+
+int sacx_target(sacx_agent_t h, const float* eps1, float* y_out) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  RunArgs a; memset(&a, 0, sizeof a);
+  a.eps1_ext = eps1;
+  int rc = engine_launch(&h->e, PLAN_TARGET, 0, -1, 1, a, false);
+  if (rc) return rc;
+  return copy_out(h->e, h->e.b_y, y_out, h->e.cfg.batch_size);
+}
+
+static int critic_run(sacx_agent_t h, const float* y, int plan) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  RunArgs a; memset(&a, 0, sizeof a);
+  a.y_ext = y;
+  return engine_launch(&h->e, plan, 0, -1, 1, a, false);
+}
+int sacx_critic_step(sacx_agent_t h, const float* y) { return critic_run(h, y, PLAN_CRITIC); }
+int sacx_critic_grads(sacx_agent_t h, const float* y) { return critic_run(h, y, PLAN_CRITIC_GRADS); }
+
+static int actor_run(sacx_agent_t h, const float* eps2, float* lp_out, int plan) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  RunArgs a; memset(&a, 0, sizeof a);
+  a.eps2_ext = eps2;
+  int rc = engine_launch(&h->e, plan, 0, -1, 1, a, false);
+  if (rc) return rc;
+  return copy_out(h->e, h->e.b_lp, lp_out, h->e.cfg.batch_size);
+}
+int sacx_actor_step(sacx_agent_t h, const float* eps2, float* lp_out) { return actor_run(h, eps2, lp_out, PLAN_ACTOR); }
+int sacx_actor_grads(sacx_agent_t h, const float* eps2, float* lp_out) { return actor_run(h, eps2, lp_out, PLAN_ACTOR_GRADS); }
+
+int sacx_alpha_step(sacx_agent_t h, const float* logpi, sacx_metrics* m) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  RunArgs a; memset(&a, 0, sizeof a);
+  a.lp_ext = logpi;
+  int rc = engine_launch(&h->e, PLAN_ALPHA, 0, -1, 1, a, false);
+  if (rc) return rc;
+  if (m) { rc = ensure_io(h->e, 0); if (rc) return rc; return read_metrics(h->e, 0, m); }
+  return SACX_OK;
+}
+
+int sacx_polyak(sacx_agent_t h) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  RunArgs a; memset(&a, 0, sizeof a);
+  return engine_launch(&h->e, PLAN_POLYAK, 0, -1, 1, a, false);
+}
+
+int sacx_apply_grads(sacx_agent_t h, int32_t which, int32_t polyak) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  RunArgs a; memset(&a, 0, sizeof a);
+  int rc = SACX_OK;
+  if (which & 1) rc = engine_launch(&h->e, polyak ? PLAN_APPLY_Q_POLYAK : PLAN_APPLY_Q, 0, -1, 1, a, false);
+  if (!rc && (which & 2)) rc = engine_launch(&h->e, PLAN_APPLY_PI, 0, -1, 1, a, false);
+  if (!rc && (which & 4)) rc = engine_launch(&h->e, PLAN_ALPHA, 0, -1, 1, a, false);
+  return rc;
+}
+
+static NetRef make_ref(const NetLayout& n, i64 shift) {
+  NetRef r;
+  memset(&r, 0, sizeof r);
+  r.n_lin = n.n_lin; r.in_dim = n.dims[0]; r.out_dim = n.dims[n.n_lin]; r.act_h = n.act_h; r.act_o = n.act_o;
+  for (int l = 0; l <= n.n_lin; ++l) r.dims[l] = n.dims[l];
+  for (int l = 0; l < n.n_lin; ++l) { r.W[l] = n.W[l] + shift; r.b[l] = n.b[l] + shift; }
+  return r;
+}
+static int max_width(const NetLayout& n) {
+  int m = 0;
+  for (int l = 0; l <= n.n_lin; ++l) m = std::max(m, n.dims[l]);
+  return m;
+}
+
+int sacx_act(sacx_agent_t h, int32_t agent, const float* s, int32_t n, const float* eps, int32_t deterministic, float* a_out) {
+  if (!h || !s || !a_out || n <= 0) return fail(SACX_ERR_INVALID, "act: bad arguments");
+  Engine& e = h->e;
+  if (agent < 0 || agent >= e.cfg.n_agents) return fail(SACX_ERR_INVALID, "act: agent out of range");
+  const int mw = max_width(e.pi);
+  act_kernel<<<n, 256, (size_t)2 * mw * 4, e.stream>>>(e.arena + (i64)agent * e.stride, make_ref(e.pi, 0), mw, s, eps, deterministic,
+                                                      a_out, e.cfg.act_dim, e.hp.log_std_min, e.hp.log_std_max, e.hp.action_scale,
+                                                      e.hp.seed, e.act_calls++, agent);
+  ++e.launches;
+  SACX_CUDA(cudaGetLastError());
+  return SACX_OK;
+}
+
+int sacx_act_host(sacx_agent_t h, int32_t agent, const float* s, int32_t n, const float* eps, int32_t deterministic, float* a_out) {
+  if (!h || !s || !a_out || n <= 0) return fail(SACX_ERR_INVALID, "act_host: bad arguments");
+  Engine& e = h->e;
+  const size_t bs = (size_t)n * e.cfg.obs_dim * 4, be = eps ? (size_t)n * e.cfg.act_dim * 4 : 0, ba = (size_t)n * e.cfg.act_dim * 4;
+  int rc = ensure_io(e, bs + be + ba);
+  if (rc) return rc;
+  char* hp = (char*)e.pinned_io; char* dp = (char*)e.dev_io;
+  memcpy(hp, s, bs);
+  if (eps) memcpy(hp + bs, eps, be);
+  SACX_CUDA(cudaMemcpyAsync(dp, hp, bs + be, cudaMemcpyHostToDevice, e.stream));
+  rc = sacx_act(h, agent, (const float*)dp, n, eps ? (const float*)(dp + bs) : nullptr, deterministic, (float*)(dp + bs + be));
+  if (rc) return rc;
+  SACX_CUDA(cudaMemcpyAsync(hp + bs + be, dp + bs + be, ba, cudaMemcpyDeviceToHost, e.stream));
+  SACX_CUDA(cudaStreamSynchronize(e.stream));
+  memcpy(a_out, hp + bs + be, ba);
+  return SACX_OK;
+}
+
+int sacx_q_values(sacx_agent_t h, int32_t agent, const float* s, const float* a_, int32_t n, float* q1o, float* q2o) {
+  if (!h || !s || !a_ || !q1o || !q2o || n <= 0) return fail(SACX_ERR_INVALID, "q_values: bad arguments");
+  Engine& e = h->e;
+  if (agent < 0 || agent >= e.cfg.n_agents) return fail(SACX_ERR_INVALID, "q_values: agent out of range");
+  const int mw = max_width(e.q1);
+  qvalue_kernel<<<dim3(n, 2), 256, (size_t)2 * mw * 4, e.stream>>>(e.arena + (i64)agent * e.stride, make_ref(e.q1, 0), make_ref(e.q2, 0),
+                                                                  mw, e.cfg.obs_dim, e.cfg.act_dim, s, a_, q1o, q2o);
+  ++e.launches;
+  SACX_CUDA(cudaGetLastError());
+  return SACX_OK;
+}
+
+int sacx_q_values_host(sacx_agent_t h, int32_t agent, const float* s, const float* a_, int32_t n, float* q1o, float* q2o) {
+  if (!h || !s || !a_ || !q1o || !q2o || n <= 0) return fail(SACX_ERR_INVALID, "q_values_host: bad arguments");
+  Engine& e = h->e;
+  const size_t bs = (size_t)n * e.cfg.obs_dim * 4, ba = (size_t)n * e.cfg.act_dim * 4, bq = (size_t)n * 4;
+  int rc = ensure_io(e, bs + ba + 2 * bq);
+  if (rc) return rc;
+  char* hp = (char*)e.pinned_io; char* dp = (char*)e.dev_io;
+  memcpy(hp, s, bs);
+  memcpy(hp + bs, a_, ba);
+  SACX_CUDA(cudaMemcpyAsync(dp, hp, bs + ba, cudaMemcpyHostToDevice, e.stream));
+  rc = sacx_q_values(h, agent, (const float*)dp, (const float*)(dp + bs), n, (float*)(dp + bs + ba), (float*)(dp + bs + ba + bq));
+  if (rc) return rc;
+  SACX_CUDA(cudaMemcpyAsync(hp + bs + ba, dp + bs + ba, 2 * bq, cudaMemcpyDeviceToHost, e.stream));
+  SACX_CUDA(cudaStreamSynchronize(e.stream));
+  memcpy(q1o, hp + bs + ba, bq);
+  memcpy(q2o, hp + bs + ba + bq, bq);
+  return SACX_OK;
+}
+
+int sacx_get_metrics(sacx_agent_t h, int32_t agent, sacx_metrics* m) {
+  if (!h || !m) return fail(SACX_ERR_INVALID, "get_metrics: bad arguments");
+  if (agent < 0 || agent >= h->e.cfg.n_agents) return fail(SACX_ERR_INVALID, "agent out of range");
+  int rc = ensure_io(h->e, 0);
+  if (rc) return rc;
+  return read_metrics(h->e, agent, m);
+}
+
+int sacx_sync(sacx_agent_t h) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  SACX_CUDA(cudaStreamSynchronize(h->e.stream));
+  return SACX_OK;
+}
+
+int64_t sacx_launch_count(sacx_agent_t h) { return h ? h->e.launches + (h->e.ring ? h->e.ring->launches : 0) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,543 @@
+// Host side of the engine: arena layout, plan (op table) construction, launches.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sacx_kernels.cuh"
+
+namespace sacx {
+
+extern thread_local std::string g_err;
+int fail(int code, const std::string& msg);
+#define SACX_CUDA(call)                                                                        \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(SACX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+
+inline i64 align4(i64 x) { return (x + 3) & ~(i64)3; }
+inline int rup4(int x) { return (x + 3) & ~3; }
+
+struct NetLayout {
+  int n_lin = 0, act_h = 0, act_o = 0;
+  int dims[SACX_MAX_HIDDEN + 2] = {0};
+  i64 W[SACX_MAX_HIDDEN + 1], b[SACX_MAX_HIDDEN + 1];
+  i64 begin = 0, end = 0;
+  int L() const { return n_lin - 1; }                 // hidden layers
+};
+
+struct ActSet {                                         // hidden activations of one forward pass
+  i64 h[SACX_MAX_HIDDEN], z[SACX_MAX_HIDDEN];
+  int ld[SACX_MAX_HIDDEN];
+  i64 aux(int l) const { return z[l] >= 0 ? z[l] : h[l]; }
+};
+
+enum PlanId { PLAN_FUSED = 0, PLAN_SAMPLE, PLAN_TARGET, PLAN_CRITIC, PLAN_CRITIC_GRADS, PLAN_ACTOR, PLAN_ACTOR_GRADS,
+              PLAN_ALPHA, PLAN_POLYAK, PLAN_APPLY_Q, PLAN_APPLY_Q_POLYAK, PLAN_APPLY_PI, PLAN_FUSED_NOGATHER, N_PLANS };
+
+struct Ring;
+
+struct Engine {
+  sacx_config cfg;
+  int n_sms = 0, max_ctas = 0;
+  bool large = false;
+  int grid_x = 1, grid_y = 1, smem_bytes = 0;
+  std::vector<sacx_tensor_desc> lay;
+  i64 cur = 0, stride = 0;
+  NetLayout pi, q1, q2;
+  i64 P0 = 0, blk = 0, T0 = 0, scal_off = 0;
+  i64 n_online = 0, n_critic = 0;
+  // batch / scratch
+  int ldx = 0;
+  i64 x_sa, x_s2, x_pi, b_r, b_d, b_idx, b_eps1, b_eps2, b_lp2, b_lp, b_y, b_tq[2], b_q[2], b_qa[2], b_dout[2], b_loss[2],
+      b_ploss, b_tz, b_se, b_mask, b_headz, b_dhead;
+  ActSet a_pit, a_pia, a_q[2], a_qt[2];
+  i64 d_q[2][SACX_MAX_HIDDEN], d_p[SACX_MAX_HIDDEN];
+  float* arena = nullptr;
+  bool own_arena = false;
+  Plan* d_plans = nullptr;
+  std::vector<Plan> h_plans;
+  unsigned* d_barrier = nullptr;
+  sacx_metrics* pinned_metrics = nullptr;
+  void* pinned_io = nullptr;
+  size_t pinned_io_bytes = 0;
+  void* dev_io = nullptr;
+  size_t dev_io_bytes = 0;
+  cudaStream_t stream = 0;
+  Ring* ring = nullptr;
+  long long launches = 0;
+  unsigned long long act_calls = 0;
+  Hyper hp;
+
+  // ---------------------------------------------------------------- layout
+  i64 alloc(const std::string& name, int rows, int cols, int ld = -1, int dtype = 0) {
+    if (ld < 0) ld = cols;
+    cur = align4(cur);
+    sacx_tensor_desc d;
+    memset(&d, 0, sizeof d);
+    snprintf(d.name, sizeof d.name, "%s", name.c_str());
+    d.offset = cur; d.rows = rows; d.cols = cols; d.ld = ld; d.dtype = dtype;
+    lay.push_back(d);
+    cur += (i64)rows * ld * (dtype == 0 ? 1 : 2);
+    return d.offset;
+  }
+
+  void layout_net(NetLayout& n, const std::string& tag, int in, const int32_t* hidden, int nh, int out, int act_h, int act_o) {
+    n.n_lin = nh + 1; n.act_h = act_h; n.act_o = act_o;
+    n.dims[0] = in;
+    for (int i = 0; i < nh; ++i) n.dims[i + 1] = hidden[i];
+    n.dims[nh + 1] = out;
+    cur = align4(cur);
+    n.begin = cur;
+    for (int l = 0; l < n.n_lin; ++l) {
+      n.W[l] = alloc(tag + ".W" + std::to_string(l), n.dims[l + 1], n.dims[l]);
+      n.b[l] = alloc(tag + ".b" + std::to_string(l), 1, n.dims[l + 1]);
+    }
+    n.end = align4(cur);
+    cur = n.end;
+  }
+
+  void alias_block(const std::string& prefix, i64 shift, const NetLayout& n, const std::string& tag) {
+    for (int l = 0; l < n.n_lin; ++l) {
+      for (int wb = 0; wb < 2; ++wb) {
+        sacx_tensor_desc d;
+        memset(&d, 0, sizeof d);
+        snprintf(d.name, sizeof d.name, "%s%s.%c%d", prefix.c_str(), tag.c_str(), wb ? 'b' : 'W', l);
+        d.offset = (wb ? n.b[l] : n.W[l]) + shift;
+        d.rows = wb ? 1 : n.dims[l + 1];
+        d.cols = wb ? n.dims[l + 1] : n.dims[l];
+        d.ld = d.cols;
+        lay.push_back(d);
+      }
+    }
+  }
+
+  void alloc_actset(ActSet& s, const std::string& tag, const NetLayout& n, bool save_z) {
+    const int B = cfg.batch_size;
+    for (int l = 0; l < SACX_MAX_HIDDEN; ++l) { s.h[l] = s.z[l] = -1; s.ld[l] = 0; }
+    for (int l = 0; l < n.L(); ++l) {
+      s.ld[l] = rup4(n.dims[l + 1]);
+      s.h[l] = alloc(tag + ".h" + std::to_string(l), B, n.dims[l + 1], s.ld[l]);
+      if (save_z && act_needs_z(n.act_h)) s.z[l] = alloc(tag + ".z" + std::to_string(l), B, n.dims[l + 1], s.ld[l]);
+    }
+  }
+
+  void build_layout() {
+    const int O = cfg.obs_dim, A = cfg.act_dim, B = cfg.batch_size;
+    cur = 0;
+    scal_off = alloc("scalars", 1, (int)((sizeof(AgentScalars) + 3) / 4));
+    {  // named views of the scalar block (offsetof keeps the Python side in step with the struct)
+      auto sub = [&](const char* name, size_t byte_off, int count, int dtype) {
+        sacx_tensor_desc d; memset(&d, 0, sizeof d);
+        snprintf(d.name, sizeof d.name, "%s", name);
+        d.offset = scal_off + (i64)(byte_off / 4); d.rows = 1; d.cols = d.ld = count; d.dtype = dtype;
+        lay.push_back(d);
+      };
+      sub("scal.log_alpha", offsetof(AgentScalars, log_alpha), 1, 1);
+      sub("scal.alpha_m", offsetof(AgentScalars, alpha_m), 1, 1);
+      sub("scal.alpha_v", offsetof(AgentScalars, alpha_v), 1, 1);
+      sub("scal.alpha", offsetof(AgentScalars, alpha), 1, 1);
+      sub("scal.step", offsetof(AgentScalars, step), N_OPT, 2);
+      sub("scal.updates", offsetof(AgentScalars, updates), 1, 2);
+      sub("scal.alpha_f32", offsetof(AgentScalars, alpha_f32), 1, 0);
+      sub("scal.metrics", offsetof(AgentScalars, metrics), 12, 0);
+      sub("scal.nonfinite", offsetof(AgentScalars, nonfinite), 1, 0);
+    }
+    cur = align4(cur);
+    P0 = cur;
+    layout_net(pi, "pi", O, cfg.hidden_pi, cfg.n_hidden_pi, 2 * A, cfg.act_hidden_pi, cfg.act_out_pi);
+    layout_net(q1, "q1", O + A, cfg.hidden_q, cfg.n_hidden_q, 1, cfg.act_hidden_q, cfg.act_out_q);
+    layout_net(q2, "q2", O + A, cfg.hidden_q, cfg.n_hidden_q, 1, cfg.act_hidden_q, cfg.act_out_q);
+    blk = align4(cur - P0);
+    n_online = cur - P0;
+    n_critic = q2.end - q1.begin;
+    { sacx_tensor_desc d; memset(&d, 0, sizeof d); snprintf(d.name, sizeof d.name, "block.params"); d.offset = P0; d.rows = 1; d.cols = d.ld = (int)n_online; lay.push_back(d); }
+    const char* pre[3] = {"m.", "v.", "g."};
+    for (int k = 0; k < 3; ++k) {
+      const i64 shift = blk * (k + 1);
+      alias_block(pre[k], shift, pi, "pi");
+      alias_block(pre[k], shift, q1, "q1");
+      alias_block(pre[k], shift, q2, "q2");
+      sacx_tensor_desc d; memset(&d, 0, sizeof d);
+      snprintf(d.name, sizeof d.name, "block.%c", pre[k][0]); d.offset = P0 + shift; d.rows = 1; d.cols = d.ld = (int)n_online; lay.push_back(d);
+    }
+    cur = P0 + 4 * blk;
+    T0 = align4(cur);
+    alias_block("", T0 - q1.begin, q1, "q1t");
+    alias_block("", T0 - q1.begin, q2, "q2t");
+    { sacx_tensor_desc d; memset(&d, 0, sizeof d); snprintf(d.name, sizeof d.name, "block.targets"); d.offset = T0; d.rows = 1; d.cols = d.ld = (int)n_critic; lay.push_back(d); }
+    cur = T0 + align4(n_critic);
+    // batch buffers
+    ldx = rup4(O + A);
+    x_sa = alloc("batch.sa", B, O + A, ldx);
+    x_s2 = alloc("batch.s2a", B, O + A, ldx);
+    x_pi = alloc("batch.spi", B, O + A, ldx);
+    b_r = alloc("batch.r", 1, B);
+    b_d = alloc("batch.d", 1, B);
+    b_idx = alloc("batch.idx", 1, B, B, 2);
+    b_eps1 = alloc("batch.eps1", B, A);
+    b_eps2 = alloc("batch.eps2", B, A);
+    b_lp2 = alloc("out.logpi_next", 1, B);
+    b_lp = alloc("out.logpi", 1, B);
+    b_y = alloc("out.y", 1, B);
+    for (int c = 0; c < 2; ++c) {
+      const std::string s = std::to_string(c + 1);
+      b_tq[c] = alloc("out.tq" + s, 1, B);
+      b_q[c] = alloc("out.q" + s, 1, B);
+      b_qa[c] = alloc("out.q" + s + "_pi", 1, B);
+      b_dout[c] = alloc("scr.dout" + s, 1, B);
+      b_loss[c] = alloc("scr.lossrow" + s, 1, B);
+    }
+    b_ploss = alloc("scr.plossrow", 1, B);
+    b_tz = alloc("scr.tz", B, A);
+    b_se = alloc("scr.se", B, A);
+    b_mask = alloc("scr.mask", B, A);
+    b_headz = alloc("scr.headz", B, 2 * A);
+    b_dhead = alloc("scr.dhead", B, 2 * A);
+    alloc_actset(a_pit, "act.pit", pi, false);
+    alloc_actset(a_pia, "act.pia", pi, true);
+    for (int c = 0; c < 2; ++c) {
+      alloc_actset(a_q[c], "act.q" + std::to_string(c + 1), c ? q2 : q1, true);
+      alloc_actset(a_qt[c], "act.qt" + std::to_string(c + 1), c ? q2 : q1, false);
+      for (int l = 0; l < q1.L(); ++l)
+        d_q[c][l] = alloc("delta.q" + std::to_string(c + 1) + "." + std::to_string(l), B, q1.dims[l + 1], rup4(q1.dims[l + 1]));
+    }
+    for (int l = 0; l < pi.L(); ++l) d_p[l] = alloc("delta.pi." + std::to_string(l), B, pi.dims[l + 1], rup4(pi.dims[l + 1]));
+    stride = (align4(cur) + 127) & ~(i64)127;   // 512-byte aligned agent blocks
+  }
+
+  // ---------------------------------------------------------------- op constructors
+  static Op blank(int type) {
+    Op o;
+    memset(&o, 0, sizeof o);
+    o.type = type;
+    o.a = o.b = o.c = o.bias = o.aux = o.zout = -1;
+    o.p = o.pm = o.pv = o.pt = o.pg = o.pb = o.pbm = o.pbv = o.pbt = o.pbg = -1;
+    for (auto& x : o.o) x = -1;
+    return o;
+  }
+  int BMt() const { return large ? CfgLarge::BM : CfgSmall::BM; }
+  int BNt() const { return large ? CfgLarge::BN : CfgSmall::BN; }
+  void finish_gemm(Op& o) const {
+    const int tm = (o.M + BMt() - 1) / BMt();
+    o.tiles_n = (o.N + BNt() - 1) / BNt();
+    o.ntiles = tm * o.tiles_n;
+    o.cfg = large ? 1 : 0;
+    const bool a_ck = (o.a_sk == 1), b_ck = (o.b_sk == 1);
+    const int ao = a_ck ? o.a_sm : o.a_sk, bo = b_ck ? o.b_sn : o.b_sk;
+    o.a_vec = (o.a % 4 == 0) && (ao % 4 == 0 || (a_ck && o.M == 1));
+    o.b_vec = (o.b % 4 == 0) && (bo % 4 == 0 || (b_ck && o.N == 1));
+  }
+  Op gemm_fwd(const NetLayout& n, int l, i64 wshift, i64 x, int ld_x, const ActSet& as) const {
+    Op o = blank(OP_GEMM);
+    o.epi = EPI_FWD; o.act = n.act_h;
+    o.M = cfg.batch_size; o.N = n.dims[l + 1]; o.K = n.dims[l];
+    o.a = x; o.a_sm = ld_x; o.a_sk = 1;
+    o.b = n.W[l] + wshift; o.b_sk = 1; o.b_sn = o.K;
+    o.bias = n.b[l] + wshift;
+    o.c = as.h[l]; o.ldc = as.ld[l]; o.zout = as.z[l];
+    finish_gemm(o);
+    return o;
+  }
+  // delta_{l-1} = (delta_l . W_l) * act'(layer l-1)
+  Op gemm_da(const NetLayout& n, int l, i64 dy, int ld_dy, i64 dx, int ld_dx, i64 aux, int ld_aux) const {
+    Op o = blank(OP_GEMM);
+    o.epi = EPI_DACT; o.act = n.act_h;
+    o.M = cfg.batch_size; o.N = n.dims[l]; o.K = n.dims[l + 1];
+    o.a = dy; o.a_sm = ld_dy; o.a_sk = 1;
+    o.b = n.W[l]; o.b_sk = n.dims[l]; o.b_sn = 1;
+    o.c = dx; o.ldc = ld_dx; o.aux = aux; o.ld_aux = ld_aux;
+    finish_gemm(o);
+    return o;
+  }
+  // dW_l = delta_l^T . input_l  (+ db_l) with the optimiser step fused into the epilogue
+  Op gemm_dw(const NetLayout& n, int l, int opt, int flags, i64 dy, int ld_dy, i64 x, int ld_x, bool is_critic) const {
+    Op o = blank(OP_GEMM);
+    o.epi = EPI_DW; o.opt = opt; o.flags = flags;
+    o.M = n.dims[l + 1]; o.N = n.dims[l]; o.K = cfg.batch_size;
+    o.a = dy; o.a_sm = 1; o.a_sk = ld_dy;
+    o.b = x; o.b_sk = ld_x; o.b_sn = 1;
+    o.p = n.W[l]; o.pm = n.W[l] + blk; o.pv = n.W[l] + 2 * blk; o.pg = n.W[l] + 3 * blk;
+    o.pb = n.b[l]; o.pbm = n.b[l] + blk; o.pbv = n.b[l] + 2 * blk; o.pbg = n.b[l] + 3 * blk;
+    if (is_critic) { o.pt = n.W[l] - q1.begin + T0; o.pbt = n.b[l] - q1.begin + T0; }
+    finish_gemm(o);
+    return o;
+  }
+  int row_tiles() const { return (cfg.batch_size + ROWS_PER_TILE - 1) / ROWS_PER_TILE; }
+
+  Op op_gather() const {
+    Op o = blank(OP_GATHER);
+    o.o[0] = x_sa; o.o[1] = x_s2; o.o[2] = x_pi; o.o[3] = b_r; o.o[4] = b_d; o.o[5] = b_idx;
+    o.i[0] = ldx; o.ntiles = row_tiles();
+    return o;
+  }
+  Op op_pi_head(bool actor) const {
+    Op o = blank(OP_PI_HEAD);
+    const ActSet& as = actor ? a_pia : a_pit;
+    const int L = pi.L();
+    o.mode = actor ? 2 : 1; o.act_out = pi.act_o;
+    o.o[0] = as.h[L - 1]; o.i[0] = as.ld[L - 1]; o.i[1] = pi.dims[L];
+    o.o[1] = pi.W[L]; o.o[2] = pi.b[L];
+    o.o[3] = actor ? x_pi : x_s2; o.i[2] = ldx;
+    o.o[4] = actor ? b_lp : b_lp2;
+    o.o[5] = actor ? b_eps2 : b_eps1;
+    if (actor) { o.o[6] = b_tz; o.o[7] = b_se; o.o[8] = b_mask; o.o[9] = b_headz; }
+    o.ntiles = row_tiles();
+    return o;
+  }
+  Op op_q_target() const {
+    Op o = blank(OP_Q_ROW);
+    const int L = q1.L();
+    o.act_out = q1.act_o;
+    for (int c = 0; c < 2; ++c) {
+      const NetLayout& n = c ? q2 : q1;
+      o.o[c] = a_qt[c].h[L - 1];
+      o.o[2 + c] = n.W[L] - q1.begin + T0;
+      o.o[4 + c] = n.b[L] - q1.begin + T0;
+      o.o[10 + c] = b_tq[c];
+    }
+    o.i[0] = a_qt[0].ld[L - 1]; o.i[1] = q1.dims[L];
+    o.o[6] = b_r; o.o[7] = b_d; o.o[8] = b_lp2; o.o[9] = b_y;
+    o.ntiles = row_tiles();
+    return o;
+  }
+  Op op_critic_row() const {
+    Op o = blank(OP_CRITIC_ROW);
+    const int L = q1.L();
+    o.act = q1.act_h; o.act_out = q1.act_o;
+    for (int c = 0; c < 2; ++c) {
+      const NetLayout& n = c ? q2 : q1;
+      o.o[c] = a_q[c].h[L - 1]; o.o[2 + c] = a_q[c].aux(L - 1);
+      o.o[4 + c] = n.W[L]; o.o[6 + c] = n.b[L];
+      o.o[9 + c] = b_q[c]; o.o[11 + c] = b_dout[c]; o.o[13 + c] = d_q[c][L - 1]; o.o[15 + c] = b_loss[c];
+    }
+    o.o[8] = b_y;
+    o.i[0] = a_q[0].ld[L - 1]; o.i[1] = q1.dims[L];
+    o.ntiles = row_tiles();
+    return o;
+  }
+  Op op_actor_q() const {
+    Op o = blank(OP_ACTOR_Q);
+    const int L = q1.L();
+    o.act = q1.act_h; o.act_out = q1.act_o;
+    for (int c = 0; c < 2; ++c) {
+      const NetLayout& n = c ? q2 : q1;
+      o.o[c] = a_q[c].h[L - 1]; o.o[2 + c] = a_q[c].aux(L - 1);
+      o.o[4 + c] = n.W[L]; o.o[6 + c] = n.b[L];
+      o.o[9 + c] = b_qa[c]; o.o[13 + c] = d_q[c][L - 1];
+    }
+    o.o[8] = b_lp; o.o[15] = b_ploss;
+    o.i[0] = a_q[0].ld[L - 1]; o.i[1] = q1.dims[L];
+    o.ntiles = row_tiles();
+    return o;
+  }
+  Op op_actor_bwd() const {
+    Op o = blank(OP_ACTOR_BWD);
+    const int L = pi.L();
+    o.act = pi.act_h; o.act_out = pi.act_o;
+    for (int c = 0; c < 2; ++c) {
+      o.o[c] = d_q[c][0];
+      o.o[2 + c] = (c ? q2 : q1).W[0];
+    }
+    o.i[0] = rup4(q1.dims[1]); o.i[1] = q1.dims[1]; o.i[2] = q1.dims[0];
+    o.o[4] = b_tz; o.o[5] = b_se; o.o[6] = b_mask; o.o[7] = b_headz; o.o[8] = b_dhead;
+    o.o[9] = pi.W[L]; o.o[11] = a_pia.aux(L - 1); o.o[12] = d_p[L - 1];
+    o.i[3] = a_pia.ld[L - 1]; o.i[4] = pi.dims[L];
+    o.ntiles = row_tiles();
+    return o;
+  }
+  Op op_prologue(int mask) const { Op o = blank(OP_PROLOGUE); o.mode = mask; o.ntiles = 1; return o; }
+  Op op_final(int mode) const {
+    Op o = blank(OP_FINAL);
+    o.mode = mode; o.ntiles = 1;
+    o.o[0] = b_loss[0]; o.o[1] = b_loss[1]; o.o[2] = b_ploss; o.o[3] = b_lp; o.o[4] = b_q[0]; o.o[5] = b_q[1]; o.o[6] = b_y;
+    return o;
+  }
+  Op op_polyak() const {
+    Op o = blank(OP_POLYAK);
+    o.o[0] = q1.begin; o.o[1] = T0; o.o[2] = n_critic;
+    o.ntiles = (int)((n_critic + FLAT_TILE - 1) / FLAT_TILE);
+    return o;
+  }
+  Op op_adam_flat(const NetLayout& n, int opt, bool polyak) const {
+    Op o = blank(OP_ADAM_FLAT);
+    const i64 cnt = n.end - n.begin;
+    o.opt = opt;
+    o.o[0] = n.begin; o.o[1] = n.begin + blk; o.o[2] = n.begin + 2 * blk; o.o[3] = n.begin + 3 * blk; o.o[4] = cnt;
+    o.o[5] = polyak ? n.begin - q1.begin + T0 : -1;
+    o.ntiles = (int)((cnt + FLAT_TILE - 1) / FLAT_TILE);
+    return o;
+  }
+
+  // ---------------------------------------------------------------- plan construction
+  struct PB {
+    Plan p;
+    bool overflow = false;
+    PB() { memset(&p, 0, sizeof p); }
+    void phase() {
+      if (p.n_phases >= MAX_PHASES) { overflow = true; return; }
+      p.phases[p.n_phases] = Phase{p.n_ops, 0, 0, 0};
+      p.n_phases++;
+    }
+    void add(const Op& o) {
+      if (p.n_ops >= MAX_OPS || p.n_phases == 0) { overflow = true; return; }
+      Phase& ph = p.phases[p.n_phases - 1];
+      Op& d = p.ops[p.n_ops++];
+      d = o;
+      d.tile0 = ph.ntiles;
+      ph.ntiles += d.ntiles;
+      ph.nops++;
+    }
+  };
+
+  // backward stages of one MLP given delta of the last hidden layer (row op) and dout = delta of the output
+  // layer. Stage k: DA producing delta_{L-2-k}; DW of layer L-k; DW of layer 0 joins the last stage.
+  int bwd_stages(const NetLayout& n) const { return std::max(1, n.L()); }
+  void emit_bwd_stage(PB& pb, int k, const NetLayout& n, const ActSet& as, const i64* delta, i64 dout, int ld_dout,
+                      i64 x, int ld_x, int opt, int flags, bool is_critic, bool with_dw) const {
+    const int L = n.L();
+    auto dl = [&](int l) { return delta[l]; };
+    auto ldd = [&](int l) { return rup4(n.dims[l + 1]); };
+    if (L - 2 - k >= 0) {   // DA: delta_{l-1} from delta_l with l = L-1-k
+      const int l = L - 1 - k;
+      pb.add(gemm_da(n, l, dl(l), ldd(l), dl(l - 1), ldd(l - 1), as.aux(l - 1), as.ld[l - 1]));
+    }
+    if (!with_dw) return;
+    const int lw = L - k;     // layer whose weights get their gradient in this stage
+    if (lw >= 1) {
+      const i64 dy = (lw == L) ? dout : dl(lw);
+      const int ldy = (lw == L) ? ld_dout : ldd(lw);
+      pb.add(gemm_dw(n, lw, opt, flags, dy, ldy, as.h[lw - 1], as.ld[lw - 1], is_critic));
+    }
+    if (k == bwd_stages(n) - 1)   // layer 0 joins the last stage
+      pb.add(gemm_dw(n, 0, opt, flags, L >= 1 ? dl(0) : dout, L >= 1 ? ldd(0) : ld_dout, x, ld_x, is_critic));
+  }
+
+  void emit_target(PB& pb) const {
+    for (int l = 0; l < pi.L(); ++l) { pb.phase(); pb.add(gemm_fwd(pi, l, 0, l ? a_pit.h[l - 1] : x_s2, l ? a_pit.ld[l - 1] : ldx, a_pit)); }
+    pb.phase(); pb.add(op_pi_head(false));
+    for (int l = 0; l < q1.L(); ++l) {
+      pb.phase();
+      for (int c = 0; c < 2; ++c)
+        pb.add(gemm_fwd(c ? q2 : q1, l, T0 - q1.begin, l ? a_qt[c].h[l - 1] : x_s2, l ? a_qt[c].ld[l - 1] : ldx, a_qt[c]));
+    }
+    pb.phase(); pb.add(op_q_target());
+  }
+  void emit_critic(PB& pb, int flags) const {
+    for (int l = 0; l < q1.L(); ++l) {
+      pb.phase();
+      if (l == 0 && (flags & DW_ADAM)) pb.add(op_prologue((1 << OPT_Q1) | (1 << OPT_Q2)));
+      for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l, 0, l ? a_q[c].h[l - 1] : x_sa, l ? a_q[c].ld[l - 1] : ldx, a_q[c]));
+    }
+    pb.phase(); pb.add(op_critic_row());
+    for (int k = 0; k < bwd_stages(q1); ++k) {
+      pb.phase();
+      for (int c = 0; c < 2; ++c)
+        emit_bwd_stage(pb, k, c ? q2 : q1, a_q[c], d_q[c], b_dout[c], 1, x_sa, ldx, c ? OPT_Q2 : OPT_Q1, flags, true, true);
+      if (k == 0) pb.add(op_final(1));
+    }
+  }
+  void emit_actor(PB& pb, int flags) const {
+    for (int l = 0; l < pi.L(); ++l) {
+      pb.phase();
+      if (l == 0 && (flags & DW_ADAM)) pb.add(op_prologue(1 << OPT_PI));
+      pb.add(gemm_fwd(pi, l, 0, l ? a_pia.h[l - 1] : x_pi, l ? a_pia.ld[l - 1] : ldx, a_pia));
+    }
+    pb.phase(); pb.add(op_pi_head(true));
+    emit_actor_tail(pb, flags, 2);
+  }
+  // critics on (s, a~pi) -> routed dQ -> dQ/da -> head backward -> policy backward (+Adam)
+  void emit_actor_tail(PB& pb, int flags, int final_mode) const {
+    for (int l = 0; l < q1.L(); ++l) {
+      pb.phase();
+      for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l, 0, l ? a_q[c].h[l - 1] : x_pi, l ? a_q[c].ld[l - 1] : ldx, a_q[c]));
+    }
+    pb.phase(); pb.add(op_actor_q());
+    for (int k = 0; k + 1 < q1.L(); ++k) {
+      pb.phase();
+      for (int c = 0; c < 2; ++c)
+        emit_bwd_stage(pb, k, c ? q2 : q1, a_q[c], d_q[c], -1, 1, x_pi, ldx, 0, 0, true, false);
+    }
+    pb.phase(); pb.add(op_actor_bwd());
+    for (int k = 0; k < bwd_stages(pi); ++k) {
+      pb.phase();
+      emit_bwd_stage(pb, k, pi, a_pia, d_p, b_dhead, 2 * cfg.act_dim, x_pi, ldx, OPT_PI, flags, false, true);
+      if (k == 0 && final_mode) pb.add(op_final(final_mode));
+    }
+  }
+  void emit_fused(PB& pb, bool gather) const {
+    const int AD = DW_ADAM;
+    pb.phase();
+    pb.add(op_prologue(7));
+    if (gather) pb.add(op_gather());
+    const int Lm = std::max(pi.L(), q1.L());
+    for (int l = 0; l < Lm; ++l) {     // pi(s'), pi(s), Q1(s,a), Q2(s,a) side by side
+      pb.phase();
+      if (l < pi.L()) {
+        pb.add(gemm_fwd(pi, l, 0, l ? a_pit.h[l - 1] : x_s2, l ? a_pit.ld[l - 1] : ldx, a_pit));
+        pb.add(gemm_fwd(pi, l, 0, l ? a_pia.h[l - 1] : x_pi, l ? a_pia.ld[l - 1] : ldx, a_pia));
+      }
+      if (l < q1.L())
+        for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l, 0, l ? a_q[c].h[l - 1] : x_sa, l ? a_q[c].ld[l - 1] : ldx, a_q[c]));
+    }
+    pb.phase(); pb.add(op_pi_head(false)); pb.add(op_pi_head(true));
+    for (int l = 0; l < q1.L(); ++l) {
+      pb.phase();
+      for (int c = 0; c < 2; ++c)
+        pb.add(gemm_fwd(c ? q2 : q1, l, T0 - q1.begin, l ? a_qt[c].h[l - 1] : x_s2, l ? a_qt[c].ld[l - 1] : ldx, a_qt[c]));
+    }
+    pb.phase(); pb.add(op_q_target());
+    pb.phase(); pb.add(op_critic_row());
+    for (int k = 0; k < bwd_stages(q1); ++k) {   // critic Adam with the Polyak update fused behind it (K10)
+      pb.phase();
+      for (int c = 0; c < 2; ++c)
+        emit_bwd_stage(pb, k, c ? q2 : q1, a_q[c], d_q[c], b_dout[c], 1, x_sa, ldx, c ? OPT_Q2 : OPT_Q1, AD | DW_POLYAK, true, true);
+    }
+    emit_actor_tail(pb, AD, 1 | 2 | 4 | 8);
+  }
+
+  int build_plans() {
+    h_plans.assign(N_PLANS, Plan());
+    auto put = [&](int id, PB& pb) -> int {
+      if (pb.overflow) return fail(SACX_ERR_INVALID, "network too deep for the op table (MAX_OPS/MAX_PHASES)");
+      h_plans[id] = pb.p;
+      return SACX_OK;
+    };
+    int rc;
+    { PB pb; emit_fused(pb, true); if ((rc = put(PLAN_FUSED, pb))) return rc; }
+    { PB pb; emit_fused(pb, false); if ((rc = put(PLAN_FUSED_NOGATHER, pb))) return rc; }
+    { PB pb; pb.phase(); pb.add(op_gather()); if ((rc = put(PLAN_SAMPLE, pb))) return rc; }
+    { PB pb; emit_target(pb); if ((rc = put(PLAN_TARGET, pb))) return rc; }
+    { PB pb; emit_critic(pb, DW_ADAM); if ((rc = put(PLAN_CRITIC, pb))) return rc; }
+    { PB pb; emit_critic(pb, DW_STORE_GRAD); if ((rc = put(PLAN_CRITIC_GRADS, pb))) return rc; }
+    { PB pb; emit_actor(pb, DW_ADAM); if ((rc = put(PLAN_ACTOR, pb))) return rc; }
+    { PB pb; emit_actor(pb, DW_STORE_GRAD); if ((rc = put(PLAN_ACTOR_GRADS, pb))) return rc; }
+    { PB pb; pb.phase(); pb.add(op_final(4)); if ((rc = put(PLAN_ALPHA, pb))) return rc; }
+    { PB pb; pb.phase(); pb.add(op_polyak()); pb.add(op_final(8)); if ((rc = put(PLAN_POLYAK, pb))) return rc; }
+    for (int pol = 0; pol < 2; ++pol) {
+      PB pb;
+      pb.phase(); pb.add(op_prologue((1 << OPT_Q1) | (1 << OPT_Q2)));
+      pb.phase(); pb.add(op_adam_flat(q1, OPT_Q1, pol)); pb.add(op_adam_flat(q2, OPT_Q2, pol));
+      if ((rc = put(pol ? PLAN_APPLY_Q_POLYAK : PLAN_APPLY_Q, pb))) return rc;
+    }
+    { PB pb; pb.phase(); pb.add(op_prologue(1 << OPT_PI)); pb.phase(); pb.add(op_adam_flat(pi, OPT_PI, false));
+      if ((rc = put(PLAN_APPLY_PI, pb))) return rc; }
+    return SACX_OK;
+  }
+
+  int max_phase_tiles() const {
+    int m = 1;
+    for (const Plan& p : h_plans)
+      for (int i = 0; i < p.n_phases; ++i) m = std::max(m, p.phases[i].ntiles);
+    return m;
+  }
+};
+
+}  // namespace sacx

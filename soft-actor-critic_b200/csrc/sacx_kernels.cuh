@@ -1,0 +1,272 @@
+// The persistent fused update kernel and the small standalone kernels (ring scatter/gather, batch
+// load, rollout-side policy / critic forwards).
+#pragma once
+#include "sacx_gemm.cuh"
+#include "sacx_rowops.cuh"
+
+namespace sacx {
+
+constexpr int SMEM_OPS = 64;                                   // ops of the active phase range cached in smem
+constexpr int WSM_FLOATS = 8 * 4 * SACX_MAX_ACT;               // per-warp scratch for the row ops
+
+// Barrier among the gridDim.x CTAs that work on the same agent (cooperative launch => co-resident).
+// Monotonic counter, release/acquire at gpu scope; thread 0's fences make the CTA's global writes
+// visible and drop stale L1 lines before the other threads continue.
+__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  if (gridDim.x > 1) {
+    if (threadIdx.x == 0) {
+      epoch += gridDim.x;
+      __threadfence();
+      atomicAdd(counter, 1u);
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      } while (v < epoch);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+}
+
+template <bool LARGE>
+__global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict__ gplan, const RunArgs args) {
+  using C = typename std::conditional<LARGE, CfgLarge, CfgSmall>::type;
+  extern __shared__ __align__(16) float smem_raw[];
+  Op* sops = reinterpret_cast<Op*>(smem_raw);
+  float* wsm = smem_raw + (SMEM_OPS * sizeof(Op)) / 4;
+  float* gsm = wsm + WSM_FLOATS;
+  __shared__ Phase sphase[MAX_PHASES];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int op_lo = gplan->phases[args.phase_begin].op0;
+  const int op_hi = gplan->phases[args.phase_end - 1].op0 + gplan->phases[args.phase_end - 1].nops;
+  const bool cached = (op_hi - op_lo) <= SMEM_OPS;
+  if (cached) {
+    const int words = (op_hi - op_lo) * (int)(sizeof(Op) / 4);
+    const int* src = reinterpret_cast<const int*>(gplan->ops + op_lo);
+    int* dst = reinterpret_cast<int*>(sops);
+    for (int i = tid; i < words; i += 256) dst[i] = src[i];
+  }
+  for (int i = tid; i < gplan->n_phases; i += 256) sphase[i] = gplan->phases[i];
+  __syncthreads();
+  const Op* ops = cached ? (sops - op_lo) : gplan->ops;
+
+  unsigned epoch = 0;
+  unsigned* counter = args.barrier + blockIdx.y;
+  for (int agent = blockIdx.y; agent < args.n_agents; agent += gridDim.y) {
+    float* base = args.arena + (i64)agent * args.agent_stride;
+    AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
+    RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT};
+    EpiCtx ec{base, scal, &args.hp};
+    const bool last_agent = (agent + (int)gridDim.y >= args.n_agents);
+    for (int step = 0; step < args.n_steps; ++step) {
+      rc.step = step;
+      for (int p = args.phase_begin; p < args.phase_end; ++p) {
+        const Phase ph = sphase[p];
+        for (int t = blockIdx.x; t < ph.ntiles; t += gridDim.x) {
+          int oi = ph.op0;
+          while (oi + 1 < ph.op0 + ph.nops && t >= ops[oi + 1].tile0) ++oi;
+          const Op& op = ops[oi];
+          const int lt = t - op.tile0;
+          switch (op.type) {
+            case OP_GEMM: gemm_tile<C>(op, ec, lt, gsm); break;
+            case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
+            case OP_PI_HEAD: op_pi_head(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
+            case OP_Q_ROW: op_q_target(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
+            case OP_CRITIC_ROW: op_critic_row(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
+            case OP_ACTOR_Q: op_actor_q(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
+            case OP_ACTOR_BWD: op_actor_bwd(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
+            case OP_PROLOGUE: if (tid == 0) op_prologue(op, rc); break;
+            case OP_FINAL: if (warp == 0) op_final(op, rc, lane); break;
+            case OP_POLYAK: op_polyak(op, rc, lt); break;
+            case OP_ADAM_FLAT: op_adam_flat(op, rc, lt); break;
+            default: break;
+          }
+        }
+        const bool very_last = last_agent && (step + 1 == args.n_steps) && (p + 1 == args.phase_end);
+        if (!very_last) group_barrier(counter, epoch);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- ring kernels
+struct StageHdr {
+  int agent, pad;
+  i64 push_no;
+};
+
+// staged AoS rows [s | a | r | s2 | d] -> SoA ring slots (push_no % capacity); bumps the agent's push count
+__global__ void ring_scatter_kernel(float* __restrict__ ring, i64 ring_stride, i64 cap, i64 off_s, i64 off_a, i64 off_r,
+                                    i64 off_s2, i64 off_d, int O, int A, const float* __restrict__ rows,
+                                    const StageHdr* __restrict__ hdr, int n) {
+  const int W = 2 * O + A + 2;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const StageHdr h = hdr[row];
+  float* rb = ring + (i64)h.agent * ring_stride;
+  const i64 slot = h.push_no % cap;
+  const float* src = rows + (i64)row * W;
+  for (int k = lane; k < O; k += 32) {
+    rb[off_s + slot * O + k] = src[k];
+    rb[off_s2 + slot * O + k] = src[O + A + 1 + k];
+  }
+  for (int k = lane; k < A; k += 32) rb[off_a + slot * A + k] = src[O + k];
+  if (lane == 0) {
+    rb[off_r + slot] = src[O + A];
+    rb[off_d + slot] = src[2 * O + A + 1];
+    atomicMax(reinterpret_cast<unsigned long long*>(&reinterpret_cast<RingMeta*>(rb)->pushes),
+              (unsigned long long)(h.push_no + 1));
+  }
+}
+
+// rows already on the device (SoA inputs) for one agent
+__global__ void ring_scatter_dev_kernel(float* __restrict__ rb, i64 cap, i64 off_s, i64 off_a, i64 off_r, i64 off_s2,
+                                        i64 off_d, int O, int A, const float* __restrict__ s, const float* __restrict__ a,
+                                        const float* __restrict__ r, const float* __restrict__ s2,
+                                        const float* __restrict__ d, i64 push0, int n) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const i64 slot = (push0 + row) % cap;
+  for (int k = lane; k < O; k += 32) {
+    rb[off_s + slot * O + k] = s[(i64)row * O + k];
+    rb[off_s2 + slot * O + k] = s2[(i64)row * O + k];
+  }
+  for (int k = lane; k < A; k += 32) rb[off_a + slot * A + k] = a[(i64)row * A + k];
+  if (lane == 0) {
+    rb[off_r + slot] = r[row];
+    rb[off_d + slot] = d[row];
+    if (row == n - 1)
+      atomicMax(reinterpret_cast<unsigned long long*>(&reinterpret_cast<RingMeta*>(rb)->pushes),
+                (unsigned long long)(push0 + n));
+  }
+}
+
+// uniform-index gather: one warp per sampled row; logical deque position -> ring slot.
+// Streaming loads (ld.global.cs): every row is touched once per update and the 1M-row ring does not fit L2.
+__global__ void ring_gather_kernel(const float* __restrict__ rb, i64 cap, i64 off_s, i64 off_a, i64 off_r, i64 off_s2,
+                                   i64 off_d, int O, int A, const i64* __restrict__ idx, int B, float* __restrict__ s,
+                                   float* __restrict__ a, float* __restrict__ r, float* __restrict__ s2,
+                                   float* __restrict__ d) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const i64 pushes = reinterpret_cast<const RingMeta*>(rb)->pushes;
+  const i64 oldest = pushes > cap ? pushes - cap : 0;
+  const i64 slot = (oldest + idx[row]) % cap;
+  if (s) for (int k = lane; k < O; k += 32) s[(i64)row * O + k] = __ldcs(rb + off_s + slot * O + k);
+  if (s2) for (int k = lane; k < O; k += 32) s2[(i64)row * O + k] = __ldcs(rb + off_s2 + slot * O + k);
+  if (a) for (int k = lane; k < A; k += 32) a[(i64)row * A + k] = __ldcs(rb + off_a + slot * A + k);
+  if (lane == 0) {
+    if (r) r[row] = __ldcs(rb + off_r + slot);
+    if (d) d[row] = __ldcs(rb + off_d + slot);
+  }
+}
+
+__global__ void ring_indices_kernel(const float* __restrict__ rb, i64 cap, unsigned long long seed,
+                                    unsigned long long counter, int agent, int B, i64* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const i64 pushes = reinterpret_cast<const RingMeta*>(rb)->pushes;
+  const i64 n = pushes < cap ? pushes : cap;
+  out[i] = (i64)feistel_index((unsigned long long)i, (unsigned long long)n, seed, counter, (uint32_t)agent);
+}
+
+// external batch -> the arena's batch buffers (staged API): X_sa=[s|a], X_pi=[s|.], X_s2=[s2|.], r, d
+__global__ void load_batch_kernel(float* __restrict__ base, i64 x_sa, i64 x_s2, i64 x_pi, i64 r_off, i64 d_off, int ldx,
+                                  int O, int A, int B, const float* __restrict__ s, const float* __restrict__ a,
+                                  const float* __restrict__ r, const float* __restrict__ s2, const float* __restrict__ d) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  if (s) for (int k = lane; k < O; k += 32) {
+    const float v = s[(i64)row * O + k];
+    base[x_sa + (i64)row * ldx + k] = v;
+    base[x_pi + (i64)row * ldx + k] = v;
+  }
+  if (s2) for (int k = lane; k < O; k += 32) base[x_s2 + (i64)row * ldx + k] = s2[(i64)row * O + k];
+  if (a) for (int k = lane; k < A; k += 32) base[x_sa + (i64)row * ldx + O + k] = a[(i64)row * A + k];
+  if (lane == 0) {
+    if (r) base[r_off + row] = r[row];
+    if (d) base[d_off + row] = d[row];
+  }
+}
+
+__global__ void copy_out_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------- rollout-side forwards (a13, _log_q_values)
+struct NetRef {          // one MLP inside an agent arena
+  int n_lin, in_dim, out_dim, act_h, act_o;
+  int dims[SACX_MAX_HIDDEN + 2];
+  i64 W[SACX_MAX_HIDDEN + 1], b[SACX_MAX_HIDDEN + 1];
+};
+
+// one CTA per row: activations ping-pong in shared memory, one warp per output neuron
+__device__ __forceinline__ const float* mlp_row(const float* __restrict__ base, const NetRef& net, float* buf0, float* buf1) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* in = buf0;
+  float* out = buf1;
+  for (int l = 0; l < net.n_lin; ++l) {
+    const int K = net.dims[l], N = net.dims[l + 1];
+    const int act = (l + 1 < net.n_lin) ? net.act_h : net.act_o;
+    for (int o = warp; o < N; o += nw) {
+      const float* w = base + net.W[l] + (i64)o * K;
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s = fmaf(in[k], __ldg(w + k), s);
+      s = warp_sum(s);
+      if (lane == 0) out[o] = act_fwd(act, s + __ldg(base + net.b[l] + o));
+    }
+    __syncthreads();
+    float* t = in; in = out; out = t;
+  }
+  return in;
+}
+
+__global__ void act_kernel(const float* __restrict__ base, NetRef net, int maxw, const float* __restrict__ s,
+                           const float* __restrict__ eps, int deterministic, float* __restrict__ a_out, int A,
+                           float lo, float hi, float scale, unsigned long long seed, unsigned long long counter,
+                           int agent) {
+  extern __shared__ float sm[];
+  float* b0 = sm;
+  float* b1 = sm + maxw;
+  const int row = blockIdx.x;
+  for (int k = threadIdx.x; k < net.in_dim; k += blockDim.x) b0[k] = s[(i64)row * net.in_dim + k];
+  __syncthreads();
+  const float* head = mlp_row(base, net, b0, b1);
+  for (int j = threadIdx.x; j < A; j += blockDim.x) {
+    const float mu = head[j];
+    float v;
+    if (deterministic) {
+      v = tanhf(mu) * scale;                                     // models.py:89-92
+    } else {
+      const float ls = fminf(fmaxf(head[A + j], lo), hi);
+      const float e = eps ? eps[(i64)row * A + j]
+                          : philox_normal(seed, counter, 3, (uint32_t)row, (uint32_t)j, (uint32_t)agent);
+      v = tanhf(mu + e * expf(ls)) * scale;                      // models.py:79-84
+    }
+    a_out[(i64)row * A + j] = v;
+  }
+}
+
+__global__ void qvalue_kernel(const float* __restrict__ base, NetRef q1, NetRef q2, int maxw, int O, int A,
+                              const float* __restrict__ s, const float* __restrict__ a, float* __restrict__ q1_out,
+                              float* __restrict__ q2_out) {
+  extern __shared__ float sm[];
+  float* b0 = sm;
+  float* b1 = sm + maxw;
+  const int row = blockIdx.x;
+  const NetRef& net = blockIdx.y == 0 ? q1 : q2;
+  for (int k = threadIdx.x; k < O + A; k += blockDim.x)
+    b0[k] = k < O ? s[(i64)row * O + k] : a[(i64)row * A + (k - O)];
+  __syncthreads();
+  const float* out = mlp_row(base, net, b0, b1);
+  if (threadIdx.x == 0) (blockIdx.y == 0 ? q1_out : q2_out)[row] = out[0];
+}
+
+}  // namespace sacx

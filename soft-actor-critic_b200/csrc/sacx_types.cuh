@@ -1,0 +1,114 @@
+// Shared host/device types of the fused SAC update engine: the op table ("plan") that the
+// persistent kernel interprets, per-agent scalar state, and launch arguments.
+#pragma once
+#include <stdint.h>
+
+namespace sacx {
+
+typedef long long i64;
+
+enum OpType : int {
+  OP_NONE = 0,
+  OP_GATHER,      // ring rows -> batch buffers (a2/a3: replay_buffer.py:32-39, agent.py:166-193)
+  OP_GEMM,        // tiled FP32 GEMM with fused epilogue (a4 forward, backward dA, backward dW+Adam)
+  OP_PI_HEAD,     // policy output layer + tanh-Gaussian rsample/log_prob (a5: models.py:73-87)
+  OP_Q_ROW,       // target critics' output layers + soft Bellman target y (a6)
+  OP_CRITIC_ROW,  // online critics' output layers, MSE delta, delta of the last hidden layer (a7)
+  OP_ACTOR_Q,     // critics' heads on (s, a~pi): min, policy loss rows, routed dQ (a8)
+  OP_ACTOR_BWD,   // dQ/da through layer 0, head backward, policy delta of last hidden (a8)
+  OP_PROLOGUE,    // per-update scalars: Adam step/bias corrections (a11)
+  OP_FINAL,       // loss means, temperature step (a9), counters
+  OP_POLYAK,      // standalone soft target update (a10)
+  OP_ADAM_FLAT,   // Adam over a packed gradient block (data-parallel apply)
+  OP_LOAD_EXT,    // copy external y / logpi into arena buffers
+};
+
+enum Epi : int { EPI_FWD = 1, EPI_DACT = 2, EPI_DW = 3 };
+enum DwFlags : int { DW_STORE_GRAD = 1, DW_ADAM = 2, DW_POLYAK = 4 };
+enum OptId : int { OPT_PI = 0, OPT_Q1 = 1, OPT_Q2 = 2, OPT_ALPHA = 3, N_OPT = 4 };
+
+// One schedulable operation. All `long long` fields are float32-word offsets from the agent's
+// arena base (or -1 when unused).
+struct Op {
+  int type, mode, act, act_out;
+  int tile0, ntiles, tiles_n, cfg;
+  // GEMM: C[M,N] = sum_k A(m,k) * B(k,n);  A(m,k) = a[m*a_sm + k*a_sk], B(k,n) = b[k*b_sk + n*b_sn]
+  int M, N, K, epi;
+  int a_sm, a_sk, b_sk, b_sn;
+  int ldc, ld_aux, a_vec, b_vec;
+  i64 a, b, c, bias, aux, zout;
+  // EPI_DW: parameter / Adam / target / gradient blocks for the weight (ld = K_in) and its bias
+  i64 p, pm, pv, pt, pg;
+  i64 pb, pbm, pbv, pbt, pbg;
+  int opt, flags;
+  // row ops: generic slots (documented at each op's builder)
+  i64 o[24];
+  int i[8];
+  float f[4];
+};
+
+struct Phase {
+  int op0, nops, ntiles, pad;
+};
+
+constexpr int MAX_OPS = 112;
+constexpr int MAX_PHASES = 48;
+
+struct Plan {
+  int n_phases, n_ops, pad0, pad1;
+  Phase phases[MAX_PHASES];
+  Op ops[MAX_OPS];
+};
+
+// Per-agent scalar state (lives in the arena at `scal_off`, 8-byte aligned).
+struct AgentScalars {
+  double log_alpha, alpha_m, alpha_v, alpha;         // F6: float64 temperature state
+  i64 step[N_OPT];                                   // Adam step counters (pi, q1, q2, alpha)
+  i64 updates;                                       // completed updates (device RNG counter)
+  i64 reserved;
+  float alpha_f32;                                   // alpha as used by target/actor (F5)
+  float adam_step_size[3];                           // lr / (1 - beta1^t)      per optimiser
+  float adam_bc2_sqrt[3];                            // sqrt(1 - beta2^t)
+  float pad;
+  float metrics[12];                                 // q1_loss q2_loss policy_loss alpha_loss alpha log_alpha q1_mean q2_mean logpi_mean y_mean
+  int nonfinite;
+  int pad2[3];
+};
+
+struct RingMeta {          // one per agent, at the head of the agent's ring block
+  i64 pushes;
+  i64 reserved[3];
+};
+
+struct Hyper {
+  float gamma, tau, one_minus_tau, log_std_min, log_std_max, action_scale;
+  double lr[3];
+  double alpha_lr, alpha_init;
+  float target_entropy;
+  int auto_alpha;
+  int obs, act, B, B_global, row0_global;            // data-parallel: this rank's rows are [row0, row0+B)
+  unsigned long long seed;
+};
+
+struct RunArgs {
+  float* arena;
+  i64 agent_stride;          // float words
+  float* ring;               // ring arena base (may be null when no gather op runs)
+  i64 ring_stride;           // float words per agent ring block
+  i64 ring_capacity;
+  // ring field offsets (float words from the agent's ring block)
+  i64 ring_s, ring_a, ring_r, ring_s2, ring_d;
+  const i64* idx_ext;        // [n_steps, n_agents, B] or null
+  const float* eps1_ext;     // [n_steps, n_agents, B, A] or null
+  const float* eps2_ext;
+  const float* y_ext;        // staged critic step: external y [B] or null
+  const float* lp_ext;       // staged alpha step: external logpi [B] or null
+  int n_steps, n_agents;
+  int phase_begin, phase_end;
+  int ctas_per_agent;
+  unsigned* barrier;         // [agent_slots] monotonic counters (zeroed before launch)
+  i64 scal_off;
+  Hyper hp;
+};
+
+}  // namespace sacx

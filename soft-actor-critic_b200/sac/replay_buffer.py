@@ -1,0 +1,188 @@
+"""Device-resident replay ring behind the reference's ReplayBuffer API.
+
+Reference: /root/reference/sac/replay_buffer.py -- ``Transition`` (:6-8), ``ReplayBuffer.__init__``
+(:12-19, ``deque(maxlen=capacity)``), ``push`` (:21-30), ``sample`` (:32-39, ``random.sample`` on the
+deque, ``ValueError`` when under-filled), ``__len__`` (:41-42).
+
+Here the storage is a struct-of-arrays ring in HBM owned by libsacx (``sacx_ring_*``): pushes go
+through a pinned host staging block, sampling is a coalesced gather kernel.  The sampling *semantics*
+are the reference's: ``sample`` draws ``random.sample(range(len), batch_size)`` from Python's global
+Mersenne Twister -- the very index stream ``random.sample(deque, k)`` consumes -- and maps
+logical deque positions (0 = oldest survivor) to ring slots on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from collections import namedtuple
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _engine as E
+
+Transition = namedtuple("Transition", ("state", "action", "reward", "next_state", "done"))
+
+
+class _Occupancy:
+    """Stand-in for the reference's ``.memory`` deque: callers only ever take ``len()`` of it."""
+
+    def __init__(self, owner: "ReplayBuffer"):
+        self._owner = owner
+
+    def __len__(self) -> int:
+        return len(self._owner)
+
+
+class ReplayBuffer:
+    def __init__(self, capacity: int, obs_dim: Optional[int] = None, act_dim: Optional[int] = None,
+                 device: Optional[str] = None, n_agents: int = 1):
+        """capacity: maximum number of stored transitions (oldest evicted first).
+
+        ``obs_dim`` / ``act_dim`` are optional: the reference constructor does not know them
+        (replay_buffer.py:12, agent.py:29), so the ring is allocated lazily on the first push.
+        """
+        self.capacity = int(capacity)
+        self.memory = _Occupancy(self)
+        self.n_agents = int(n_agents)
+        self.device = torch.device(device) if device is not None else None
+        self.obs_dim = self.act_dim = None
+        self._h = None
+        self._store = None
+        if obs_dim is not None and act_dim is not None:
+            self._allocate(int(obs_dim), int(act_dim))
+
+    # ------------------------------------------------------------------ native handle
+    def _allocate(self, obs_dim: int, act_dim: int) -> None:
+        E.require_cuda()
+        lib = E.load()
+        if self.device is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("the replay ring is device-resident: ReplayBuffer needs a CUDA device")
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        nbytes = lib.sacx_ring_bytes(obs_dim, act_dim, self.capacity, self.n_agents)
+        with torch.cuda.device(self.device):
+            self._store = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            h = C.c_void_p()
+            E.check(lib.sacx_ring_create(obs_dim, act_dim, self.capacity, self.n_agents, self._store.data_ptr(), C.byref(h)))
+        self._h = h
+        self._lib = lib
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._lib.sacx_ring_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reference API
+    def push(self, state, action, reward, next_state, done, agent: int = 0) -> None:
+        """Store one transition (reference: replay_buffer.py:21-30). Values are cast to float32,
+        exactly the cast the reference applies at sample time (agent.py:171-185)."""
+        s = np.ascontiguousarray(state, dtype=np.float32).reshape(-1)
+        a = np.ascontiguousarray(action, dtype=np.float32).reshape(-1)
+        s2 = np.ascontiguousarray(next_state, dtype=np.float32).reshape(-1)
+        if self._h is None:
+            self._allocate(s.size, a.size)
+        if s.size != self.obs_dim or s2.size != self.obs_dim or a.size != self.act_dim:
+            raise ValueError("transition shape does not match the buffer's (obs_dim, act_dim)")
+        E.check(self._lib.sacx_ring_push_host(self._h, agent, s.ctypes.data, a.ctypes.data, float(reward),
+                                              s2.ctypes.data, 1.0 if done else 0.0))
+
+    add = push          # BASELINE.json calls it "add"; the reference method is ``push``
+
+    def push_batch(self, states, actions, rewards, next_states, dones, agent: int = 0) -> None:
+        """n transitions from host arrays in one call."""
+        s = np.ascontiguousarray(states, dtype=np.float32)
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        s2 = np.ascontiguousarray(next_states, dtype=np.float32)
+        r = np.ascontiguousarray(rewards, dtype=np.float32).reshape(-1)
+        d = np.ascontiguousarray(dones, dtype=np.float32).reshape(-1)
+        n = r.shape[0]
+        if self._h is None:
+            self._allocate(s.reshape(n, -1).shape[1], a.reshape(n, -1).shape[1])
+        E.check(self._lib.sacx_ring_push_n_host(self._h, agent, n, s.ctypes.data, a.ctypes.data, r.ctypes.data,
+                                                s2.ctypes.data, d.ctypes.data))
+
+    def push_device(self, states: torch.Tensor, actions: torch.Tensor, rewards: torch.Tensor,
+                    next_states: torch.Tensor, dones: torch.Tensor, agent: int = 0) -> None:
+        """n transitions that already live on the device (no host bounce)."""
+        f = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
+        s, a, r, s2, d = f(states), f(actions), f(rewards).reshape(-1), f(next_states), f(dones).reshape(-1)
+        n = r.shape[0]
+        if self._h is None:
+            self._allocate(s.reshape(n, -1).shape[1], a.reshape(n, -1).shape[1])
+        E.check(self._lib.sacx_ring_push_n_dev(self._h, agent, n, s.data_ptr(), a.data_ptr(), r.data_ptr(),
+                                               s2.data_ptr(), d.data_ptr()))
+
+    def __len__(self) -> int:
+        return 0 if self._h is None else int(self._lib.sacx_ring_len(self._h, 0))
+
+    def size(self, agent: int = 0) -> int:
+        return 0 if self._h is None else int(self._lib.sacx_ring_len(self._h, agent))
+
+    def _require(self, batch_size: int, agent: int = 0) -> None:
+        n = self.size(agent)
+        if n < batch_size:
+            raise ValueError(
+                f"Not enough samples in the replay buffer to sample {batch_size} transitions. Current size: {n}")
+
+    def draw_indices(self, batch_size: int, agent: int = 0) -> List[int]:
+        """The reference's index stream: k distinct logical positions from the global ``random``."""
+        self._require(batch_size, agent)
+        return random.sample(range(self.size(agent)), batch_size)
+
+    def sample(self, batch_size: int) -> List[Transition]:
+        """Legacy list-of-Transition result (reference: replay_buffer.py:32-39)."""
+        idx = np.asarray(self.draw_indices(batch_size), dtype=np.int64)
+        s, a, r, s2, d = self.gather_host(idx)
+        return [Transition(s[i], a[i], float(r[i]), s2[i], bool(d[i] != 0.0)) for i in range(batch_size)]
+
+    # ------------------------------------------------------------------ fast paths
+    def gather_host(self, logical_idx: Sequence[int], agent: int = 0):
+        idx = np.ascontiguousarray(logical_idx, dtype=np.int64)
+        B = idx.shape[0]
+        self._require(B, agent)
+        s = np.empty((B, self.obs_dim), np.float32)
+        a = np.empty((B, self.act_dim), np.float32)
+        r = np.empty(B, np.float32)
+        s2 = np.empty((B, self.obs_dim), np.float32)
+        d = np.empty(B, np.float32)
+        E.check(self._lib.sacx_ring_gather_host(self._h, agent, idx.ctypes.data, B, s.ctypes.data, a.ctypes.data,
+                                                r.ctypes.data, s2.ctypes.data, d.ctypes.data))
+        return s, a, r, s2, d
+
+    def sample_tensors(self, batch_size: int, indices=None, agent: int = 0) -> Transition:
+        """Batch as device tensors. ``indices``: logical positions (host sequence or device int64
+        tensor); None draws them from the global ``random`` like the reference."""
+        self._require(batch_size, agent)
+        if indices is None:
+            indices = self.draw_indices(batch_size, agent)
+        if not torch.is_tensor(indices):
+            indices = torch.as_tensor(np.asarray(indices, dtype=np.int64))
+        idx = indices.to(device=self.device, dtype=torch.int64).contiguous()
+        B = idx.shape[0]
+        kw = dict(dtype=torch.float32, device=self.device)
+        s, a = torch.empty(B, self.obs_dim, **kw), torch.empty(B, self.act_dim, **kw)
+        r, s2, d = torch.empty(B, **kw), torch.empty(B, self.obs_dim, **kw), torch.empty(B, **kw)
+        E.check(self._lib.sacx_ring_gather(self._h, agent, idx.data_ptr(), B, s.data_ptr(), a.data_ptr(), r.data_ptr(),
+                                           s2.data_ptr(), d.data_ptr()))
+        return Transition(s, a, r, s2, d)
+
+    def device_indices(self, batch_size: int, seed: int, counter: int, agent: int = 0) -> torch.Tensor:
+        """B distinct logical positions generated on the device (throughput mode's sampler)."""
+        self._require(batch_size, agent)
+        out = torch.empty(batch_size, dtype=torch.int64, device=self.device)
+        E.check(self._lib.sacx_ring_sample_indices(self._h, agent, seed, counter, batch_size, out.data_ptr()))
+        return out
+
+    def flush(self) -> None:
+        if self._h is not None:
+            E.check(self._lib.sacx_ring_flush(self._h))
