@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- SAC updates/s at BipedalWalker shape (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload bipedal|population|donkey]
+
+A "step" is one full SAC gradient update (ring gather + target + 2 critic steps + actor step + temperature step
++ Polyak; reference: SAC.training_step, sac/agent.py:302-327) on synthetic transitions.
+One JSON line is printed by rank 0:
+  value     updates/s with everything resident in HBM (device RNG, K updates timed with CUDA events)
+  e2e       updates/s through the public API SAC.training_step() in host-RNG mode: every step draws the
+            reference's index stream + normals on the host, copies them from pinned memory (H2D), runs the
+            fused kernel and reads the metrics back (D2H)
+  roofline  the fused update kernel against the measured peaks (MEASURED_PEAKS.json)
+  cpu_baseline  the torch-eager CPU port of the reference (oracle/torch_port.py) on this box's host cores
+N > 1: the single-agent update does not shard ("replicas only"): every rank runs an independent
+agent (the population-of-seeds mode, no collective on the data path); value = all ranks' updates / max time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "soft-actor-critic_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (obs, act, hidden, batch, ring capacity, fill, n_agents, activation)
+    "bipedal": dict(obs=24, act=4, hidden=[256, 256], batch=256, capacity=1_000_000, fill=1_000_000, n_agents=1, act_fn="relu",
+                    label="BipedalWalker-v3 shape: obs 24, act 4, 2x256 relu MLPs, batch 256, 1M-transition ring (216 MB > L2)"),
+    "donkey": dict(obs=32, act=2, hidden=[256, 256], batch=1024, capacity=50_000, fill=50_000, n_agents=1, act_fn="relu",
+                   label="DonkeyVae latent shape: obs 32, act 2, 2x256 relu, batch 1024, 50k ring"),
+    "population": dict(obs=4, act=1, hidden=[256, 256], batch=256, capacity=100_000, fill=20_000, n_agents=1024, act_fn="relu",
+                       label="InvertedPendulum shape: obs 4, act 1, 2x256, batch 256, 1024 independent agents sharded over ranks"),
+}
+
+
+def flops_per_update(obs, act, hidden, batch):
+    """Algorithmic FLOPs of one update: 2*MACs, no autograd waste."""
+    dims_p = [obs] + hidden + [2 * act]
+    dims_q = [obs + act] + hidden + [1]
+    FP = sum(a * b for a, b in zip(dims_p[:-1], dims_p[1:]))
+    FQ = sum(a * b for a, b in zip(dims_q[:-1], dims_q[1:]))
+    macs = 2 * FP + 6 * FQ + 2 * (2 * FQ - (obs + act) * hidden[0]) + 2 * (FQ - obs * hidden[0]) + (2 * FP - obs * hidden[0])
+    return 2 * macs * batch
+
+
+def param_counts(obs, act, hidden):
+    dims_p = [obs] + hidden + [2 * act]
+    dims_q = [obs + act] + hidden + [1]
+    NP = sum(a * b + b for a, b in zip(dims_p[:-1], dims_p[1:]))
+    NQ = sum(a * b + b for a, b in zip(dims_q[:-1], dims_q[1:]))
+    return NP + 2 * NQ, 2 * NQ
+
+
+def bytes_per_update(obs, act, hidden, batch):
+    """Algorithmic bytes: gather + read theta,theta_bar + r/w m,v + write theta, theta_bar."""
+    n_on, n_tg = param_counts(obs, act, hidden)
+    return batch * (2 * obs + act + 2) * 4 + 4 * (n_on + n_tg) + 16 * n_on + 4 * n_on + 4 * n_tg
+
+
+def make_config(w, rng, seed=0):
+    return {
+        "sac": {"gamma": 0.99, "tau": 0.005, "alpha": 0.1, "auto_entropy_tuning": True,
+                "actor_lr": 3e-4, "critic_lr": 3e-4, "alpha_lr": 3e-4},
+        "q_net": {"hidden_sizes": list(w["hidden"]), "hidden_layers_act": w["act_fn"], "output_activation": "identity"},
+        "policy_net": {"hidden_sizes": list(w["hidden"]), "hidden_layers_act": w["act_fn"], "output_activation": "identity",
+                       "log_std_min": -20, "log_std_max": 2, "action_scale": 1.0},
+        "buffer": {"capacity": w["capacity"]},
+        "train": {"gradient_steps_per_update": 1, "seed": seed, "batch_size": w["batch"], "warming_steps": 1000,
+                  "device": "cuda", "rng": rng},
+        "logger": {"enabled": False, "log_dir": "runs", "env_name": "Synthetic", "agent_name": "SAC", "run_name": "bench",
+                   "use_timestamp": False, "timestamp_format": "%Y", "flush_secs": 10, "log_episode_stats": False,
+                   "log_q_values": False, "save_model": {"enabled": False, "path": None}},
+    }
+
+
+def synth(n, obs, act, seed=0):
+    rng = np.random.default_rng(seed)
+    s = rng.standard_normal((n, obs), dtype=np.float32)
+    s2 = rng.standard_normal((n, obs), dtype=np.float32)
+    a = rng.uniform(-1, 1, (n, act)).astype(np.float32)
+    r = rng.standard_normal(n, dtype=np.float32)
+    d = (rng.random(n) < 0.01).astype(np.float32)
+    return s, a, r, s2, d
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class _Space:
+    def __init__(self, n):
+        self.shape = (n,)
+
+    def seed(self, s):
+        return [s]
+
+
+class FakeEnv:
+    """Shape-only environment: the benchmark feeds synthetic transitions, no simulator."""
+    spec = None
+
+    def __init__(self, obs, act):
+        self.observation_space, self.action_space = _Space(obs), _Space(act)
+
+    def reset(self, seed=None):
+        return np.zeros(self.observation_space.shape, np.float32), {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference(w, steps, warmup, budget_s=40.0, fill_cap=None):
+    """The reference's CPU update (torch-eager port, pinned bit-exact to the reference in tests/) on this box's
+    host cores. Comparator (A): full training_step incl. random.sample on the filled deque; (B): compute only."""
+    import torch
+    from oracle.torch_port import TorchPortSAC
+
+    cfg = make_config(w, "host")
+    cfg["train"]["device"] = "cpu"
+    port = TorchPortSAC(w["obs"], w["act"], cfg, capacity=w["capacity"])
+    n = w["fill"] if fill_cap is None else min(w["fill"], fill_cap)
+    s, a, r, s2, d = synth(n, w["obs"], w["act"])
+    t0 = time.perf_counter()
+    rl, dl = r.tolist(), (d != 0).tolist()
+    for i in range(n):
+        port.push(s[i], a[i], rl[i], s2[i], dl[i])
+    fill_s = time.perf_counter() - t0
+    nproc = os.cpu_count() or 1
+    best = None
+    for threads in sorted({1, max(1, nproc // 2), nproc}):
+        torch.set_num_threads(threads)
+        for _ in range(max(3, min(warmup, 10))):
+            port.training_step()
+        k, t0 = 0, time.perf_counter()
+        while k < steps and (time.perf_counter() - t0) < budget_s / 3:
+            port.training_step()
+            k += 1
+        dt = time.perf_counter() - t0
+        if best is None or k / dt > best["value"]:
+            best = {"value": k / dt, "cores": threads, "updates": k, "seconds": dt}
+    torch.set_num_threads(best["cores"])
+    batch = port.sample_batch(w["batch"])
+    for _ in range(3):
+        port.update_from_batch(*batch)
+    k, t0 = 0, time.perf_counter()
+    while k < steps and (time.perf_counter() - t0) < budget_s / 4:
+        port.update_from_batch(*batch)
+        k += 1
+    compute_only = k / (time.perf_counter() - t0)
+    return {"value": best["value"], "unit": "updates/s", "cores": best["cores"], "host_cores": nproc, "kind": "port", "updates": best["updates"],
+            "sample": f"{best['updates']} full training_step() calls (deque of {n} transitions, random.sample + eager torch + Adam) in {best['seconds']:.1f}s; "
+                      f"thread sweep {{1,{max(1, nproc // 2)},{nproc}}}, best kept",
+            "compute_only_value": compute_only, "fill_seconds": fill_s}
+
+
+# ---------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bipedal", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 2000)")
+    ap.add_argument("--chunk", type=int, default=1000, help="updates per kernel launch in the device-resident loop")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(3, args.warmup)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(args.steps, 600)
+        base = cpu_reference(w, steps, W, budget_s=120.0)
+        line = {"impl": "reference", "metric": "SAC updates/s", "value": base["value"], "unit": "updates/s", "n_gpus": args.gpus,
+                "steps": base["updates"], "warmup": W,
+                "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": {"workload": w["label"], "device": "host CPU"},
+                "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the update path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from sac.engine import UpdateEngine
+    from sac.replay_buffer import ReplayBuffer
+
+    n_agents_local = max(1, w["n_agents"] // world) if w["n_agents"] > 1 else 1
+    cfg_dev = make_config(w, "device", seed=rank)
+
+    # ---- device-resident throughput: engine + ring, device RNG ------------------------------------------
+    if w["n_agents"] == 1:
+        from sac.agent import SAC
+        agent = SAC(FakeEnv(w["obs"], w["act"]), cfg_dev)
+        eng, ring = agent.engine, agent.replay_buffer
+        s, a, r, s2, d = synth(w["fill"], w["obs"], w["act"], seed=rank)
+        ring.push_batch(s, a, r, s2, d)
+    else:
+        agent = None
+        eng = UpdateEngine(w["obs"], w["act"], cfg_dev, n_agents=n_agents_local)
+        g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        for tag in ("pi", "q1", "q2"):
+            for l in range(len(w["hidden"]) + 1):
+                v = eng.population_view(f"{tag}.W{l}")
+                bound = (6.0 / (v.shape[1] + v.shape[2])) ** 0.5           # xavier_uniform_, independent per agent
+                v.copy_((torch.rand(v.shape, device="cuda", generator=g) * 2 - 1) * bound)
+        eng.reset_state()
+        ring = ReplayBuffer(w["capacity"], w["obs"], w["act"], n_agents=n_agents_local)
+        s, a, r, s2, d = synth(w["fill"], w["obs"], w["act"], seed=rank)
+        ds, da, dr, ds2, dd = (torch.from_numpy(x).cuda() for x in (s, a, r, s2, d))
+        for ag in range(n_agents_local):
+            ring.push_device(ds, da, dr, ds2, dd, agent=ag)
+        eng.attach_ring(ring)
+    torch.cuda.synchronize()
+    gx, gy, smem = eng.grid()
+
+    def run_updates(n):
+        done = 0
+        while done < n:
+            c = min(args.chunk, n - done)
+            eng.update(None, None, None, c)
+            done += c
+
+    run_updates(W)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    run_updates(args.steps)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - l0
+    # a longer stretch for the clock sampler when K is small (kept outside the timed region)
+    if ms < 1500:
+        run_updates(int(min(50000, 1500 / max(ms / args.steps, 1e-3))))
+        torch.cuda.synchronize()
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    m = eng.metrics()
+    assert m["nonfinite"] == 0 and np.isfinite(m["q1_loss"]), f"non-finite update: {m}"
+    total_updates = args.steps * n_agents_local * world
+    value = total_updates / (ms / 1000.0)
+
+    # ---- e2e through the public API (host RNG, H2D + D2H per step) ---------------------------------------
+    e2e = None
+    if agent is not None:
+        agent.rng_mode = "host"
+        import random
+        random.seed(0)
+        torch.manual_seed(0)
+        n_e2e = args.e2e_steps or min(args.steps, 2000)
+        B, A = w["batch"], w["act"]
+
+        def api_step():
+            # every step: host index stream + normals -> pinned H2D -> fused kernel -> metrics D2H; the metrics
+            # of step t are read while step t+1 is already queued (software pipelining, still one read per step)
+            idx = np.asarray(agent.replay_buffer.draw_indices(B), dtype=np.int64)
+            return agent.engine.update_host_pipelined(idx, agent._normal(B), agent._normal(B), 1)
+
+        for _ in range(max(3, min(W, 50))):
+            api_step()
+        agent.engine.update_host_flush()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n_e2e):
+            mm = api_step()
+        mm = agent.engine.update_host_flush()
+        e1.record()
+        barrier()
+        assert mm["nonfinite"] == 0 and np.isfinite(mm["q1_loss"])
+        e_ms = e0.elapsed_time(e1)
+        wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": n_e2e * world / (e_ms / 1000.0), "unit": "updates/s", "h2d_bytes_per_step": B * 8 + 2 * B * A * 4,
+               "d2h_bytes_per_step": 184, "steps": n_e2e, "wall_s": wall,
+               "api": "SAC.training_step() host-RNG path: random.sample index stream + torch CPU normals -> sacx_update_host (pinned H2D, fused kernel, metrics D2H)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    fl = flops_per_update(w["obs"], w["act"], w["hidden"], w["batch"])
+    by = bytes_per_update(w["obs"], w["act"], w["hidden"], w["batch"])
+    per_gpu_rate = value / world                       # agent-updates/s on one GPU
+    ach_tf = fl * per_gpu_rate / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_update")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": traffic,
+                "kernel": "sacx_run_kernel (persistent fused update)", "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long loop)",
+                "flop_per_update": fl, "fp32_ffma_nominal_tflops": 148 * 128 * 2 * 1.965e-3,
+                "frac_of_fp32_ffma_nominal": ach_tf / (148 * 128 * 2 * 1.965e-3),
+                "hbm_view": {"bytes_per_update": by, "achieved_gbs": by * per_gpu_rate / 1e9, "peak_gbs": pk["hbm_gbs"],
+                             "frac": by * per_gpu_rate / 1e9 / pk["hbm_gbs"]},
+                "note": "FP32 FFMA path (parity contract rel 1e-4 rules out TF32/BF16 inputs); single agent at batch 256 is "
+                        "latency-bound: ~17 dependent phases per update separated by grid barriers"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference(w if w["n_agents"] == 1 else dict(w, fill=w["fill"]), 400, 10, budget_s=40.0)
+    line = {"metric": "SAC updates/s", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": w["label"], "agents_per_gpu": n_agents_local, "updates_per_launch": args.chunk,
+                                            "l2": "inputs larger than L2 (216 MB ring; each update gathers fresh random rows)",
+                                            "grid": [gx, gy], "smem_bytes": smem, "multi_gpu": "replicas only (independent agents per rank, no collective)"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "final_metrics": {k: m[k] for k in ("q1_loss", "policy_loss", "alpha", "updates")}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -163,6 +163,12 @@ int sacx_update(sacx_agent_t h, const int64_t* idx_dev, const float* eps1_dev, c
 /* same through HOST buffers (the e2e path): H2D of idx/eps, update, D2H of the metrics, sync */
 int sacx_update_host(sacx_agent_t h, const int64_t* idx_host, const float* eps1_host,
                      const float* eps2_host, int32_t n_steps, sacx_metrics* metrics_host);
+/* software-pipelined form of sacx_update_host: submits this update (H2D, kernel, metrics D2H) and returns the
+ * metrics of the PREVIOUS submission, so the host prepares update t+1 while update t runs.  *have_prev = 0 on the
+ * first call.  sacx_update_host_flush waits for the last submission and returns its metrics. */
+int sacx_update_host_pipelined(sacx_agent_t h, const int64_t* idx_host, const float* eps1_host, const float* eps2_host,
+                               int32_t n_steps, sacx_metrics* prev_metrics_host, int32_t* have_prev);
+int sacx_update_host_flush(sacx_agent_t h, sacx_metrics* last_metrics_host);
 /* multi-kernel variant of the same update (one launch per phase); used as a cross-check and
  * as the fallback schedule when a cooperative launch is unavailable */
 int sacx_update_staged(sacx_agent_t h, const int64_t* idx_dev, const float* eps1_dev,
@@ -204,6 +210,9 @@ int sacx_q_values_host(sacx_agent_t h, int32_t agent, const float* s_host, const
 
 int sacx_get_metrics(sacx_agent_t h, int32_t agent, sacx_metrics* metrics_host);   /* syncs */
 int sacx_sync(sacx_agent_t h);
+/* profiling aid: run n_steps fused updates (device RNG) recording, for every CTA and phase, clock64 at barrier
+ * arrival and release: out_host[n_steps][n_phases][n_ctas][2] */
+int sacx_debug_profile(sacx_agent_t h, int32_t n_steps, uint64_t* out_host, int64_t capacity, int32_t* n_phases, int32_t* n_ctas);
 /* number of kernels this handle has launched since create (bench.py's gpu_launches) */
 int64_t sacx_launch_count(sacx_agent_t h);
 

@@ -110,7 +110,7 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
   if (pe < 0) pe = hp.n_phases;
   RunArgs a = proto;
   a.arena = e->arena; a.agent_stride = e->stride; a.scal_off = e->scal_off; a.hp = e->hp;
-  a.n_agents = e->cfg.n_agents; a.barrier = e->d_barrier; a.ctas_per_agent = e->grid_x;
+  a.n_agents = e->cfg.n_agents; a.barrier = e->d_barrier; a.ctas_per_agent = e->grid_x; a.barrier_mode = e->barrier_mode;
   if (e->ring) {
     Ring* r = e->ring;
     a.ring = r->dev; a.ring_stride = r->stride; a.ring_capacity = r->cap;
@@ -122,7 +122,7 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
     void* args[] = {(void*)&dplan, (void*)&a};
     const void* fn = e->large ? (const void*)sacx_run_kernel<true> : (const void*)sacx_run_kernel<false>;
     if (coop) {
-      SACX_CUDA(cudaMemsetAsync(e->d_barrier, 0, sizeof(unsigned) * (size_t)std::max(1, (int)grid.y), e->stream));
+      SACX_CUDA(cudaMemsetAsync(e->d_barrier, 0, sizeof(unsigned) * 64 * (size_t)std::max(1, (int)grid.y), e->stream));
       SACX_CUDA(cudaLaunchCooperativeKernel(fn, grid, dim3(256), args, (size_t)e->smem_bytes, e->stream));
     } else {
       SACX_CUDA(cudaLaunchKernel(fn, grid, dim3(256), args, (size_t)e->smem_bytes, e->stream));
@@ -445,8 +445,9 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   }
   SACX_CUDA(cudaMalloc((void**)&e.d_plans, sizeof(Plan) * N_PLANS));
   SACX_CUDA(cudaMemcpy(e.d_plans, e.h_plans.data(), sizeof(Plan) * N_PLANS, cudaMemcpyHostToDevice));
-  SACX_CUDA(cudaMalloc((void**)&e.d_barrier, sizeof(unsigned) * 65536));
-  SACX_CUDA(cudaMemset(e.d_barrier, 0, sizeof(unsigned) * 65536));
+  SACX_CUDA(cudaMalloc((void**)&e.d_barrier, sizeof(unsigned) * 64 * 4096));
+  SACX_CUDA(cudaMemset(e.d_barrier, 0, sizeof(unsigned) * 64 * 4096));
+  { const char* bm = getenv("SACX_BARRIER"); e.barrier_mode = bm ? atoi(bm) : 1; }
   SACX_CUDA(cudaMallocHost((void**)&e.pinned_metrics, sizeof(sacx_metrics)));
   if ((rc = engine_init_scalars(&e))) { delete h; return rc; }
   *out = h;
@@ -463,6 +464,7 @@ int sacx_agent_destroy(sacx_agent_t h) {
   if (e.pinned_metrics) cudaFreeHost(e.pinned_metrics);
   if (e.pinned_io) cudaFreeHost(e.pinned_io);
   if (e.dev_io) cudaFree(e.dev_io);
+  for (auto& io : e.slots) { if (io.pinned) cudaFreeHost(io.pinned); if (io.dev) cudaFree(io.dev); if (io.done) cudaEventDestroy(io.done); }
   delete h;
   return SACX_OK;
 }
@@ -586,28 +588,90 @@ static int ensure_io(Engine& e, size_t bytes) {
   return SACX_OK;
 }
 
-int sacx_update_host(sacx_agent_t h, const int64_t* idx, const float* e1, const float* e2, int32_t n_steps, sacx_metrics* m) {
-  if (!h || n_steps <= 0) return fail(SACX_ERR_INVALID, "update_host: bad arguments");
-  Engine& e = h->e;
+// Two staging slots (pinned host + device + event) so that the host can prepare update t+1 while update t runs.
+static int host_update_submit(Engine& e, int slot, const int64_t* idx, const float* e1, const float* e2, int n_steps) {
+  Engine::IoSlot& io = e.slots[slot];
   const size_t nb = (size_t)n_steps * e.cfg.n_agents * e.cfg.batch_size;
   const size_t b_idx = idx ? nb * sizeof(i64) : 0;
   const size_t b_eps = nb * e.cfg.act_dim * sizeof(float);
-  const size_t total = b_idx + (e1 ? b_eps : 0) + (e2 ? b_eps : 0);
-  int rc = ensure_io(e, total + 256);
-  if (rc) return rc;
-  char* hp = (char*)e.pinned_io;
-  char* dp = (char*)e.dev_io;
+  const size_t total = b_idx + (e1 ? b_eps : 0) + (e2 ? b_eps : 0) + sizeof(AgentScalars) + 256;
+  if (io.busy) { SACX_CUDA(cudaEventSynchronize(io.done)); io.busy = false; }
+  if (total > io.bytes) {
+    if (io.pinned) cudaFreeHost(io.pinned);
+    if (io.dev) cudaFree(io.dev);
+    io.pinned = io.dev = nullptr; io.bytes = 0;
+    SACX_CUDA(cudaMallocHost(&io.pinned, total));
+    SACX_CUDA(cudaMalloc(&io.dev, total));
+    io.bytes = total;
+  }
+  if (!io.done) SACX_CUDA(cudaEventCreateWithFlags(&io.done, cudaEventDisableTiming));
+  char* hp = (char*)io.pinned;
+  char* dp = (char*)io.dev;
   size_t off = 0;
   const i64* d_idx = nullptr; const float* d_e1 = nullptr; const float* d_e2 = nullptr;
   if (idx) { memcpy(hp + off, idx, b_idx); d_idx = (const i64*)(dp + off); off += b_idx; }
   if (e1) { memcpy(hp + off, e1, b_eps); d_e1 = (const float*)(dp + off); off += b_eps; }
   if (e2) { memcpy(hp + off, e2, b_eps); d_e2 = (const float*)(dp + off); off += b_eps; }
   if (off) SACX_CUDA(cudaMemcpyAsync(dp, hp, off, cudaMemcpyHostToDevice, e.stream));
-  rc = do_update(h, (const int64_t*)d_idx, d_e1, d_e2, n_steps, false);
+  int rc = need_ring(e, idx == nullptr);
   if (rc) return rc;
-  if (m) return read_metrics(e, 0, m);
-  SACX_CUDA(cudaStreamSynchronize(e.stream));
+  RunArgs a;
+  memset(&a, 0, sizeof a);
+  a.idx_ext = d_idx; a.eps1_ext = d_e1; a.eps2_ext = d_e2;
+  rc = engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
+  if (rc) return rc;
+  // the step's result travels back right behind the kernel (metrics block of agent 0)
+  io.metrics_off = (off + 255) & ~(size_t)255;
+  SACX_CUDA(cudaMemcpyAsync(hp + io.metrics_off, e.arena + e.scal_off, sizeof(AgentScalars), cudaMemcpyDeviceToHost, e.stream));
+  SACX_CUDA(cudaEventRecord(io.done, e.stream));
+  io.busy = true;
   return SACX_OK;
+}
+
+static int host_update_collect(Engine& e, int slot, sacx_metrics* out) {
+  Engine::IoSlot& io = e.slots[slot];
+  if (!io.pinned) return fail(SACX_ERR_INVALID, "no update was submitted on this slot");
+  if (io.busy) { SACX_CUDA(cudaEventSynchronize(io.done)); io.busy = false; }
+  if (out) {
+    AgentScalars s;
+    memcpy(&s, (char*)io.pinned + io.metrics_off, sizeof s);
+    out->q1_loss = s.metrics[0]; out->q2_loss = s.metrics[1]; out->policy_loss = s.metrics[2]; out->alpha_loss = s.metrics[3];
+    out->alpha = s.metrics[4]; out->log_alpha = s.metrics[5]; out->q1_mean = s.metrics[6]; out->q2_mean = s.metrics[7];
+    out->logpi_mean = s.metrics[8]; out->y_mean = s.metrics[9];
+    out->nonfinite = s.nonfinite; out->reserved = 0; out->updates = s.updates;
+  }
+  return SACX_OK;
+}
+
+int sacx_update_host(sacx_agent_t h, const int64_t* idx, const float* e1, const float* e2, int32_t n_steps, sacx_metrics* m) {
+  if (!h || n_steps <= 0) return fail(SACX_ERR_INVALID, "update_host: bad arguments");
+  Engine& e = h->e;
+  const int slot = (int)(e.host_calls++ & 1);
+  int rc = host_update_submit(e, slot, idx, e1, e2, n_steps);
+  if (rc) return rc;
+  return m ? host_update_collect(e, slot, m) : SACX_OK;     // without metrics the call stays asynchronous
+}
+
+int sacx_update_host_pipelined(sacx_agent_t h, const int64_t* idx, const float* e1, const float* e2, int32_t n_steps,
+                               sacx_metrics* prev_metrics, int32_t* have_prev) {
+  if (!h || n_steps <= 0) return fail(SACX_ERR_INVALID, "update_host_pipelined: bad arguments");
+  Engine& e = h->e;
+  const int slot = (int)(e.host_calls++ & 1);
+  int rc = host_update_submit(e, slot, idx, e1, e2, n_steps);
+  if (rc) return rc;
+  const bool prev = e.slots[slot ^ 1].pinned != nullptr && e.pipelined_pending;
+  if (have_prev) *have_prev = prev ? 1 : 0;
+  if (prev) rc = host_update_collect(e, slot ^ 1, prev_metrics);
+  e.pipelined_pending = true;
+  return rc;
+}
+
+int sacx_update_host_flush(sacx_agent_t h, sacx_metrics* last_metrics) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  Engine& e = h->e;
+  if (e.host_calls == 0) return fail(SACX_ERR_INVALID, "no host update was submitted");
+  e.pipelined_pending = false;
+  return host_update_collect(e, (int)((e.host_calls - 1) & 1), last_metrics);
 }
 
 int sacx_sample_batch(sacx_agent_t h, const int64_t* idx) {
@@ -773,6 +837,32 @@ int sacx_get_metrics(sacx_agent_t h, int32_t agent, sacx_metrics* m) {
   int rc = ensure_io(h->e, 0);
   if (rc) return rc;
   return read_metrics(h->e, agent, m);
+}
+
+int sacx_debug_profile(sacx_agent_t h, int32_t n_steps, uint64_t* out_host, int64_t capacity, int32_t* n_phases, int32_t* n_ctas) {
+  if (!h || !out_host || n_steps <= 0) return fail(SACX_ERR_INVALID, "debug_profile: bad arguments");
+  Engine& e = h->e;
+  int rc = need_ring(e, true);
+  if (rc) return rc;
+  const int np = e.h_plans[PLAN_FUSED].n_phases;
+  const size_t words = (size_t)n_steps * np * e.grid_x * 10;
+  if ((int64_t)words > capacity) return fail(SACX_ERR_INVALID, "debug_profile: output too small");
+  unsigned long long* d = nullptr;
+  SACX_CUDA(cudaMalloc((void**)&d, words * 8));
+  SACX_CUDA(cudaMemset(d, 0, words * 8));
+  RunArgs a; memset(&a, 0, sizeof a);
+  a.dbg = d;
+  a.dbg2 = d + (size_t)n_steps * np * e.grid_x * 2;
+  rc = engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
+  if (!rc) {
+    cudaError_t ce = cudaStreamSynchronize(e.stream);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out_host, d, words * 8, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) rc = fail(SACX_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  cudaFree(d);
+  if (n_phases) *n_phases = np;
+  if (n_ctas) *n_ctas = e.grid_x;
+  return rc;
 }
 
 int sacx_sync(sacx_agent_t h) {

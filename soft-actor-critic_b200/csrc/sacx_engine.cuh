@@ -48,7 +48,7 @@ struct Engine {
   sacx_config cfg;
   int n_sms = 0, max_ctas = 0;
   bool large = false;
-  int grid_x = 1, grid_y = 1, smem_bytes = 0;
+  int grid_x = 1, grid_y = 1, smem_bytes = 0, barrier_mode = 1;
   std::vector<sacx_tensor_desc> lay;
   i64 cur = 0, stride = 0;
   NetLayout pi, q1, q2;
@@ -70,6 +70,10 @@ struct Engine {
   size_t pinned_io_bytes = 0;
   void* dev_io = nullptr;
   size_t dev_io_bytes = 0;
+  struct IoSlot { void* pinned = nullptr; void* dev = nullptr; size_t bytes = 0, metrics_off = 0; cudaEvent_t done = nullptr; bool busy = false; };
+  IoSlot slots[2];
+  unsigned long long host_calls = 0;
+  bool pipelined_pending = false;
   cudaStream_t stream = 0;
   Ring* ring = nullptr;
   long long launches = 0;
@@ -230,10 +234,11 @@ struct Engine {
     o.tiles_n = (o.N + BNt() - 1) / BNt();
     o.ntiles = tm * o.tiles_n;
     o.cfg = large ? 1 : 0;
-    const bool a_ck = (o.a_sk == 1), b_ck = (o.b_sk == 1);
-    const int ao = a_ck ? o.a_sm : o.a_sk, bo = b_ck ? o.b_sn : o.b_sk;
-    o.a_vec = (o.a % 4 == 0) && (ao % 4 == 0 || (a_ck && o.M == 1));
-    o.b_vec = (o.b % 4 == 0) && (bo % 4 == 0 || (b_ck && o.N == 1));
+    // operand orientation follows the epilogue kind (forward: A,B row-major; dA: B k-major; dW: both k-major)
+    const bool a_km = (o.epi == EPI_DW), b_km = (o.epi != EPI_FWD);
+    const int ao = a_km ? o.a_sk : o.a_sm, bo = b_km ? o.b_sk : o.b_sn;
+    o.a_vec = (o.a % 4 == 0) && (ao % 4 == 0);
+    o.b_vec = (o.b % 4 == 0) && (bo % 4 == 0);
   }
   Op gemm_fwd(const NetLayout& n, int l, i64 wshift, i64 x, int ld_x, const ActSet& as) const {
     Op o = blank(OP_GEMM);
@@ -292,34 +297,27 @@ struct Engine {
     o.ntiles = row_tiles();
     return o;
   }
-  Op op_q_target() const {
+  // mode: 1 target y, 2 critic delta, 3 both chained on the same row (fused plan)
+  Op op_q_row(int mode) const {
     Op o = blank(OP_Q_ROW);
     const int L = q1.L();
-    o.act_out = q1.act_o;
+    o.mode = mode; o.act = q1.act_h; o.act_out = q1.act_o;
     for (int c = 0; c < 2; ++c) {
       const NetLayout& n = c ? q2 : q1;
-      o.o[c] = a_qt[c].h[L - 1];
-      o.o[2 + c] = n.W[L] - q1.begin + T0;
-      o.o[4 + c] = n.b[L] - q1.begin + T0;
-      o.o[10 + c] = b_tq[c];
+      if (mode & 1) {
+        o.o[c] = a_qt[c].h[L - 1];
+        o.o[2 + c] = n.W[L] - q1.begin + T0;
+        o.o[4 + c] = n.b[L] - q1.begin + T0;
+        o.o[10 + c] = b_tq[c];
+      }
+      if (mode & 2) {
+        o.o[12 + c] = a_q[c].h[L - 1]; o.o[14 + c] = a_q[c].aux(L - 1);
+        o.o[16 + c] = n.W[L]; o.o[18 + c] = n.b[L];
+        o.o[20 + c] = b_q[c]; o.o[22 + c] = b_dout[c]; o.o[24 + c] = d_q[c][L - 1]; o.o[26 + c] = b_loss[c];
+      }
     }
-    o.i[0] = a_qt[0].ld[L - 1]; o.i[1] = q1.dims[L];
-    o.o[6] = b_r; o.o[7] = b_d; o.o[8] = b_lp2; o.o[9] = b_y;
-    o.ntiles = row_tiles();
-    return o;
-  }
-  Op op_critic_row() const {
-    Op o = blank(OP_CRITIC_ROW);
-    const int L = q1.L();
-    o.act = q1.act_h; o.act_out = q1.act_o;
-    for (int c = 0; c < 2; ++c) {
-      const NetLayout& n = c ? q2 : q1;
-      o.o[c] = a_q[c].h[L - 1]; o.o[2 + c] = a_q[c].aux(L - 1);
-      o.o[4 + c] = n.W[L]; o.o[6 + c] = n.b[L];
-      o.o[9 + c] = b_q[c]; o.o[11 + c] = b_dout[c]; o.o[13 + c] = d_q[c][L - 1]; o.o[15 + c] = b_loss[c];
-    }
-    o.o[8] = b_y;
     o.i[0] = a_q[0].ld[L - 1]; o.i[1] = q1.dims[L];
+    o.o[6] = b_r; o.o[7] = b_d; o.o[8] = b_lp2; o.o[9] = b_y;
     o.ntiles = row_tiles();
     return o;
   }
@@ -428,7 +426,7 @@ struct Engine {
       for (int c = 0; c < 2; ++c)
         pb.add(gemm_fwd(c ? q2 : q1, l, T0 - q1.begin, l ? a_qt[c].h[l - 1] : x_s2, l ? a_qt[c].ld[l - 1] : ldx, a_qt[c]));
     }
-    pb.phase(); pb.add(op_q_target());
+    pb.phase(); pb.add(op_q_row(1));
   }
   void emit_critic(PB& pb, int flags) const {
     for (int l = 0; l < q1.L(); ++l) {
@@ -436,7 +434,7 @@ struct Engine {
       if (l == 0 && (flags & DW_ADAM)) pb.add(op_prologue((1 << OPT_Q1) | (1 << OPT_Q2)));
       for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l, 0, l ? a_q[c].h[l - 1] : x_sa, l ? a_q[c].ld[l - 1] : ldx, a_q[c]));
     }
-    pb.phase(); pb.add(op_critic_row());
+    pb.phase(); pb.add(op_q_row(2));
     for (int k = 0; k < bwd_stages(q1); ++k) {
       pb.phase();
       for (int c = 0; c < 2; ++c)
@@ -477,24 +475,24 @@ struct Engine {
     pb.phase();
     pb.add(op_prologue(7));
     if (gather) pb.add(op_gather());
-    const int Lm = std::max(pi.L(), q1.L());
-    for (int l = 0; l < Lm; ++l) {     // pi(s'), pi(s), Q1(s,a), Q2(s,a) side by side
+    // Forward work off the critical chain (critics on (s,a)) rides along with later phases so that no phase
+    // needs two waves of tiles: pi(s'), pi(s) layer by layer; then heads + Q(s,a) layer 0; then the target critics
+    // layer by layer with Q(s,a)'s deeper layers next to them.
+    for (int l = 0; l < pi.L(); ++l) {
       pb.phase();
-      if (l < pi.L()) {
-        pb.add(gemm_fwd(pi, l, 0, l ? a_pit.h[l - 1] : x_s2, l ? a_pit.ld[l - 1] : ldx, a_pit));
-        pb.add(gemm_fwd(pi, l, 0, l ? a_pia.h[l - 1] : x_pi, l ? a_pia.ld[l - 1] : ldx, a_pia));
-      }
-      if (l < q1.L())
-        for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l, 0, l ? a_q[c].h[l - 1] : x_sa, l ? a_q[c].ld[l - 1] : ldx, a_q[c]));
+      pb.add(gemm_fwd(pi, l, 0, l ? a_pit.h[l - 1] : x_s2, l ? a_pit.ld[l - 1] : ldx, a_pit));
+      pb.add(gemm_fwd(pi, l, 0, l ? a_pia.h[l - 1] : x_pi, l ? a_pia.ld[l - 1] : ldx, a_pia));
     }
     pb.phase(); pb.add(op_pi_head(false)); pb.add(op_pi_head(true));
+    for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, 0, 0, x_sa, ldx, a_q[c]));
     for (int l = 0; l < q1.L(); ++l) {
       pb.phase();
       for (int c = 0; c < 2; ++c)
         pb.add(gemm_fwd(c ? q2 : q1, l, T0 - q1.begin, l ? a_qt[c].h[l - 1] : x_s2, l ? a_qt[c].ld[l - 1] : ldx, a_qt[c]));
+      if (l + 1 < q1.L())
+        for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l + 1, 0, a_q[c].h[l], a_q[c].ld[l], a_q[c]));
     }
-    pb.phase(); pb.add(op_q_target());
-    pb.phase(); pb.add(op_critic_row());
+    pb.phase(); pb.add(op_q_row(3));      // target y and critic delta chained on the same row: one phase
     for (int k = 0; k < bwd_stages(q1); ++k) {   // critic Adam with the Polyak update fused behind it (K10)
       pb.phase();
       for (int c = 0; c < 2; ++c)

@@ -12,18 +12,32 @@ constexpr int WSM_FLOATS = 8 * 4 * SACX_MAX_ACT;               // per-warp scrat
 // Barrier among the gridDim.x CTAs that work on the same agent (cooperative launch => co-resident).
 // Monotonic counter, release/acquire at gpu scope; thread 0's fences make the CTA's global writes
 // visible and drop stale L1 lines before the other threads continue.
-__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned& epoch) {
+__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned& epoch, int mode) {
   __syncthreads();
   if (gridDim.x > 1) {
     if (threadIdx.x == 0) {
       epoch += gridDim.x;
-      __threadfence();
-      atomicAdd(counter, 1u);
       unsigned v;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      } while (v < epoch);
-      __threadfence();
+      if (mode == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < epoch);
+        __threadfence();
+      } else {
+        // arrivals on one line, release flag on another: pollers do not queue behind the atomics
+        unsigned* flag = counter + 32;
+        unsigned old;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+        if (old + 1 == epoch) {
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+        } else {
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          } while ((int)(v - epoch) < 0);
+        }
+      }
     }
     __syncthreads();
   }
@@ -53,17 +67,18 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
   const Op* ops = cached ? (sops - op_lo) : gplan->ops;
 
   unsigned epoch = 0;
-  unsigned* counter = args.barrier + blockIdx.y;
+  unsigned* counter = args.barrier + blockIdx.y * 64;
   for (int agent = blockIdx.y; agent < args.n_agents; agent += gridDim.y) {
     float* base = args.arena + (i64)agent * args.agent_stride;
     AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
-    RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT};
-    EpiCtx ec{base, scal, &args.hp};
+    RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, C::SMEM_FLOATS};
+    EpiCtx ec{base, scal, &args.hp, nullptr};
     const bool last_agent = (agent + (int)gridDim.y >= args.n_agents);
     for (int step = 0; step < args.n_steps; ++step) {
       rc.step = step;
       for (int p = args.phase_begin; p < args.phase_end; ++p) {
         const Phase ph = sphase[p];
+        if (args.dbg2) ec.t = args.dbg2 + (((size_t)step * (args.phase_end - args.phase_begin) + (p - args.phase_begin)) * gridDim.x + blockIdx.x) * 8;
         for (int t = blockIdx.x; t < ph.ntiles; t += gridDim.x) {
           int oi = ph.op0;
           while (oi + 1 < ph.op0 + ph.nops && t >= ops[oi + 1].tile0) ++oi;
@@ -72,11 +87,10 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
           switch (op.type) {
             case OP_GEMM: gemm_tile<C>(op, ec, lt, gsm); break;
             case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
-            case OP_PI_HEAD: op_pi_head(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
-            case OP_Q_ROW: op_q_target(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
-            case OP_CRITIC_ROW: op_critic_row(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
-            case OP_ACTOR_Q: op_actor_q(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
-            case OP_ACTOR_BWD: op_actor_bwd(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
+            case OP_PI_HEAD: tile_pi_head(op, rc, lt); __syncthreads(); break;
+            case OP_Q_ROW: tile_q_row(op, rc, lt); __syncthreads(); break;
+            case OP_ACTOR_Q: tile_actor_q(op, rc, lt); __syncthreads(); break;
+            case OP_ACTOR_BWD: tile_actor_bwd(op, rc, lt); __syncthreads(); break;
             case OP_PROLOGUE: if (tid == 0) op_prologue(op, rc); break;
             case OP_FINAL: if (warp == 0) op_final(op, rc, lane); break;
             case OP_POLYAK: op_polyak(op, rc, lt); break;
@@ -85,7 +99,13 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
           }
         }
         const bool very_last = last_agent && (step + 1 == args.n_steps) && (p + 1 == args.phase_end);
-        if (!very_last) group_barrier(counter, epoch);
+        unsigned long long* dbg = nullptr;
+        if (args.dbg && tid == 0) {
+          dbg = args.dbg + (((size_t)step * (args.phase_end - args.phase_begin) + (p - args.phase_begin)) * gridDim.x + blockIdx.x) * 2;
+          dbg[0] = clock64();
+        }
+        if (!very_last) group_barrier(counter, epoch, args.barrier_mode);
+        if (dbg) dbg[1] = clock64();
       }
     }
   }

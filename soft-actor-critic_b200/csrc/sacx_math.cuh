@@ -13,7 +13,7 @@ namespace sacx {
 #define SELU_ALPHA 1.6732632423543772848170429916717f
 #define SELU_SCALE 1.0507009873554804934193349852946f
 
-__device__ __forceinline__ float act_fwd(int act, float z) {
+__device__ __noinline__ float act_fwd_general(int act, float z) {
   switch (act) {
     case SACX_ACT_RELU: return fmaxf(z, 0.f);
     case SACX_ACT_TANH: return tanhf(z);
@@ -25,13 +25,20 @@ __device__ __forceinline__ float act_fwd(int act, float z) {
   }
 }
 
+// ReLU / identity (every shipped config) stay inline; the transcendental activations are one out-of-line call
+__device__ __forceinline__ float act_fwd(int act, float z) {
+  if (act == SACX_ACT_RELU) return fmaxf(z, 0.f);
+  if (act == SACX_ACT_IDENTITY) return z;
+  return act_fwd_general(act, z);
+}
+
 // activations whose derivative is evaluated from the pre-activation z (the others use the output h)
 __host__ __device__ __forceinline__ bool act_needs_z(int act) {
   return act == SACX_ACT_ELU || act == SACX_ACT_GELU || act == SACX_ACT_SELU;
 }
 
 // d act / d z given aux = z (elu, gelu, selu) or aux = h (relu, tanh, leaky_relu, identity)
-__device__ __forceinline__ float act_dz(int act, float aux) {
+__device__ __noinline__ float act_dz_general(int act, float aux) {
   switch (act) {
     case SACX_ACT_RELU: return aux > 0.f ? 1.f : 0.f;
     case SACX_ACT_TANH: return 1.f - aux * aux;
@@ -45,6 +52,12 @@ __device__ __forceinline__ float act_dz(int act, float aux) {
     case SACX_ACT_SELU: return aux > 0.f ? SELU_SCALE : (SELU_SCALE * SELU_ALPHA) * expf(aux);
     default: return 1.f;
   }
+}
+
+__device__ __forceinline__ float act_dz(int act, float aux) {
+  if (act == SACX_ACT_RELU) return aux > 0.f ? 1.f : 0.f;
+  if (act == SACX_ACT_IDENTITY) return 1.f;
+  return act_dz_general(act, aux);
 }
 
 // derivative when both z and h are at hand (output layers)

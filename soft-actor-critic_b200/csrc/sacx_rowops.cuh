@@ -1,37 +1,79 @@
-// Row-wise operations of the SAC update: one warp owns one batch row. These are the narrow output
-// layers (policy head N=2A, critic head N=1) and everything the reference computes right after them:
-// the tanh-squashed Gaussian rsample/log_prob (sac/models.py:79-87), the soft Bellman target
-// (sac/agent.py:207-210), the critic/actor loss gradients and the closed-form head backward
-// (SURVEY section 8 a5/a8), the temperature step (agent.py:263-280). Reductions use warp shuffles.
+// Row-wise operations of the SAC update: one warp owns one batch row, one CTA tile = 8 rows. These are the
+// narrow output layers (policy head N=2A, critic head N=1) and everything the reference computes right
+// after them: the tanh-squashed Gaussian rsample/log_prob (sac/models.py:79-87), the soft Bellman target
+// (sac/agent.py:207-210), the critic/actor loss gradients and the closed-form head backward (SURVEY
+// section 8 a5/a8), the temperature step (agent.py:263-280).
+//
+// Latency structure (what the profile asked for): the small weight matrices a tile needs are staged once
+// per CTA into shared memory with cp.async while every warp's own row (last hidden activations, saved
+// activations) travels into registers, so a tile pays ONE L2 round trip; all dot products then read
+// shared memory / registers and reduce with warp shuffles.
 #pragma once
+#include "sacx_gemm.cuh"
 #include "sacx_math.cuh"
 #include "sacx_types.cuh"
 
 namespace sacx {
 
-constexpr int ROWS_PER_TILE = 8;   // 256 threads = 8 warps = 8 rows
+constexpr int ROWS_PER_TILE = 8;     // 256 threads = 8 warps = 8 rows
+constexpr int ROW_MAXK = 256;        // widest last-hidden layer handled by the register-resident path
+constexpr int ROW_KREG = ROW_MAXK / 128;
 
 struct RowCtx {
   float* base;
   AgentScalars* scal;
   const RunArgs* args;
   int agent, step;
-  float* wsm;          // per-warp shared scratch, 2*SACX_MAX_ACT*2 floats
+  float* wsm;          // per-warp shared scratch, 4*SACX_MAX_ACT floats
+  float* tsm;          // CTA-wide shared staging area (aliases the GEMM ring), tsm_floats floats
+  int tsm_floats;
 };
 
-// dot(h[0:K], w[0:K]) over the lanes of a warp (all lanes receive the result)
-__device__ __forceinline__ float warp_dot(const float* __restrict__ h, const float* __restrict__ w, int K, int lane) {
-  float s = 0.f;
-  if (((K & 3) == 0) && ((((uintptr_t)h | (uintptr_t)w) & 15) == 0)) {
-    for (int k = lane * 4; k < K; k += 128) {
-      const float4 a = __ldcg(reinterpret_cast<const float4*>(h + k));
-      const float4 b = __ldcg(reinterpret_cast<const float4*>(w + k));
-      s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
-    }
+// ---- staging helpers -------------------------------------------------------------------------------
+// copy n floats global -> shared by the whole CTA (cp.async when 16B-aligned, scalar otherwise)
+__device__ __forceinline__ void stage_vec(float* dst, const float* src, int n) {
+  if (((n & 3) == 0) && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 15) == 0)) {
+    for (int i = threadIdx.x * 4; i < n; i += 1024) cp_async16(dst + i, src + i, 16);
   } else {
-    for (int k = lane; k < K; k += 32) s = fmaf(__ldcg(h + k), __ldcg(w + k), s);
+    for (int i = threadIdx.x; i < n; i += 256) dst[i] = __ldcg(src + i);
   }
-  return warp_sum(s);
+}
+__device__ __forceinline__ void stage_finish() {
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+// a row of K floats (K <= ROW_MAXK, row 16B-aligned, K % 4 == 0) in registers: lane owns float4 chunks lane + 32*i
+struct RowReg {
+  float4 v[ROW_KREG];
+};
+__device__ __forceinline__ bool row_fast(int K, const float* p) { return K <= ROW_MAXK && (K & 3) == 0 && ((((uintptr_t)p) & 15) == 0); }
+__device__ __forceinline__ void row_load(RowReg& r, const float* __restrict__ p, int K, int lane) {
+#pragma unroll
+  for (int i = 0; i < ROW_KREG; ++i) {
+    const int k = (lane + 32 * i) * 4;
+    r.v[i] = (k < K) ? __ldcg(reinterpret_cast<const float4*>(p + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// dot(row in registers, w in shared memory)
+__device__ __forceinline__ float row_dot_partial(const RowReg& r, const float* __restrict__ w, int K, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_KREG; ++i) {
+    const int k = (lane + 32 * i) * 4;
+    if (k < K) {
+      const float4 b = *reinterpret_cast<const float4*>(w + k);
+      s = fmaf(r.v[i].x, b.x, s); s = fmaf(r.v[i].y, b.y, s); s = fmaf(r.v[i].z, b.z, s); s = fmaf(r.v[i].w, b.w, s);
+    }
+  }
+  return s;
+}
+// generic fallback: both operands wherever they live
+__device__ __forceinline__ float warp_dot_any(const float* __restrict__ h, const float* __restrict__ w, int K, int lane) {
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(__ldcg(h + k), w[k], s);
+  return s;
 }
 
 // ---------------------------------------------------------------- OP_GATHER
@@ -45,12 +87,12 @@ __device__ __forceinline__ void op_gather(const Op& op, const RowCtx& c, int row
   const i64 pushes = meta->pushes;
   const i64 cap = a.ring_capacity;
   const i64 n = pushes < cap ? pushes : cap;
-  const i64 upd = __ldcg(&c.scal->updates);
   i64 j;
   if (a.idx_ext) {
     j = a.idx_ext[((i64)c.step * a.n_agents + c.agent) * hp.B + row];
   } else {
     // throughput mode: position (global row) of a keyed bijection on [0, n) -> distinct indices
+    const i64 upd = __ldcg(&c.scal->updates);
     j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, hp.seed,
                            (unsigned long long)upd, (uint32_t)c.agent);
   }
@@ -81,36 +123,53 @@ __device__ __forceinline__ void op_gather(const Op& op, const RowCtx& c, int row
 // ---------------------------------------------------------------- OP_PI_HEAD
 // o[0]=h(last hidden) o[1]=W_L o[2]=b_L o[3]=X(dest, action at col obs+j) o[4]=lp o[5]=eps buf
 // o[6]=tz o[7]=se o[8]=mask o[9]=headz (each -1 when not saved)   i[0]=ldh i[1]=K i[2]=ldx   mode: 1 target / 2 actor
-__device__ __forceinline__ void op_pi_head(const Op& op, const RowCtx& c, int row, int lane) {
+__device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int tile) {
   const RunArgs& a = *c.args;
   const Hyper& hp = a.hp;
-  if (row >= hp.B) return;
   float* base = c.base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = tile * ROWS_PER_TILE + warp;
   const int A = hp.act, K = op.i[1];
+  const bool in = row < hp.B;
   const float* h = base + op.o[0] + (i64)row * op.i[0];
-  const float* W = base + op.o[1];
-  const float* bias = base + op.o[2];
+  const float* Wg = base + op.o[1];
+  const bool staged = (2 * A * K + 2 * A) <= c.tsm_floats;
+  const bool fast = staged && row_fast(K, h) && row_fast(K, Wg);
+  float* Ws = c.tsm;
+  float* bs = c.tsm + 2 * A * K;
+  RowReg hr;
+  const float* eps_ext = (op.mode == 1) ? a.eps1_ext : a.eps2_ext;
+  float e_pre = 0.f;
+  if (in && lane < A) {
+    if (eps_ext) e_pre = eps_ext[(((i64)c.step * a.n_agents + c.agent) * hp.B + row) * A + lane];
+    else e_pre = philox_normal(hp.seed, (unsigned long long)__ldcg(&c.scal->updates), op.mode, (uint32_t)(hp.row0_global + row),
+                               (uint32_t)lane, (uint32_t)c.agent);
+  }
+  if (staged) {
+    stage_vec(Ws, Wg, 2 * A * K);
+    for (int i = threadIdx.x; i < 2 * A; i += 256) bs[i] = __ldcg(base + op.o[2] + i);
+    if (fast && in) row_load(hr, h, K, lane);
+    stage_finish();
+  }
+  if (!in) return;
+  const float* W = staged ? Ws : Wg;
   float* hs = c.wsm;                      // head post-activation [2A], then pre-activation [2A]
   for (int j = 0; j < 2 * A; ++j) {
-    const float z = warp_dot(h, W + (i64)j * K, K, lane) + __ldcg(bias + j);
+    const float part = fast ? row_dot_partial(hr, W + (i64)j * K, K, lane) : warp_dot_any(h, W + (i64)j * K, K, lane);
+    const float z = warp_sum(part) + (staged ? bs[j] : __ldcg(base + op.o[2] + j));
     if (lane == 0) {
       hs[j] = act_fwd(op.act_out, z);
       hs[2 * SACX_MAX_ACT + j] = z;
     }
   }
   __syncwarp();
-  const float* eps_ext = (op.mode == 1) ? a.eps1_ext : a.eps2_ext;
-  const i64 upd = __ldcg(&c.scal->updates);
   float lp_part = 0.f;
   bool bad = false;
   for (int j = lane; j < A; j += 32) {
     const float mu = hs[j], ls_raw = hs[A + j];
     const float ls = fminf(fmaxf(ls_raw, hp.log_std_min), hp.log_std_max);
     const float sd = expf(ls);
-    float e;
-    if (eps_ext) e = eps_ext[(((i64)c.step * a.n_agents + c.agent) * hp.B + row) * A + j];
-    else e = philox_normal(hp.seed, (unsigned long long)upd, op.mode, (uint32_t)(hp.row0_global + row), (uint32_t)j,
-                           (uint32_t)c.agent);
+    const float e = e_pre;
     base[op.o[5] + (i64)row * A + j] = e;
     const float z = mu + e * sd;                       // Normal.rsample: loc + eps * scale
     const float tz = tanhf(z);
@@ -136,99 +195,222 @@ __device__ __forceinline__ void op_pi_head(const Op& op, const RowCtx& c, int ro
   __syncwarp();
 }
 
-// ---------------------------------------------------------------- OP_Q_ROW (target)
-// o[0..1]=hqt(last hidden) o[2..3]=Wt_L o[4..5]=bt_L o[6]=r o[7]=d o[8]=lp2 o[9]=y o[10..11]=tq   i[0]=ldh i[1]=K
-__device__ __forceinline__ void op_q_target(const Op& op, const RowCtx& c, int row, int lane) {
+// ---------------------------------------------------------------- OP_Q_ROW: target y (mode & 1) and / or critic delta (mode & 2)
+// target: o[0..1]=hqt(last hidden) o[2..3]=Wt_L o[4..5]=bt_L o[6]=r o[7]=d o[8]=lp2 o[9]=y o[10..11]=tq
+// critic: o[12..13]=hq(last hidden) o[14..15]=aux(z or h) o[16..17]=W_L o[18..19]=b_L o[20..21]=q out o[22..23]=dout
+//         o[24..25]=delta(last hidden) o[26..27]=lossrow          i[0]=ldh i[1]=K      (y read from o[9] or y_ext)
+__device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile) {
   const Hyper& hp = c.args->hp;
-  if (row >= hp.B) return;
   float* base = c.base;
-  float tq[2];
-#pragma unroll
-  for (int n = 0; n < 2; ++n) {
-    const float z = warp_dot(base + op.o[n] + (i64)row * op.i[0], base + op.o[2 + n], op.i[1], lane) + __ldcg(base + op.o[4 + n]);
-    tq[n] = act_fwd(op.act_out, z);
-  }
-  if (lane == 0) {
-    const float alpha = __ldcg(&c.scal->alpha_f32);
-    const float r = __ldcg(base + op.o[6] + row), d = __ldcg(base + op.o[7] + row), lp2 = __ldcg(base + op.o[8] + row);
-    const float minq = fminf(tq[0], tq[1]);
-    // y = r + gamma * (1 - d) * (minq - alpha * logpi')      (agent.py:208-210)
-    const float y = r + (hp.gamma * (1.f - d)) * (minq - alpha * lp2);
-    base[op.o[9] + row] = y;
-    base[op.o[10] + row] = tq[0];
-    base[op.o[11] + row] = tq[1];
-  }
-}
-
-// ---------------------------------------------------------------- OP_CRITIC_ROW
-// o[0..1]=hq(last hidden) o[2..3]=aux(z or h) o[4..5]=W_L o[6..7]=b_L o[8]=y o[9..10]=q out
-// o[11..12]=dout o[13..14]=delta(last hidden) o[15..16]=lossrow    i[0]=ldh i[1]=K
-__device__ __forceinline__ void op_critic_row(const Op& op, const RowCtx& c, int row, int lane) {
-  const Hyper& hp = c.args->hp;
-  if (row >= hp.B) return;
-  float* base = c.base;
-  const float y = c.args->y_ext ? c.args->y_ext[row] : __ldcg(base + op.o[8] + row);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = tile * ROWS_PER_TILE + warp;
+  const bool in = row < hp.B;
   const int K = op.i[1], ld = op.i[0];
-#pragma unroll
-  for (int n = 0; n < 2; ++n) {
-    const float* W = base + op.o[4 + n];
-    const float z = warp_dot(base + op.o[n] + (i64)row * ld, W, K, lane) + __ldcg(base + op.o[6 + n]);
-    const float q = act_fwd(op.act_out, z);
-    const float diff = q - y;
-    // d mse / d q = 2 (q - y) / B_global; through the output activation
-    const float dout = (2.f * diff / (float)hp.B_global) * act_dz2(op.act_out, z, q);
-    if (lane == 0) {
-      base[op.o[9 + n] + row] = q;
-      base[op.o[11 + n] + row] = dout;
-      base[op.o[15 + n] + row] = diff * diff;
+  const bool do_t = op.mode & 1, do_c = op.mode & 2;
+  const bool staged = 4 * K <= c.tsm_floats;
+  float* Ws = c.tsm;                          // [4][K]: target W x2, online W x2
+  const float* hp_t[2] = {base + (do_t ? op.o[0] : 0) + (i64)row * ld, base + (do_t ? op.o[1] : 0) + (i64)row * ld};
+  const float* hp_c[2] = {base + (do_c ? op.o[12] : 0) + (i64)row * ld, base + (do_c ? op.o[13] : 0) + (i64)row * ld};
+  const float* ax_c[2] = {base + (do_c ? op.o[14] : 0) + (i64)row * ld, base + (do_c ? op.o[15] : 0) + (i64)row * ld};
+  const bool fast = staged && row_fast(K, base + (do_t ? op.o[0] : op.o[12]) + (i64)row * ld) && ((ld & 3) == 0);
+  const bool aux_is_h = do_c && (op.o[14] == op.o[12]);
+  RowReg ht[2], hc[2], ac[2];
+  // scalars of this row travel together with the staged weights (no dependent L2 round trip after the barrier)
+  float bt[2] = {0.f, 0.f}, bc_[2] = {0.f, 0.f}, alpha = 0.f, r_ = 0.f, d_ = 0.f, lp2_ = 0.f, y_in = 0.f;
+  if (in) {
+    if (do_t) {
+      bt[0] = __ldcg(base + op.o[4]); bt[1] = __ldcg(base + op.o[5]);
+      alpha = __ldcg(&c.scal->alpha_f32);
+      r_ = __ldcg(base + op.o[6] + row); d_ = __ldcg(base + op.o[7] + row); lp2_ = __ldcg(base + op.o[8] + row);
     }
-    const float* aux = base + op.o[2 + n] + (i64)row * ld;
-    float* dl = base + op.o[13 + n] + (i64)row * ld;
-    for (int k = lane; k < K; k += 32) dl[k] = dout * __ldcg(W + k) * act_dz(op.act, __ldcg(aux + k));
+    if (do_c) {
+      bc_[0] = __ldcg(base + op.o[18]); bc_[1] = __ldcg(base + op.o[19]);
+      if (c.args->y_ext) y_in = c.args->y_ext[row];
+      else if (!do_t) y_in = __ldcg(base + op.o[9] + row);
+    }
+  }
+  if (staged) {
+    if (do_t) { stage_vec(Ws, base + op.o[2], K); stage_vec(Ws + K, base + op.o[3], K); }
+    if (do_c) { stage_vec(Ws + 2 * K, base + op.o[16], K); stage_vec(Ws + 3 * K, base + op.o[17], K); }
+    if (fast && in) {
+      if (do_t) { row_load(ht[0], hp_t[0], K, lane); row_load(ht[1], hp_t[1], K, lane); }
+      if (do_c) {
+        row_load(hc[0], hp_c[0], K, lane); row_load(hc[1], hp_c[1], K, lane);
+        if (!aux_is_h) { row_load(ac[0], ax_c[0], K, lane); row_load(ac[1], ax_c[1], K, lane); }
+        else { ac[0] = hc[0]; ac[1] = hc[1]; }
+      }
+    }
+    stage_finish();
+  }
+  if (!in) return;
+  float y = 0.f;
+  if (do_t) {
+    float tq[2];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const float* W = staged ? Ws + n * K : base + op.o[2 + n];
+      const float part = fast ? row_dot_partial(ht[n], W, K, lane) : warp_dot_any(hp_t[n], W, K, lane);
+      tq[n] = act_fwd(op.act_out, warp_sum(part) + bt[n]);
+    }
+    const float r = r_, d = d_, lp2 = lp2_;
+    // y = r + gamma * (1 - d) * (min(Q1t, Q2t) - alpha * logpi')      (agent.py:208-210)
+    y = r + (hp.gamma * (1.f - d)) * (fminf(tq[0], tq[1]) - alpha * lp2);
+    if (lane == 0) {
+      base[op.o[9] + row] = y;
+      base[op.o[10] + row] = tq[0];
+      base[op.o[11] + row] = tq[1];
+    }
+  }
+  if (do_c) {
+    if (c.args->y_ext || !do_t) y = y_in;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const float* W = staged ? Ws + (2 + n) * K : base + op.o[16 + n];
+      const float part = fast ? row_dot_partial(hc[n], W, K, lane) : warp_dot_any(hp_c[n], W, K, lane);
+      const float z = warp_sum(part) + bc_[n];
+      const float q = act_fwd(op.act_out, z);
+      const float diff = q - y;
+      // d mse / d q = 2 (q - y) / B; through the output activation
+      const float dout = (2.f * diff / (float)hp.B_global) * act_dz2(op.act_out, z, q);
+      if (lane == 0) {
+        base[op.o[20 + n] + row] = q;
+        base[op.o[22 + n] + row] = dout;
+        base[op.o[26 + n] + row] = diff * diff;
+      }
+      float* dl = base + op.o[24 + n] + (i64)row * ld;
+      if (fast) {
+        const RowReg& ar = ac[n];
+#pragma unroll
+        for (int i = 0; i < ROW_KREG; ++i) {
+          const int k = (lane + 32 * i) * 4;
+          if (k < K) {
+            const float4 w = *reinterpret_cast<const float4*>(W + k);
+            *reinterpret_cast<float4*>(dl + k) =
+                make_float4(dout * w.x * act_dz(op.act, ar.v[i].x), dout * w.y * act_dz(op.act, ar.v[i].y),
+                            dout * w.z * act_dz(op.act, ar.v[i].z), dout * w.w * act_dz(op.act, ar.v[i].w));
+          }
+        }
+      } else {
+        for (int k = lane; k < K; k += 32) dl[k] = dout * W[k] * act_dz(op.act, __ldcg(ax_c[n] + k));
+      }
+    }
   }
 }
 
 // ---------------------------------------------------------------- OP_ACTOR_Q
 // o[0..1]=hq(last hidden) o[2..3]=aux o[4..5]=W_L o[6..7]=b_L o[8]=lp o[9..10]=q out o[13..14]=delta o[15]=plossrow
-__device__ __forceinline__ void op_actor_q(const Op& op, const RowCtx& c, int row, int lane) {
+__device__ __noinline__ void tile_actor_q(const Op& op, const RowCtx& c, int tile) {
   const Hyper& hp = c.args->hp;
-  if (row >= hp.B) return;
   float* base = c.base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = tile * ROWS_PER_TILE + warp;
+  const bool in = row < hp.B;
   const int K = op.i[1], ld = op.i[0];
+  const bool staged = 2 * K <= c.tsm_floats;
+  float* Ws = c.tsm;
+  const float* hq[2] = {base + op.o[0] + (i64)row * ld, base + op.o[1] + (i64)row * ld};
+  const float* ax[2] = {base + op.o[2] + (i64)row * ld, base + op.o[3] + (i64)row * ld};
+  const bool fast = staged && row_fast(K, hq[0]) && ((ld & 3) == 0);
+  const bool aux_is_h = op.o[2] == op.o[0];
+  RowReg hr[2], ar[2];
+  float bq[2] = {0.f, 0.f}, alpha = 0.f, lp_ = 0.f;
+  if (in) {
+    bq[0] = __ldcg(base + op.o[6]); bq[1] = __ldcg(base + op.o[7]);
+    alpha = __ldcg(&c.scal->alpha_f32);
+    lp_ = __ldcg(base + op.o[8] + row);
+  }
+  if (staged) {
+    stage_vec(Ws, base + op.o[4], K);
+    stage_vec(Ws + K, base + op.o[5], K);
+    if (fast && in) {
+      row_load(hr[0], hq[0], K, lane); row_load(hr[1], hq[1], K, lane);
+      if (!aux_is_h) { row_load(ar[0], ax[0], K, lane); row_load(ar[1], ax[1], K, lane); }
+      else { ar[0] = hr[0]; ar[1] = hr[1]; }
+    }
+    stage_finish();
+  }
+  if (!in) return;
   float q[2], z[2];
 #pragma unroll
   for (int n = 0; n < 2; ++n) {
-    z[n] = warp_dot(base + op.o[n] + (i64)row * ld, base + op.o[4 + n], K, lane) + __ldcg(base + op.o[6 + n]);
+    const float* W = staged ? Ws + n * K : base + op.o[4 + n];
+    const float part = fast ? row_dot_partial(hr[n], W, K, lane) : warp_dot_any(hq[n], W, K, lane);
+    z[n] = warp_sum(part) + bq[n];
     q[n] = act_fwd(op.act_out, z[n]);
   }
-  const float alpha = __ldcg(&c.scal->alpha_f32);
   // torch.min backward: gradient to the smaller input, ties split 1/2 - 1/2
   const float w1 = q[0] < q[1] ? 1.f : (q[0] == q[1] ? 0.5f : 0.f);
   const float g[2] = {-w1 / (float)hp.B_global, -(1.f - w1) / (float)hp.B_global};
   if (lane == 0) {
     base[op.o[9] + row] = q[0];
     base[op.o[10] + row] = q[1];
-    base[op.o[15] + row] = alpha * __ldcg(base + op.o[8] + row) - fminf(q[0], q[1]);
+    base[op.o[15] + row] = alpha * lp_ - fminf(q[0], q[1]);
   }
 #pragma unroll
   for (int n = 0; n < 2; ++n) {
     const float dout = g[n] * act_dz2(op.act_out, z[n], q[n]);
-    const float* W = base + op.o[4 + n];
-    const float* aux = base + op.o[2 + n] + (i64)row * ld;
+    const float* W = staged ? Ws + n * K : base + op.o[4 + n];
     float* dl = base + op.o[13 + n] + (i64)row * ld;
-    for (int k = lane; k < K; k += 32) dl[k] = dout * __ldcg(W + k) * act_dz(op.act, __ldcg(aux + k));
+    if (fast) {
+      const RowReg& a2 = ar[n];
+#pragma unroll
+      for (int i = 0; i < ROW_KREG; ++i) {
+        const int k = (lane + 32 * i) * 4;
+        if (k < K) {
+          const float4 w = *reinterpret_cast<const float4*>(W + k);
+          *reinterpret_cast<float4*>(dl + k) =
+              make_float4(dout * w.x * act_dz(op.act, a2.v[i].x), dout * w.y * act_dz(op.act, a2.v[i].y),
+                          dout * w.z * act_dz(op.act, a2.v[i].z), dout * w.w * act_dz(op.act, a2.v[i].w));
+        }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) dl[k] = dout * W[k] * act_dz(op.act, __ldcg(ax[n] + k));
+    }
   }
 }
 
 // ---------------------------------------------------------------- OP_ACTOR_BWD
 // o[0..1]=delta0 of critics [B,H0q] o[2..3]=W_0 of critics [H0q, obs+act]
-// o[4]=tz o[5]=se o[6]=mask o[7]=headz o[8]=dhead out o[9]=Wpi_L o[10]=unused o[11]=aux pi(last hidden) o[12]=delta pi(last hidden)
+// o[4]=tz o[5]=se o[6]=mask o[7]=headz o[8]=dhead out o[9]=Wpi_L o[11]=aux pi(last hidden) o[12]=delta pi(last hidden)
 // i[0]=ld delta0  i[1]=H0q  i[2]=ldW0 (=obs+act)  i[3]=ld pi hidden  i[4]=Kpi
-__device__ __forceinline__ void op_actor_bwd(const Op& op, const RowCtx& c, int row, int lane) {
+__device__ __noinline__ void tile_actor_bwd(const Op& op, const RowCtx& c, int tile) {
   const Hyper& hp = c.args->hp;
-  if (row >= hp.B) return;
   float* base = c.base;
-  const int A = hp.act, O = hp.obs, H0 = op.i[1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = tile * ROWS_PER_TILE + warp;
+  const bool in = row < hp.B;
+  const int A = hp.act, O = hp.obs, H0 = op.i[1], Kp = op.i[4];
+  const bool staged = (2 * A * H0 + 2 * A * Kp) <= c.tsm_floats;
+  float* Wa = c.tsm;                        // [2][A][H0]: action columns of the critics' first layers
+  float* Wp = c.tsm + 2 * A * H0;           // [2A][Kp]: policy output layer
+  const float* d0[2] = {base + op.o[0] + (i64)row * op.i[0], base + op.o[1] + (i64)row * op.i[0]};
+  const float* auxp = base + op.o[11] + (i64)row * op.i[3];
+  const bool fast = staged && row_fast(H0, d0[0]) && ((op.i[0] & 3) == 0) && row_fast(Kp, auxp) && ((op.i[3] & 3) == 0) &&
+                    row_fast(Kp, Wp) && row_fast(H0, Wa);
+  RowReg dr[2], ap;
+  float alpha = 0.f, tz_ = 0.f, se_ = 0.f, mk_ = 0.f, zm_ = 0.f, zl_ = 0.f;       // lane j < A owns action dim j (A <= 32)
+  if (in) {
+    alpha = __ldcg(&c.scal->alpha_f32);
+    if (lane < A) {
+      tz_ = __ldcg(base + op.o[4] + (i64)row * A + lane);
+      se_ = __ldcg(base + op.o[5] + (i64)row * A + lane);
+      mk_ = __ldcg(base + op.o[6] + (i64)row * A + lane);
+      if (op.act_out != SACX_ACT_IDENTITY) {
+        zm_ = __ldcg(base + op.o[7] + (i64)row * 2 * A + lane);
+        zl_ = __ldcg(base + op.o[7] + (i64)row * 2 * A + A + lane);
+      }
+    }
+  }
+  if (staged) {
+    for (int i = threadIdx.x; i < 2 * A * H0; i += 256) {
+      const int n = i / (A * H0), j = (i / H0) % A, k = i % H0;
+      Wa[i] = __ldcg(base + op.o[2 + n] + (i64)k * op.i[2] + O + j);
+    }
+    stage_vec(Wp, base + op.o[9], 2 * A * Kp);
+    if (fast && in) { row_load(dr[0], d0[0], H0, lane); row_load(dr[1], d0[1], H0, lane); row_load(ap, auxp, Kp, lane); }
+    stage_finish();
+  }
+  if (!in) return;
   float* da = c.wsm;                          // [A] dQ/da, then dhead [2A]
   float* dh = c.wsm + SACX_MAX_ACT;
   // d(-minQ)/d a_j = sum_c sum_h delta0_c[h] * W0_c[h, obs + j]
@@ -236,26 +418,26 @@ __device__ __forceinline__ void op_actor_bwd(const Op& op, const RowCtx& c, int 
     float s = 0.f;
 #pragma unroll
     for (int n = 0; n < 2; ++n) {
-      const float* d0 = base + op.o[n] + (i64)row * op.i[0];
-      const float* W0 = base + op.o[2 + n] + O + j;
-      for (int k = lane; k < H0; k += 32) s = fmaf(__ldcg(d0 + k), __ldcg(W0 + (i64)k * op.i[2]), s);
+      if (fast) s += row_dot_partial(dr[n], Wa + (n * A + j) * H0, H0, lane);
+      else if (staged) s += warp_dot_any(d0[n], Wa + (n * A + j) * H0, H0, lane);
+      else {
+        const float* W0 = base + op.o[2 + n] + O + j;
+        for (int k = lane; k < H0; k += 32) s = fmaf(__ldcg(d0[n] + k), __ldcg(W0 + (i64)k * op.i[2]), s);
+      }
     }
     s = warp_sum(s);
     if (lane == 0) da[j] = s;
   }
   __syncwarp();
-  const float alpha = __ldcg(&c.scal->alpha_f32);
   const float ab = alpha / (float)hp.B_global;
   for (int j = lane; j < A; j += 32) {
-    const float tz = __ldcg(base + op.o[4] + (i64)row * A + j);
-    const float se = __ldcg(base + op.o[5] + (i64)row * A + j);
-    const float mk = __ldcg(base + op.o[6] + (i64)row * A + j);
+    const float tz = tz_, se = se_, mk = mk_;
     // dL/dz = (alpha/B) 2 tanh z + dL/da * c (1 - tanh^2 z);  dL/dmu = dL/dz;
     // dL/dlogstd_raw = (sigma eps dL/dz - alpha/B) * 1[lo <= raw <= hi]
     const float dz = ab * (2.f * tz) + da[j] * (hp.action_scale * (1.f - tz * tz));
     float dmu = dz, dls = (se * dz - ab) * mk;
     if (op.act_out != SACX_ACT_IDENTITY) {
-      const float zm = __ldcg(base + op.o[7] + (i64)row * 2 * A + j), zl = __ldcg(base + op.o[7] + (i64)row * 2 * A + A + j);
+      const float zm = zm_, zl = zl_;
       dmu *= act_dz2(op.act_out, zm, act_fwd(op.act_out, zm));
       dls *= act_dz2(op.act_out, zl, act_fwd(op.act_out, zl));
     }
@@ -266,14 +448,29 @@ __device__ __forceinline__ void op_actor_bwd(const Op& op, const RowCtx& c, int 
   }
   __syncwarp();
   // delta of the policy's last hidden layer: (dhead . Wpi_L) * act'(.)
-  const int Kp = op.i[4];
-  const float* W = base + op.o[9];
-  const float* aux = base + op.o[11] + (i64)row * op.i[3];
   float* dl = base + op.o[12] + (i64)row * op.i[3];
-  for (int k = lane; k < Kp; k += 32) {
-    float s = 0.f;
-    for (int j = 0; j < 2 * A; ++j) s = fmaf(dh[j], __ldcg(W + (i64)j * Kp + k), s);
-    dl[k] = s * act_dz(op.act, __ldcg(aux + k));
+  if (fast) {
+#pragma unroll
+    for (int i = 0; i < ROW_KREG; ++i) {
+      const int k = (lane + 32 * i) * 4;
+      if (k < Kp) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 2 * A; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(Wp + j * Kp + k);
+          const float g = dh[j];
+          s.x = fmaf(g, w.x, s.x); s.y = fmaf(g, w.y, s.y); s.z = fmaf(g, w.z, s.z); s.w = fmaf(g, w.w, s.w);
+        }
+        *reinterpret_cast<float4*>(dl + k) = make_float4(s.x * act_dz(op.act, ap.v[i].x), s.y * act_dz(op.act, ap.v[i].y),
+                                                         s.z * act_dz(op.act, ap.v[i].z), s.w * act_dz(op.act, ap.v[i].w));
+      }
+    }
+  } else {
+    const float* W = staged ? Wp : base + op.o[9];
+    for (int k = lane; k < Kp; k += 32) {
+      float s = 0.f;
+      for (int j = 0; j < 2 * A; ++j) s = fmaf(dh[j], staged ? W[j * Kp + k] : __ldcg(W + (i64)j * Kp + k), s);
+      dl[k] = s * act_dz(op.act, __ldcg(auxp + k));
+    }
   }
   __syncwarp();
 }

@@ -12,8 +12,7 @@ enum OpType : int {
   OP_GATHER,      // ring rows -> batch buffers (a2/a3: replay_buffer.py:32-39, agent.py:166-193)
   OP_GEMM,        // tiled FP32 GEMM with fused epilogue (a4 forward, backward dA, backward dW+Adam)
   OP_PI_HEAD,     // policy output layer + tanh-Gaussian rsample/log_prob (a5: models.py:73-87)
-  OP_Q_ROW,       // target critics' output layers + soft Bellman target y (a6)
-  OP_CRITIC_ROW,  // online critics' output layers, MSE delta, delta of the last hidden layer (a7)
+  OP_Q_ROW,       // critic output layers: soft Bellman target y (a6, mode&1) and/or MSE delta + delta of the last hidden layer (a7, mode&2)
   OP_ACTOR_Q,     // critics' heads on (s, a~pi): min, policy loss rows, routed dQ (a8)
   OP_ACTOR_BWD,   // dQ/da through layer 0, head backward, policy delta of last hidden (a8)
   OP_PROLOGUE,    // per-update scalars: Adam step/bias corrections (a11)
@@ -42,7 +41,7 @@ struct Op {
   i64 pb, pbm, pbv, pbt, pbg;
   int opt, flags;
   // row ops: generic slots (documented at each op's builder)
-  i64 o[24];
+  i64 o[32];
   int i[8];
   float f[4];
 };
@@ -108,6 +107,9 @@ struct RunArgs {
   int ctas_per_agent;
   unsigned* barrier;         // [agent_slots] monotonic counters (zeroed before launch)
   i64 scal_off;
+  unsigned long long* dbg;   // optional [n_steps][n_phases][gridDim.x][2] clock64 at barrier arrive / release
+  unsigned long long* dbg2;  // optional [n_steps][n_phases][gridDim.x][8] intra-tile timestamps of the CTA's last GEMM tile
+  int barrier_mode, pad_;
   Hyper hp;
 };
 

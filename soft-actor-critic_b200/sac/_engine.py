@@ -97,6 +97,8 @@ SYMBOLS = {
     "sacx_update": (C.c_int, [_P, _P, _P, _P, _I32]),
     "sacx_update_host": (C.c_int, [_P, _P, _P, _P, _I32, C.POINTER(SacxMetrics)]),
     "sacx_update_staged": (C.c_int, [_P, _P, _P, _P, _I32]),
+    "sacx_update_host_pipelined": (C.c_int, [_P, _P, _P, _P, _I32, C.POINTER(SacxMetrics), C.POINTER(_I32)]),
+    "sacx_update_host_flush": (C.c_int, [_P, C.POINTER(SacxMetrics)]),
     "sacx_sample_batch": (C.c_int, [_P, _P]),
     "sacx_load_batch": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "sacx_target": (C.c_int, [_P, _P, _P]),
@@ -113,6 +115,7 @@ SYMBOLS = {
     "sacx_q_values_host": (C.c_int, [_P, _I32, _P, _P, _I32, _P, _P]),
     "sacx_get_metrics": (C.c_int, [_P, _I32, C.POINTER(SacxMetrics)]),
     "sacx_sync": (C.c_int, [_P]),
+    "sacx_debug_profile": (C.c_int, [_P, _I32, _P, _I64, C.POINTER(_I32), C.POINTER(_I32)]),
     "sacx_launch_count": (_I64, [_P]),
 }
 

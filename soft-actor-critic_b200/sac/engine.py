@@ -124,6 +124,19 @@ class UpdateEngine:
         E.check(self.lib.sacx_update_host(self.h, E.ptr(idx), E.ptr(eps1), E.ptr(eps2), int(n_steps), m))
         return self._metrics.as_dict() if want_metrics else None
 
+    def update_host_pipelined(self, idx, eps1, eps2, n_steps: int = 1) -> Optional[dict]:
+        """Submit this update and return the metrics of the previous submission (None on the first call): the
+        host draws the next index stream / normals while the GPU runs the current update."""
+        self._sync_stream()
+        have = C.c_int32(0)
+        E.check(self.lib.sacx_update_host_pipelined(self.h, E.ptr(idx), E.ptr(eps1), E.ptr(eps2), int(n_steps),
+                                                    C.byref(self._metrics), C.byref(have)))
+        return self._metrics.as_dict() if have.value else None
+
+    def update_host_flush(self) -> dict:
+        E.check(self.lib.sacx_update_host_flush(self.h, C.byref(self._metrics)))
+        return self._metrics.as_dict()
+
     def sample_batch(self, idx: Optional[torch.Tensor] = None) -> None:
         self._sync_stream()
         E.check(self.lib.sacx_sample_batch(self.h, E.ptr(idx)))
