@@ -194,7 +194,8 @@ int sacx_polyak(sacx_agent_t h);
  * large-batch data-parallel mode (all-reduce between grads and apply) and by the parity tests. */
 int sacx_critic_grads(sacx_agent_t h, const float* y_dev);
 int sacx_actor_grads(sacx_agent_t h, const float* eps2_dev, float* logpi_out_dev);
-/* Adam on the gradient block: which = 1 critics (+Polyak if polyak != 0), 2 policy, 4 temperature */
+/* Adam on the gradient block: which = 1 critics (+Polyak if polyak != 0), 2 policy, 4 temperature (from the
+ * gradient share left in the scalar block by sacx_actor_grads, summed over ranks by the caller) */
 int sacx_apply_grads(sacx_agent_t h, int32_t which, int32_t polyak);
 
 /* SAC.select_action (agent.py:149-156) / PolicyNetwork.deterministic_action (models.py:89-92) */

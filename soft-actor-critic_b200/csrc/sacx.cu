@@ -709,8 +709,16 @@ int sacx_target(sacx_agent_t h, const float* eps1, float* y_out) {
   return copy_out(h->e, h->e.b_y, y_out, h->e.cfg.batch_size);
 }
 
+static int zero_grads(Engine& e, const NetLayout& a, const NetLayout& b) {
+  if (!e.grads_atomic) return SACX_OK;
+  for (int ag = 0; ag < e.cfg.n_agents; ++ag)
+    SACX_CUDA(cudaMemsetAsync(e.arena + (i64)ag * e.stride + a.begin + 3 * e.blk, 0, (size_t)(b.end - a.begin) * 4, e.stream));
+  return SACX_OK;
+}
+
 static int critic_run(sacx_agent_t h, const float* y, int plan) {
   if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  if (plan == PLAN_CRITIC_GRADS) { int rc = zero_grads(h->e, h->e.q1, h->e.q2); if (rc) return rc; }
   RunArgs a; memset(&a, 0, sizeof a);
   a.y_ext = y;
   return engine_launch(&h->e, plan, 0, -1, 1, a, false);
@@ -720,6 +728,7 @@ int sacx_critic_grads(sacx_agent_t h, const float* y) { return critic_run(h, y, 
 
 static int actor_run(sacx_agent_t h, const float* eps2, float* lp_out, int plan) {
   if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  if (plan == PLAN_ACTOR_GRADS) { int rc = zero_grads(h->e, h->e.pi, h->e.pi); if (rc) return rc; }
   RunArgs a; memset(&a, 0, sizeof a);
   a.eps2_ext = eps2;
   int rc = engine_launch(&h->e, plan, 0, -1, 1, a, false);
@@ -751,7 +760,7 @@ int sacx_apply_grads(sacx_agent_t h, int32_t which, int32_t polyak) {
   int rc = SACX_OK;
   if (which & 1) rc = engine_launch(&h->e, polyak ? PLAN_APPLY_Q_POLYAK : PLAN_APPLY_Q, 0, -1, 1, a, false);
   if (!rc && (which & 2)) rc = engine_launch(&h->e, PLAN_APPLY_PI, 0, -1, 1, a, false);
-  if (!rc && (which & 4)) rc = engine_launch(&h->e, PLAN_ALPHA, 0, -1, 1, a, false);
+  if (!rc && (which & 4)) rc = engine_launch(&h->e, PLAN_ALPHA_APPLY, 0, -1, 1, a, false);
   return rc;
 }
 

@@ -40,14 +40,14 @@ struct ActSet {                                         // hidden activations of
 };
 
 enum PlanId { PLAN_FUSED = 0, PLAN_SAMPLE, PLAN_TARGET, PLAN_CRITIC, PLAN_CRITIC_GRADS, PLAN_ACTOR, PLAN_ACTOR_GRADS,
-              PLAN_ALPHA, PLAN_POLYAK, PLAN_APPLY_Q, PLAN_APPLY_Q_POLYAK, PLAN_APPLY_PI, PLAN_FUSED_NOGATHER, N_PLANS };
+              PLAN_ALPHA, PLAN_POLYAK, PLAN_APPLY_Q, PLAN_APPLY_Q_POLYAK, PLAN_APPLY_PI, PLAN_FUSED_NOGATHER, PLAN_ALPHA_APPLY, N_PLANS };
 
 struct Ring;
 
 struct Engine {
   sacx_config cfg;
   int n_sms = 0, max_ctas = 0;
-  bool large = false;
+  bool large = false, grads_atomic = false;
   int grid_x = 1, grid_y = 1, smem_bytes = 0, barrier_mode = 1;
   std::vector<sacx_tensor_desc> lay;
   i64 cur = 0, stride = 0;
@@ -153,6 +153,7 @@ struct Engine {
       sub("scal.alpha_f32", offsetof(AgentScalars, alpha_f32), 1, 0);
       sub("scal.metrics", offsetof(AgentScalars, metrics), 12, 0);
       sub("scal.nonfinite", offsetof(AgentScalars, nonfinite), 1, 0);
+      sub("scal.dp_alpha", offsetof(AgentScalars, dp_mean_t), 2, 0);
     }
     cur = align4(cur);
     P0 = cur;
@@ -171,6 +172,11 @@ struct Engine {
       alias_block(pre[k], shift, q2, "q2");
       sacx_tensor_desc d; memset(&d, 0, sizeof d);
       snprintf(d.name, sizeof d.name, "block.%c", pre[k][0]); d.offset = P0 + shift; d.rows = 1; d.cols = d.ld = (int)n_online; lay.push_back(d);
+    }
+    { // contiguous gradient slices for the data-parallel all-reduce
+      sacx_tensor_desc d; memset(&d, 0, sizeof d);
+      snprintf(d.name, sizeof d.name, "block.g.policy"); d.offset = pi.begin + 3 * blk; d.rows = 1; d.cols = d.ld = (int)(pi.end - pi.begin); lay.push_back(d);
+      snprintf(d.name, sizeof d.name, "block.g.critics"); d.offset = q1.begin + 3 * blk; d.cols = d.ld = (int)(q2.end - q1.begin); lay.push_back(d);
     }
     cur = P0 + 4 * blk;
     T0 = align4(cur);
@@ -273,6 +279,13 @@ struct Engine {
     o.pb = n.b[l]; o.pbm = n.b[l] + blk; o.pbv = n.b[l] + 2 * blk; o.pbg = n.b[l] + 3 * blk;
     if (is_critic) { o.pt = n.W[l] - q1.begin + T0; o.pbt = n.b[l] - q1.begin + T0; }
     finish_gemm(o);
+    if (flags == DW_STORE_GRAD && o.K >= 2048) {      // gradient-only dW at large batch: split the batch range over CTAs
+      const int kc = 512;
+      const int ksplit = (o.K + kc - 1) / kc;
+      o.i[0] = ksplit; o.i[1] = kc;
+      o.ntiles *= ksplit;
+      o.flags = DW_STORE_GRAD | DW_ATOMIC;
+    }
     return o;
   }
   int row_tiles() const { return (cfg.batch_size + ROWS_PER_TILE - 1) / ROWS_PER_TILE; }
@@ -449,7 +462,7 @@ struct Engine {
       pb.add(gemm_fwd(pi, l, 0, l ? a_pia.h[l - 1] : x_pi, l ? a_pia.ld[l - 1] : ldx, a_pia));
     }
     pb.phase(); pb.add(op_pi_head(true));
-    emit_actor_tail(pb, flags, 2);
+    emit_actor_tail(pb, flags, (flags & DW_ADAM) ? 2 : (2 | 16));
   }
   // critics on (s, a~pi) -> routed dQ -> dQ/da -> head backward -> policy backward (+Adam)
   void emit_actor_tail(PB& pb, int flags, int final_mode) const {
@@ -517,7 +530,12 @@ struct Engine {
     { PB pb; emit_critic(pb, DW_STORE_GRAD); if ((rc = put(PLAN_CRITIC_GRADS, pb))) return rc; }
     { PB pb; emit_actor(pb, DW_ADAM); if ((rc = put(PLAN_ACTOR, pb))) return rc; }
     { PB pb; emit_actor(pb, DW_STORE_GRAD); if ((rc = put(PLAN_ACTOR_GRADS, pb))) return rc; }
+    grads_atomic = false;
+    for (int id : {PLAN_CRITIC_GRADS, PLAN_ACTOR_GRADS})
+      for (int i = 0; i < h_plans[id].n_ops; ++i)
+        if (h_plans[id].ops[i].type == OP_GEMM && (h_plans[id].ops[i].flags & DW_ATOMIC)) grads_atomic = true;
     { PB pb; pb.phase(); pb.add(op_final(4)); if ((rc = put(PLAN_ALPHA, pb))) return rc; }
+    { PB pb; pb.phase(); pb.add(op_final(32 | 8)); if ((rc = put(PLAN_ALPHA_APPLY, pb))) return rc; }
     { PB pb; pb.phase(); pb.add(op_polyak()); pb.add(op_final(8)); if ((rc = put(PLAN_POLYAK, pb))) return rc; }
     for (int pol = 0; pol < 2; ++pol) {
       PB pb;

@@ -179,7 +179,11 @@ __device__ __forceinline__ void epilogue_row4(const Op& op, const EpiCtx& ctx, i
     }
   } else {  // EPI_DW: (m, n) = (out neuron, in feature); parameter leading dim = N (= K_in)
     const i64 e = (i64)m * op.N + n;
-    if (vec) {
+    if (op.flags & DW_ATOMIC) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < op.N) atomicAdd(base + op.pg + e + j, v[j]);
+    } else if (vec) {
       if (op.flags & DW_STORE_GRAD) *reinterpret_cast<float4*>(base + op.pg + e) = acc;
       if (op.flags & DW_ADAM) {
         float p[4] = {pre.a.x, pre.a.y, pre.a.z, pre.a.w}, mm[4] = {pre.b.x, pre.b.y, pre.b.z, pre.b.w},
@@ -221,6 +225,7 @@ __device__ __forceinline__ void epilogue_row4(const Op& op, const EpiCtx& ctx, i
 __device__ __forceinline__ void epilogue_bias(const Op& op, const EpiCtx& ctx, int m, float g, const float (&bpre)[6]) {
   if (m >= op.M) return;
   float* base = ctx.base;
+  if (op.flags & DW_ATOMIC) { atomicAdd(base + op.pbg + m, g); return; }
   if (op.flags & DW_STORE_GRAD) base[op.pbg + m] = g;
   if (op.flags & DW_ADAM) {
     const float ss = bpre[4], bc = bpre[5];
@@ -366,14 +371,21 @@ __device__ __noinline__ void gemm_tile_impl(const Op& op, const EpiCtx& ctx, int
   constexpr bool AKM = (MODE == 2), BKM = (MODE >= 1), BSUM = (MODE == 2);
   constexpr int BM = C::BM, BN = C::BN, RS = C::RS, KG = C::KG;
   const int tid = threadIdx.x;
-  const int tm = tile / op.tiles_n, tn = tile % op.tiles_n;
+  // dW at large batch: the reduction (batch) range is split over op.i[0] CTAs, partial sums meet in the gradient
+  // block with atomic adds (DW_ATOMIC)
+  const int ksplit = (MODE == 2 && op.i[0] > 1) ? op.i[0] : 1;
+  const int tiles_mn = op.ntiles / ksplit;
+  const int ks = tile / tiles_mn, tmn = tile % tiles_mn;
+  const int tm = tmn / op.tiles_n, tn = tmn % op.tiles_n;
   const int m0 = tm * BM, n0 = tn * BN;
-  const float* __restrict__ A = ctx.base + op.a;
-  const float* __restrict__ Bp = ctx.base + op.b;
+  const int kc = (MODE == 2 && ksplit > 1) ? op.i[1] : 0;
+  const float* __restrict__ A = ctx.base + op.a + (AKM ? (i64)ks * kc * op.a_sk : 0);
+  const float* __restrict__ Bp = ctx.base + op.b + (BKM && MODE == 2 ? (i64)ks * kc * op.b_sk : 0);
   const int lda = AKM ? op.a_sk : op.a_sm;
   const int ldb = BKM ? op.b_sk : op.b_sn;
   const bool a_vec = op.a_vec != 0, b_vec = op.b_vec != 0;
-  const int M = op.M, N = op.N, K = op.K;
+  const int M = op.M, N = op.N;
+  const int K = (ksplit > 1) ? min(kc, op.K - ks * kc) : op.K;
   const bool bias_tile = BSUM && (tn == 0) && (op.pb >= 0);
   const int nk = (K + GEMM_BK - 1) / GEMM_BK;
   SACX_TSTAMP(0);

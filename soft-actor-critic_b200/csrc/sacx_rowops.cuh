@@ -493,7 +493,7 @@ __device__ __forceinline__ void op_prologue(const Op& op, const RowCtx& c) {
 }
 
 // ---------------------------------------------------------------- OP_FINAL (one warp)
-// mode bits: 1 critic loss means, 2 policy loss mean, 4 temperature step, 8 count the update
+// mode bits: 1 critic loss means, 2 policy loss mean, 4 temperature step, 8 count the update, 16/32 see below
 // o[0..1]=lossrow o[2]=plossrow o[3]=lp o[4..5]=q o[6]=y
 __device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane) {
   const Hyper& hp = c.args->hp;
@@ -516,7 +516,9 @@ __device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane
     const float pl = mean_of(base + op.o[2]);
     if (lane == 0) s->metrics[2] = pl;
   }
-  if (op.mode & 4) {
+  // temperature (a9): bit 4 = gradient + step (single GPU); bit 16 = this rank's share of the gradient only;
+  // bit 32 = step from the (all-reduced) shares in the scalar block
+  if (op.mode & (4 | 16)) {
     const float* lp = c.args->lp_ext ? c.args->lp_ext : base + op.o[3];
     float acc = 0.f, accl = 0.f;
     const float la32 = (float)s->log_alpha;
@@ -527,26 +529,27 @@ __device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane
     }
     const float mean_t = warp_sum(acc) * invB;           // f32 mean, as in the reference
     const float mean_lt = warp_sum(accl) * invB;
-    const float lpm = mean_t - hp.target_entropy;
-    if (lane == 0) {
-      s->metrics[8] = lpm;
-      if (hp.auto_alpha) {
-        // alpha_loss = -(log_alpha * (logpi + H).detach()).mean();  d/dlog_alpha = -mean(logpi + H)
-        const double g = -(double)mean_t;
-        const i64 t = s->step[OPT_ALPHA] + 1;
-        s->step[OPT_ALPHA] = t;
-        s->alpha_m = s->alpha_m + (1.0 - 0.9) * (g - s->alpha_m);
-        s->alpha_v = s->alpha_v * 0.999 + (1.0 - 0.999) * g * g;
-        const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
-        const double denom = sqrt(s->alpha_v) / sqrt(bc2) + 1e-8;
-        s->log_alpha = s->log_alpha - (hp.alpha_lr / bc1) * (s->alpha_m / denom);
-        s->alpha = exp(s->log_alpha);
-        s->alpha_f32 = (float)s->alpha;
-        s->metrics[3] = -mean_lt;
-      }
-      s->metrics[4] = (float)s->alpha;
-      s->metrics[5] = (float)s->log_alpha;
+    if (lane == 0) { s->dp_mean_t = mean_t; s->dp_mean_lt = mean_lt; }
+  }
+  if ((op.mode & (4 | 32)) && lane == 0) {
+    const float mean_t = s->dp_mean_t, mean_lt = s->dp_mean_lt;
+    s->metrics[8] = mean_t - hp.target_entropy;
+    if (hp.auto_alpha) {
+      // alpha_loss = -(log_alpha * (logpi + H).detach()).mean();  d/dlog_alpha = -mean(logpi + H)
+      const double g = -(double)mean_t;
+      const i64 t = s->step[OPT_ALPHA] + 1;
+      s->step[OPT_ALPHA] = t;
+      s->alpha_m = s->alpha_m + (1.0 - 0.9) * (g - s->alpha_m);
+      s->alpha_v = s->alpha_v * 0.999 + (1.0 - 0.999) * g * g;
+      const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+      const double denom = sqrt(s->alpha_v) / sqrt(bc2) + 1e-8;
+      s->log_alpha = s->log_alpha - (hp.alpha_lr / bc1) * (s->alpha_m / denom);
+      s->alpha = exp(s->log_alpha);
+      s->alpha_f32 = (float)s->alpha;
+      s->metrics[3] = -mean_lt;
     }
+    s->metrics[4] = (float)s->alpha;
+    s->metrics[5] = (float)s->log_alpha;
   }
   if ((op.mode & 8) && lane == 0) s->updates += 1;
 }

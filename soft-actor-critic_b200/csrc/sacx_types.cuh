@@ -23,7 +23,7 @@ enum OpType : int {
 };
 
 enum Epi : int { EPI_FWD = 1, EPI_DACT = 2, EPI_DW = 3 };
-enum DwFlags : int { DW_STORE_GRAD = 1, DW_ADAM = 2, DW_POLYAK = 4 };
+enum DwFlags : int { DW_STORE_GRAD = 1, DW_ADAM = 2, DW_POLYAK = 4, DW_ATOMIC = 8 };
 enum OptId : int { OPT_PI = 0, OPT_Q1 = 1, OPT_Q2 = 2, OPT_ALPHA = 3, N_OPT = 4 };
 
 // One schedulable operation. All `long long` fields are float32-word offsets from the agent's
@@ -71,7 +71,8 @@ struct AgentScalars {
   float pad;
   float metrics[12];                                 // q1_loss q2_loss policy_loss alpha_loss alpha log_alpha q1_mean q2_mean logpi_mean y_mean
   int nonfinite;
-  int pad2[3];
+  float dp_mean_t, dp_mean_lt;                       // data parallel: this rank's share of mean(logpi + H), mean(log_alpha (logpi + H))
+  int pad2[1];
 };
 
 struct RingMeta {          // one per agent, at the head of the agent's ring block
