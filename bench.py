@@ -40,6 +40,8 @@ WORKLOADS = {
                    label="DonkeyVae latent shape: obs 32, act 2, 2x256 relu, batch 1024, 50k ring"),
     "population": dict(obs=4, act=1, hidden=[256, 256], batch=256, capacity=100_000, fill=20_000, n_agents=1024, act_fn="relu",
                        label="InvertedPendulum shape: obs 4, act 1, 2x256, batch 256, 1024 independent agents sharded over ranks"),
+    "dp": dict(obs=24, act=4, hidden=[256, 256], batch=65536, capacity=1_000_000, fill=1_000_000, n_agents=1, act_fn="relu", dp=True,
+               label="large-batch data parallel: BipedalWalker shape, global batch 65536 split over ranks, 2 NCCL all-reduces per update"),
 }
 
 
@@ -255,34 +257,42 @@ def main():
 
     n_agents_local = max(1, w["n_agents"] // world) if w["n_agents"] > 1 else 1
     cfg_dev = make_config(w, "device", seed=rank)
+    scaling = "weak"
+    dp = None
 
     # ---- device-resident throughput: engine + ring, device RNG ------------------------------------------
-    if w["n_agents"] == 1:
+    if w.get("dp"):
+        from sac.population import DataParallelSAC
+        agent = None
+        scaling = "strong"
+        cfg_dp = make_config(w, "device", seed=0)                  # identical parameters on every rank
+        dp = DataParallelSAC(w["obs"], w["act"], cfg_dp, w["batch"], rank=rank, world=world)
+        eng, ring = dp.engine, dp.ring
+        s, a, r, s2, d = synth(w["fill"], w["obs"], w["act"], seed=0)   # ring replicated
+        ring.push_batch(s, a, r, s2, d)
+    elif w["n_agents"] == 1:
         from sac.agent import SAC
         agent = SAC(FakeEnv(w["obs"], w["act"]), cfg_dev)
         eng, ring = agent.engine, agent.replay_buffer
         s, a, r, s2, d = synth(w["fill"], w["obs"], w["act"], seed=rank)
         ring.push_batch(s, a, r, s2, d)
     else:
+        from sac.population import SACPopulation
         agent = None
-        eng = UpdateEngine(w["obs"], w["act"], cfg_dev, n_agents=n_agents_local)
-        g = torch.Generator(device="cuda").manual_seed(1234 + rank)
-        for tag in ("pi", "q1", "q2"):
-            for l in range(len(w["hidden"]) + 1):
-                v = eng.population_view(f"{tag}.W{l}")
-                bound = (6.0 / (v.shape[1] + v.shape[2])) ** 0.5           # xavier_uniform_, independent per agent
-                v.copy_((torch.rand(v.shape, device="cuda", generator=g) * 2 - 1) * bound)
-        eng.reset_state()
-        ring = ReplayBuffer(w["capacity"], w["obs"], w["act"], n_agents=n_agents_local)
+        scaling = "strong"                                        # 1024 agents in total, partitioned over the ranks
+        pop = SACPopulation(w["obs"], w["act"], cfg_dev, w["n_agents"], rank=rank, world=world, reference_init=False)
+        n_agents_local = pop.n_local
+        eng, ring = pop.engine, pop.ring
         s, a, r, s2, d = synth(w["fill"], w["obs"], w["act"], seed=rank)
-        ds, da, dr, ds2, dd = (torch.from_numpy(x).cuda() for x in (s, a, r, s2, d))
-        for ag in range(n_agents_local):
-            ring.push_device(ds, da, dr, ds2, dd, agent=ag)
-        eng.attach_ring(ring)
+        pop.push_device_all(*(torch.from_numpy(x).cuda() for x in (s, a, r, s2, d)))
     torch.cuda.synchronize()
     gx, gy, smem = eng.grid()
 
     def run_updates(n):
+        if dp is not None:
+            for _ in range(n):
+                dp.update()
+            return
         done = 0
         while done < n:
             c = min(args.chunk, n - done)
@@ -313,7 +323,16 @@ def main():
         ms = float(t.item())
     m = eng.metrics()
     assert m["nonfinite"] == 0 and np.isfinite(m["q1_loss"]), f"non-finite update: {m}"
-    total_updates = args.steps * n_agents_local * world
+    if dp is not None:
+        total_updates = args.steps                                 # one global-batch update per step, whatever G is
+    elif w["n_agents"] > 1:
+        total_updates = args.steps * w["n_agents"] if world > 1 else args.steps * n_agents_local
+        if world > 1:                                              # uneven shards: count what was really done
+            t = torch.tensor([float(args.steps * n_agents_local)], device="cuda")
+            dist.all_reduce(t)
+            total_updates = float(t.item())
+    else:
+        total_updates = args.steps * world
     value = total_updates / (ms / 1000.0)
 
     # ---- e2e through the public API (host RNG, H2D + D2H per step) ---------------------------------------
@@ -364,6 +383,9 @@ def main():
     fl = flops_per_update(w["obs"], w["act"], w["hidden"], w["batch"])
     by = bytes_per_update(w["obs"], w["act"], w["hidden"], w["batch"])
     per_gpu_rate = value / world                       # agent-updates/s on one GPU
+    if dp is not None:
+        fl, by = fl // world, by                       # per rank: 1/G of the batch FLOPs, the whole parameter stream
+        per_gpu_rate = value                           # every rank takes part in every update
     ach_tf = fl * per_gpu_rate / 1e12
     traffic = None
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
@@ -386,10 +408,12 @@ def main():
     if not args.no_cpu_baseline:
         cpu = cpu_reference(w if w["n_agents"] == 1 else dict(w, fill=w["fill"]), 400, 10, budget_s=40.0)
     line = {"metric": "SAC updates/s", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": w["label"], "agents_per_gpu": n_agents_local, "updates_per_launch": args.chunk,
                                             "l2": "inputs larger than L2 (216 MB ring; each update gathers fresh random rows)",
-                                            "grid": [gx, gy], "smem_bytes": smem, "multi_gpu": "replicas only (independent agents per rank, no collective)"},
+                                            "grid": [gx, gy], "smem_bytes": smem, "multi_gpu": ("data parallel: 2 NCCL all-reduces per update" if dp is not None else
+                                                          "population sharded over ranks, no collective" if w["n_agents"] > 1 else
+                                                          "replicas only (independent agents per rank, no collective)")},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "final_metrics": {k: m[k] for k in ("q1_loss", "policy_loss", "alpha", "updates")}}
     print(json.dumps(line))

@@ -122,13 +122,14 @@ __device__ __forceinline__ bool epi_vec_ok(const Op& op, int n) {
   return (op.N & 3) == 0 && ((op.p | op.pm | op.pv | op.pg) & 3) == 0 && (op.pt < 0 || (op.pt & 3) == 0);
 }
 
+template <int MODE>
 __device__ __forceinline__ void epi_prefetch(const Op& op, const EpiCtx& ctx, int m, int n, EpiPre& pre) {
   pre.valid = (m < op.M) && epi_vec_ok(op, n);
   if (!pre.valid) return;
   const float* base = ctx.base;
-  if (op.epi == EPI_FWD) {
+  if (MODE == 0) {
     pre.a = __ldcg(reinterpret_cast<const float4*>(base + op.bias + n));
-  } else if (op.epi == EPI_DACT) {
+  } else if (MODE == 1) {
     pre.a = __ldcg(reinterpret_cast<const float4*>(base + op.aux + (i64)m * op.ld_aux + n));
   } else if (op.flags & DW_ADAM) {
     const i64 e = (i64)m * op.N + n;
@@ -141,14 +142,15 @@ __device__ __forceinline__ void epi_prefetch(const Op& op, const EpiCtx& ctx, in
   }
 }
 
+template <int MODE>
 __device__ __forceinline__ void epilogue_row4(const Op& op, const EpiCtx& ctx, int m, int n, float4 acc, EpiPre& pre,
                                               bool have_pre) {
   float* base = ctx.base;
   if (m >= op.M || n >= op.N) return;
-  if (!have_pre) epi_prefetch(op, ctx, m, n, pre);
+  if (!have_pre) epi_prefetch<MODE>(op, ctx, m, n, pre);
   const bool vec = pre.valid;
   float v[4] = {acc.x, acc.y, acc.z, acc.w};
-  if (op.epi == EPI_FWD) {
+  if (MODE == 0) {
     float* c = base + op.c + (i64)m * op.ldc + n;
     float* z = op.zout >= 0 ? base + op.zout + (i64)m * op.ldc + n : nullptr;
     if (vec) {
@@ -166,7 +168,7 @@ __device__ __forceinline__ void epilogue_row4(const Op& op, const EpiCtx& ctx, i
           c[j] = act_fwd(op.act, zz);
         }
     }
-  } else if (op.epi == EPI_DACT) {
+  } else if (MODE == 1) {
     float* c = base + op.c + (i64)m * op.ldc + n;
     if (vec) {
       *reinterpret_cast<float4*>(c) = make_float4(v[0] * act_dz(op.act, pre.a.x), v[1] * act_dz(op.act, pre.a.y),
@@ -404,19 +406,8 @@ __device__ __noinline__ void gemm_tile_impl(const Op& op, const EpiCtx& ctx, int
   pre.valid = false;
   float bpre[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // bias-row operands (p, m, v, target, step size, bc2) of dW
 
-  auto issue = [&](int s) {
-    float* st = smem + (s % GEMM_NS) * C::STAGE_FLOATS;
-    stage_load<BM, AKM>(st, A, lda, a_vec, m0, M, s * GEMM_BK, K);
-    stage_load<BN, BKM>(st + C::A_FLOATS, Bp, ldb, b_vec, n0, N, s * GEMM_BK, K);
-  };
-  // NS-deep ring; NS-1 stages go in flight before anything else (the whole K range when K <= 192)
-#pragma unroll
-  for (int s = 0; s < GEMM_NS - 1; ++s) {
-    if (s < nk) issue(s);
-    cp_async_commit();
-  }
   // epilogue operands travel while the pipeline fills
-  if (C::NV == 1) epi_prefetch(op, ctx, m0 + tid / (BN / 4), n0 + (tid % (BN / 4)) * 4, pre);
+  if (C::NV == 1) epi_prefetch<MODE>(op, ctx, m0 + tid / (BN / 4), n0 + (tid % (BN / 4)) * 4, pre);
   if (bias_tile && (op.flags & DW_ADAM) && tid < BM && m0 + tid < M) {
     bpre[0] = __ldcg(ctx.base + op.pb + m0 + tid);
     bpre[1] = __ldcg(ctx.base + op.pbm + m0 + tid);
@@ -426,23 +417,28 @@ __device__ __noinline__ void gemm_tile_impl(const Op& op, const EpiCtx& ctx, int
     bpre[5] = __ldcg(&ctx.scal->adam_bc2_sqrt[op.opt]);
   }
 
+  // NS-deep cp.async ring as ONE rolled loop (one copy of the load and math code per variant keeps the
+  // instruction footprint small: instruction-fetch stalls were 30% of this kernel's samples). Iteration j issues
+  // stage j and consumes stage j-(NS-1); for K <= 192 the whole K range is in flight before the first wait.
   float a_cur[8][4];
-  for (int it = 0; it < nk; ++it) {
-    // stages it and it+1 have landed after this wait (one-stage lookahead lets the fragment prefetch cross the
-    // stage boundary); the barrier also frees slot (it-1) % NS for the next load
-    cp_async_wait<GEMM_NS - 3>();
-    __syncthreads();
-    if (it == 0) {
-      SACX_TSTAMP(1);
-#if SACX_MATH_VARIANT == 0
-      load_a_block<C, AKM>(smem, kg * C::KPG, ty, a_cur);
-#endif
+#pragma unroll 1
+  for (int j = 0; j < nk + GEMM_NS - 1; ++j) {
+    const int it = j - (GEMM_NS - 1);
+    if (it >= 0) {
+      cp_async_wait<GEMM_NS - 3>();          // stages it and it+1 have landed
+      __syncthreads();                       // ... for everyone; slot (it-1) % NS is free again
+      if (it == 0) SACX_TSTAMP(1);
     }
-    if (it + GEMM_NS - 1 < nk) issue(it + GEMM_NS - 1);
+    if (j < nk) {
+      float* st = smem + (j % GEMM_NS) * C::STAGE_FLOATS;
+      stage_load<BM, AKM>(st, A, lda, a_vec, m0, M, j * GEMM_BK, K);
+      stage_load<BN, BKM>(st + C::A_FLOATS, Bp, ldb, b_vec, n0, N, j * GEMM_BK, K);
+    }
     cp_async_commit();
-    const float* st = smem + (it % GEMM_NS) * C::STAGE_FLOATS;
-    const float* sn = smem + ((it + 1) % GEMM_NS) * C::STAGE_FLOATS;
-    stage_math<C, AKM, BKM, BSUM>(st, sn, it + 1 < nk, kg, ty, tx, a_cur, acc, bsum);
+    if (it >= 0) {
+      const float* st = smem + (it % GEMM_NS) * C::STAGE_FLOATS;
+      stage_math<C, AKM, BKM, BSUM>(st, st, false, kg, ty, tx, a_cur, acc, bsum);
+    }
   }
   cp_async_wait<0>();
   __syncthreads();                         // all stages consumed: the ring can be reused for the reduction
@@ -477,7 +473,7 @@ __device__ __noinline__ void gemm_tile_impl(const Op& op, const EpiCtx& ctx, int
       const float4 p = *reinterpret_cast<const float4*>(&red[q * C::RBLK + row * RS + c4]);
       s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
     }
-    epilogue_row4(op, ctx, m0 + row, n0 + c4, s, pre, C::NV == 1);
+    epilogue_row4<MODE>(op, ctx, m0 + row, n0 + c4, s, pre, C::NV == 1);
   }
   if (BSUM) {
     if (bias_tile && tid < BM) {

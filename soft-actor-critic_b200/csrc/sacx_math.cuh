@@ -103,7 +103,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 // N(0,1) for element (update, which, global row, j): Box-Muller on two Philox words
-__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long update, int which,
+__device__ __noinline__ float philox_normal(unsigned long long seed, unsigned long long update, int which,
                                                uint32_t row, uint32_t j, uint32_t agent) {
   uint32_t o[4];
   philox4x32_10((uint32_t)update, (uint32_t)(update >> 32), row, ((uint32_t)which << 24) | j,
@@ -123,7 +123,7 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   return x;
 }
 
-__device__ __forceinline__ unsigned long long feistel_index(unsigned long long i, unsigned long long n,
+__device__ __noinline__ unsigned long long feistel_index(unsigned long long i, unsigned long long n,
                                                             unsigned long long seed, unsigned long long counter,
                                                             uint32_t agent) {
   if (n <= 1) return 0;

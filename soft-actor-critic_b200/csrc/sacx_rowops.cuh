@@ -31,7 +31,7 @@ struct RowCtx {
 
 // ---- staging helpers -------------------------------------------------------------------------------
 // copy n floats global -> shared by the whole CTA (cp.async when 16B-aligned, scalar otherwise)
-__device__ __forceinline__ void stage_vec(float* dst, const float* src, int n) {
+__device__ __noinline__ void stage_vec(float* dst, const float* src, int n) {
   if (((n & 3) == 0) && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 15) == 0)) {
     for (int i = threadIdx.x * 4; i < n; i += 1024) cp_async16(dst + i, src + i, 16);
   } else {
@@ -70,7 +70,7 @@ __device__ __forceinline__ float row_dot_partial(const RowReg& r, const float* _
   return s;
 }
 // generic fallback: both operands wherever they live
-__device__ __forceinline__ float warp_dot_any(const float* __restrict__ h, const float* __restrict__ w, int K, int lane) {
+__device__ __noinline__ float warp_dot_any(const float* __restrict__ h, const float* __restrict__ w, int K, int lane) {
   float s = 0.f;
   for (int k = lane; k < K; k += 32) s = fmaf(__ldcg(h + k), w[k], s);
   return s;

@@ -55,3 +55,9 @@ for p in range(P):
         continue
     d = lambda a, b: int(np.median((x[..., a] - x[..., b])[ok]))
     print(f"{p:5d} {d(1,0):7d} {d(2,1):7d} {d(3,2):7d} {d(4,3):7d} {d(4,0):7d}")
+
+if len(sys.argv) > 3:
+    for p in [int(x) for x in sys.argv[3].split(",")]:
+        wk = np.median(work[:, p - 1, :], axis=0).astype(int)
+        print(f"phase {p} work per CTA (cycles), CTA index = first tile index:")
+        print(" ".join(f"{i}:{v}" for i, v in enumerate(wk)))
