@@ -420,7 +420,7 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   if ((rc = e.build_plans())) { delete h; return rc; }
   // launch geometry: one CTA per SM; a single agent spreads over the chip, a population gets one CTA per agent
   const size_t gemm_floats = e.large ? CfgLarge::SMEM_FLOATS : CfgSmall::SMEM_FLOATS;
-  e.smem_bytes = (int)(SMEM_OPS * sizeof(Op) + WSM_FLOATS * 4 + gemm_floats * 4);
+  e.smem_bytes = (int)(SMEM_OPS * sizeof(Op) + WSM_FLOATS * 4 + gemm_floats * 4 + XSM_FLOATS * 4);
   const void* fn = e.large ? (const void*)sacx_run_kernel<true> : (const void*)sacx_run_kernel<false>;
   SACX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e.smem_bytes));
   int per_sm = 0;

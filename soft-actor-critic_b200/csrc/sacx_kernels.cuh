@@ -71,14 +71,15 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
   for (int agent = blockIdx.y; agent < args.n_agents; agent += gridDim.y) {
     float* base = args.arena + (i64)agent * args.agent_stride;
     AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
-    RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, C::SMEM_FLOATS};
-    EpiCtx ec{base, scal, &args.hp, nullptr};
+    RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, C::SMEM_FLOATS, nullptr};
+    EpiCtx ec{base, scal, &args.hp, nullptr, gsm + C::SMEM_FLOATS};
+    const FusedCtx fcx{base, scal, &args.hp, gsm + C::SMEM_FLOATS};
     const bool last_agent = (agent + (int)gridDim.y >= args.n_agents);
     for (int step = 0; step < args.n_steps; ++step) {
       rc.step = step;
       for (int p = args.phase_begin; p < args.phase_end; ++p) {
         const Phase ph = sphase[p];
-        if (args.dbg2) ec.t = args.dbg2 + (((size_t)step * (args.phase_end - args.phase_begin) + (p - args.phase_begin)) * gridDim.x + blockIdx.x) * 8;
+        if (args.dbg2) rc.t = ec.t = args.dbg2 + (((size_t)step * (args.phase_end - args.phase_begin) + (p - args.phase_begin)) * gridDim.x + blockIdx.x) * 8;
         for (int t = blockIdx.x; t < ph.ntiles; t += gridDim.x) {
           int oi = ph.op0;
           while (oi + 1 < ph.op0 + ph.nops && t >= ops[oi + 1].tile0) ++oi;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
             case OP_ACTOR_BWD: tile_actor_bwd(op, rc, lt); __syncthreads(); break;
             case OP_PROLOGUE: if (tid == 0) op_prologue(op, rc); break;
             case OP_FINAL: if (warp == 0) op_final(op, rc, lane); break;
+            case OP_DW_HEAD: tile_dw_head(op, fcx, lt, gsm); break;
             case OP_POLYAK: op_polyak(op, rc, lt); break;
             case OP_ADAM_FLAT: op_adam_flat(op, rc, lt); break;
             default: break;

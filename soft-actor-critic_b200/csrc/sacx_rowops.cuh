@@ -27,7 +27,9 @@ struct RowCtx {
   float* wsm;          // per-warp shared scratch, 4*SACX_MAX_ACT floats
   float* tsm;          // CTA-wide shared staging area (aliases the GEMM ring), tsm_floats floats
   int tsm_floats;
+  unsigned long long* t;   // optional timestamps (profiling aid)
 };
+#define SACX_RSTAMP(i) do { if (c.t && threadIdx.x == 0) c.t[i] = clock64(); } while (0)
 
 // ---- staging helpers -------------------------------------------------------------------------------
 // copy n floats global -> shared by the whole CTA (cp.async when 16B-aligned, scalar otherwise)
@@ -124,6 +126,7 @@ __device__ __forceinline__ void op_gather(const Op& op, const RowCtx& c, int row
 // o[0]=h(last hidden) o[1]=W_L o[2]=b_L o[3]=X(dest, action at col obs+j) o[4]=lp o[5]=eps buf
 // o[6]=tz o[7]=se o[8]=mask o[9]=headz (each -1 when not saved)   i[0]=ldh i[1]=K i[2]=ldx   mode: 1 target / 2 actor
 __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int tile) {
+  SACX_RSTAMP(0);
   const RunArgs& a = *c.args;
   const Hyper& hp = a.hp;
   float* base = c.base;
@@ -151,7 +154,8 @@ __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int til
     if (fast && in) row_load(hr, h, K, lane);
     stage_finish();
   }
-  if (!in) return;
+  SACX_RSTAMP(1); SACX_RSTAMP(2); SACX_RSTAMP(3);
+  if (!in) { SACX_RSTAMP(4); return; }
   const float* W = staged ? Ws : Wg;
   float* hs = c.wsm;                      // head post-activation [2A], then pre-activation [2A]
   for (int j = 0; j < 2 * A; ++j) {
@@ -193,6 +197,7 @@ __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int til
   if (lane == 0) base[op.o[4] + row] = lp;
   if (bad) atomicOr(&c.scal->nonfinite, 1);
   __syncwarp();
+  SACX_RSTAMP(4);
 }
 
 // ---------------------------------------------------------------- OP_Q_ROW: target y (mode & 1) and / or critic delta (mode & 2)
@@ -200,6 +205,7 @@ __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int til
 // critic: o[12..13]=hq(last hidden) o[14..15]=aux(z or h) o[16..17]=W_L o[18..19]=b_L o[20..21]=q out o[22..23]=dout
 //         o[24..25]=delta(last hidden) o[26..27]=lossrow          i[0]=ldh i[1]=K      (y read from o[9] or y_ext)
 __device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile) {
+  SACX_RSTAMP(0);
   const Hyper& hp = c.args->hp;
   float* base = c.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,7 +248,8 @@ __device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile)
     }
     stage_finish();
   }
-  if (!in) return;
+  SACX_RSTAMP(1); SACX_RSTAMP(2); SACX_RSTAMP(3);
+  if (!in) { SACX_RSTAMP(4); return; }
   float y = 0.f;
   if (do_t) {
     float tq[2];
@@ -274,7 +281,7 @@ __device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile)
       const float dout = (2.f * diff / (float)hp.B_global) * act_dz2(op.act_out, z, q);
       if (lane == 0) {
         base[op.o[20 + n] + row] = q;
-        base[op.o[22 + n] + row] = dout;
+        base[op.o[22 + n] + (i64)row * 4] = dout;
         base[op.o[26 + n] + row] = diff * diff;
       }
       float* dl = base + op.o[24 + n] + (i64)row * ld;
@@ -295,11 +302,13 @@ __device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile)
       }
     }
   }
+  SACX_RSTAMP(4);
 }
 
 // ---------------------------------------------------------------- OP_ACTOR_Q
 // o[0..1]=hq(last hidden) o[2..3]=aux o[4..5]=W_L o[6..7]=b_L o[8]=lp o[9..10]=q out o[13..14]=delta o[15]=plossrow
 __device__ __noinline__ void tile_actor_q(const Op& op, const RowCtx& c, int tile) {
+  SACX_RSTAMP(0);
   const Hyper& hp = c.args->hp;
   float* base = c.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -329,7 +338,8 @@ __device__ __noinline__ void tile_actor_q(const Op& op, const RowCtx& c, int til
     }
     stage_finish();
   }
-  if (!in) return;
+  SACX_RSTAMP(1); SACX_RSTAMP(2); SACX_RSTAMP(3);
+  if (!in) { SACX_RSTAMP(4); return; }
   float q[2], z[2];
 #pragma unroll
   for (int n = 0; n < 2; ++n) {
@@ -367,6 +377,7 @@ __device__ __noinline__ void tile_actor_q(const Op& op, const RowCtx& c, int til
       for (int k = lane; k < K; k += 32) dl[k] = dout * W[k] * act_dz(op.act, __ldcg(ax[n] + k));
     }
   }
+  SACX_RSTAMP(4);
 }
 
 // ---------------------------------------------------------------- OP_ACTOR_BWD
@@ -374,6 +385,7 @@ __device__ __noinline__ void tile_actor_q(const Op& op, const RowCtx& c, int til
 // o[4]=tz o[5]=se o[6]=mask o[7]=headz o[8]=dhead out o[9]=Wpi_L o[11]=aux pi(last hidden) o[12]=delta pi(last hidden)
 // i[0]=ld delta0  i[1]=H0q  i[2]=ldW0 (=obs+act)  i[3]=ld pi hidden  i[4]=Kpi
 __device__ __noinline__ void tile_actor_bwd(const Op& op, const RowCtx& c, int tile) {
+  SACX_RSTAMP(0);
   const Hyper& hp = c.args->hp;
   float* base = c.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -410,7 +422,8 @@ __device__ __noinline__ void tile_actor_bwd(const Op& op, const RowCtx& c, int t
     if (fast && in) { row_load(dr[0], d0[0], H0, lane); row_load(dr[1], d0[1], H0, lane); row_load(ap, auxp, Kp, lane); }
     stage_finish();
   }
-  if (!in) return;
+  SACX_RSTAMP(1); SACX_RSTAMP(2); SACX_RSTAMP(3);
+  if (!in) { SACX_RSTAMP(4); return; }
   float* da = c.wsm;                          // [A] dQ/da, then dhead [2A]
   float* dh = c.wsm + SACX_MAX_ACT;
   // d(-minQ)/d a_j = sum_c sum_h delta0_c[h] * W0_c[h, obs + j]
@@ -473,6 +486,7 @@ __device__ __noinline__ void tile_actor_bwd(const Op& op, const RowCtx& c, int t
     }
   }
   __syncwarp();
+  SACX_RSTAMP(4);
 }
 
 // ---------------------------------------------------------------- OP_PROLOGUE (one thread)

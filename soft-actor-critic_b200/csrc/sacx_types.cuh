@@ -20,6 +20,7 @@ enum OpType : int {
   OP_POLYAK,      // standalone soft target update (a10)
   OP_ADAM_FLAT,   // Adam over a packed gradient block (data-parallel apply)
   OP_LOAD_EXT,    // copy external y / logpi into arena buffers
+  OP_DW_HEAD,     // fused plan: gradient + Adam of the critics' output layer from the head shares
 };
 
 enum Epi : int { EPI_FWD = 1, EPI_DACT = 2, EPI_DW = 3 };

@@ -318,3 +318,107 @@ def test_population_agents_are_independent_and_match_single_agent():
         # different tile configuration (64x64 vs 32x32) => different summation order: tolerance, not bits
         assert_close(f"agent {ag} params", got, singles[ag], 2e-5)
         assert pop.metrics(ag)["updates"] == K
+
+
+# ----------------------------------------------------------------------------- edge shapes and the fused-rows plan
+def _random_nets(obs, act, hidden_pi, hidden_q, seed=0, scale=0.3):
+    rng = np.random.default_rng(seed)
+    sds = {}
+    for tag, dims in (("pi", [obs] + list(hidden_pi) + [2 * act]), ("q1", [obs + act] + list(hidden_q) + [1]),
+                      ("q2", [obs + act] + list(hidden_q) + [1])):
+        sd = {}
+        for l in range(len(dims) - 1):
+            sd[f"net.{2 * l}.weight"] = (rng.standard_normal((dims[l + 1], dims[l])) * scale).astype(np.float32)
+            sd[f"net.{2 * l}.bias"] = (rng.standard_normal(dims[l + 1]) * 0.1).astype(np.float32)
+        sds[tag] = sd
+    return sds
+
+
+@pytest.mark.parametrize("obs,act,hp,hq,B,actfn", [
+    (7, 5, (33, 17), (19, 23), 50, "tanh"),          # nothing aligned: scalar loaders / epilogues, ragged tiles, B % 8 != 0
+    (3, 1, (5,), (6,), 9, "gelu"),                   # single hidden layer, tiny
+    (11, 32, (64, 40), (48, 36), 70, "relu"),        # maximum action dimension
+    (24, 4, (320, 300), (288, 260), 96, "elu"),      # hidden wider than one 256-wide K ring / register-resident row path
+    (6, 2, (16, 16, 16, 16), (12, 12, 12), 40, "selu"),   # deep networks
+])
+def test_update_edge_shapes_vs_oracle(obs, act, hp, hq, B, actfn):
+    """One fused update on awkward shapes against the NumPy oracle (no golden needed: the oracle is pinned)."""
+    from oracle.sac_numpy import Hyper, SACOracle, mlp_from_state_dict
+    from sac.engine import UpdateEngine
+    from sac.replay_buffer import ReplayBuffer
+    cfg = base_config(hidden=hp, q_hidden=hq, act=actfn, batch=B, capacity=500)
+    eng = UpdateEngine(obs, act, cfg)
+    sds = _random_nets(obs, act, hp, hq)
+    load_nets(eng, sds)
+    eng.reset_state()
+    rb = ReplayBuffer(500, obs, act)
+    S, A, R, S2, D = fill_ring(rb, 300, obs, act)
+    eng.attach_ring(rb)
+    o = SACOracle(mlp_from_state_dict(sds["pi"], actfn, "identity"), mlp_from_state_dict(sds["q1"], actfn, "identity"),
+                  mlp_from_state_dict(sds["q2"], actfn, "identity"), Hyper())
+    rng = np.random.default_rng(3)
+    for k in range(2):
+        idx = rng.choice(300, B, replace=False).astype(np.int64)
+        e1 = rng.standard_normal((B, act)).astype(np.float32)
+        e2 = rng.standard_normal((B, act)).astype(np.float32)
+        m = eng.update_host(idx, e1, e2, 1)
+        o.update(S[idx], A[idx], R[idx], S2[idx], D[idx], e1, e2)
+        assert m["nonfinite"] == 0
+        assert_close("y", eng.view("out.y").cpu().numpy().ravel(), o.last["y"], 1e-4)
+        assert_close("logpi", eng.view("out.logpi").cpu().numpy().ravel(), o.last["lp"], 1e-4)
+        assert abs(float(eng.view("scal.log_alpha").item()) - float(o.log_alpha)) < 5e-6
+    for tag, net in (("pi", o.pi), ("q1", o.q1), ("q2", o.q2), ("q1t", o.q1t)):
+        for l, (w, b) in enumerate(zip(net.W, net.b)):
+            assert_close(f"{tag}.W{l}", eng.view(f"{tag}.W{l}").cpu().numpy(), w, 3e-4)
+            assert_close(f"{tag}.b{l}", eng.view(f"{tag}.b{l}").cpu().numpy().ravel(), b, 3e-4)
+
+
+@pytest.mark.parametrize("name", ["tiny_auto", "acts_tanh", "acts_leaky_relu", "bipedal", "pendulum128"])
+def test_fused_rows_plan_vs_reference(name, monkeypatch):
+    """SACX_FUSE_ROWS=1: row phases folded into the GEMM tiles (13 phases instead of 16). Same reference vectors."""
+    from sac.replay_buffer import ReplayBuffer
+    monkeypatch.setenv("SACX_FUSE_ROWS", "1")
+    g = Golden(name)
+    eng = engine_from_golden(g)
+    rb = ReplayBuffer(g.cfg["buffer"]["capacity"], g.obs, g.act)
+    fill_ring(rb, g.n_fill, g.obs, g.act)
+    eng.attach_ring(rb)
+    nl_pi, nl_q = len(g.cfg["policy_net"]["hidden_sizes"]) + 1, len(g.cfg["q_net"]["hidden_sizes"]) + 1
+    for k in range(g.K):
+        m = eng.update_host(g[f"step{k}/idx"], g[f"step{k}/eps1"], g[f"step{k}/eps2"], 1)
+        tol = 3e-5 * (3 ** k)
+        assert_close(f"step{k} y", eng.view("out.y").cpu().numpy().ravel(), g[f"step{k}/y"], tol)
+        assert_close(f"step{k} logpi", eng.view("out.logpi").cpu().numpy().ravel(), g[f"step{k}/lp"], tol)
+        assert abs(m["q1_loss"] - float(g[f"step{k}/q1_loss"])) <= 10 * tol * abs(float(g[f"step{k}/q1_loss"])) + 1e-7
+        if g.cfg["sac"]["auto_entropy_tuning"]:
+            assert abs(m["log_alpha"] - float(g[f"step{k}/log_alpha"])) < 2e-6
+        for tag, nl in (("pi", nl_pi), ("q1", nl_q), ("q2", nl_q), ("q1t", nl_q), ("q2t", nl_q)):
+            for nm, v in read_net(eng, tag, nl).items():
+                key = f"step{k}/{tag}/{nm}"
+                if g.full:
+                    assert_close(key, v, g[key], 1e-4 * (2 ** k))
+                else:
+                    assert_close(key + "#smp", v.ravel()[::97], g[key + "#smp"], 1e-4 * (2 ** k))
+
+
+def test_full_size_ring_properties():
+    """BASELINE config 2 size: 1M transitions (216 MB). Size-independent properties: the gather of every logical index
+    returns the row that was pushed there (round trip, bit-exact) before and after wrap-around."""
+    from sac.replay_buffer import ReplayBuffer
+    N, O, A = 1_000_000, 24, 4
+    rb = ReplayBuffer(N, O, A)
+    ids = torch.arange(N + 300_000, device="cuda", dtype=torch.float32)
+    for lo in range(0, N + 300_000, 260_000):                 # 1.3M pushes: wraps past capacity
+        blk = ids[lo: lo + 260_000]
+        s = blk[:, None] + torch.arange(O, device="cuda", dtype=torch.float32)[None, :] * 0.5
+        rb.push_device(s, blk[:, None].repeat(1, A), -blk, s + 1, (blk % 2))
+    assert len(rb) == N
+    oldest = 300_000
+    idx = torch.randint(0, N, (65536,), device="cuda")
+    got = rb.sample_tensors(65536, indices=idx)
+    want = (idx + oldest).float()
+    assert torch.equal(got.reward, -want) and torch.equal(got.action[:, 0], want)
+    assert torch.equal(got.state[:, 3], want + 1.5) and torch.equal(got.next_state[:, 0], want + 1.0)
+    assert torch.equal(got.done, want % 2)
+    dev_idx = rb.device_indices(4096, seed=1, counter=9)
+    assert dev_idx.unique().numel() == 4096 and int(dev_idx.max()) < N
