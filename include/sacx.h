@@ -152,6 +152,9 @@ int sacx_agent_reset_state(sacx_agent_t h);
 /* re-derive alpha (f32/f64) from log_alpha after a checkpoint load (agent.py:549-554) */
 int sacx_agent_refresh_alpha(sacx_agent_t h);
 int sacx_agent_grid(sacx_agent_t h, int32_t* ctas_per_agent, int32_t* agent_slots, int32_t* smem_bytes);
+/* which kernel executes sacx_update: 1 = row-parallel cluster kernel (8-CTA clusters own 16-row blocks, 3xTF32 tensor-core
+ * tiles), 0 = tile-parallel persistent kernel (any shape). reason (may be NULL) receives a short text when 0. */
+int sacx_agent_path(sacx_agent_t h, char* reason, int32_t capacity);
 
 /* replaces SAC.training_step (agent.py:302-327), n_steps consecutive updates in ONE launch of the
  * persistent fused kernel: gather -> target -> critic Adam x2 -> actor Adam -> alpha -> Polyak.

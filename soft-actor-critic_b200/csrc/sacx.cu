@@ -153,6 +153,59 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
   return launch(pb, pe, n_steps, dim3(e->grid_x, e->grid_y), coop && !single_pass);
 }
 
+// Row-parallel launch: n_groups x 8 CTAs, cooperative (all CTAs co-resident: grid and group barriers spin).
+
+static int engine_launch_rp(Engine* e, int n_steps, const RunArgs& proto) {
+  RunArgs a = proto;
+  a.arena = e->arena; a.agent_stride = e->stride; a.scal_off = e->scal_off; a.hp = e->hp;
+  a.n_agents = 1; a.barrier = e->d_barrier; a.ctas_per_agent = e->rp_grid; a.barrier_mode = e->barrier_mode;
+  a.n_steps = n_steps; a.phase_begin = 0; a.phase_end = 2;
+  if (e->ring) {
+    Ring* r = e->ring;
+    a.ring = r->dev; a.ring_stride = r->stride; a.ring_capacity = r->cap;
+    a.ring_s = r->off_s; a.ring_a = r->off_a; a.ring_r = r->off_r; a.ring_s2 = r->off_s2; a.ring_d = r->off_d;
+  }
+  a.rp_part = e->d_rp_part;
+  SACX_CUDA(cudaMemsetAsync(e->d_barrier, 0, sizeof(unsigned) * 64 * (1 + RP_MAX_GROUPS), e->stream));
+  const Plan* dplan = e->d_plans + PLAN_RP;
+  const RpProgram* dprog = e->d_prog;
+  void* kargs[] = {(void*)&dplan, (void*)&dprog, (void*)&a};
+  SACX_CUDA(cudaLaunchCooperativeKernel((const void*)sacx_rp_kernel, dim3(e->rp_grid), dim3(256), kargs, (size_t)e->rp_smem_bytes, e->stream));
+  ++e->launches;
+  return SACX_OK;
+}
+
+static int engine_setup_rp(Engine* e) {
+  if (!e->rp) return SACX_OK;
+  auto off = [&](const std::string& why) { e->rp = false; e->rp_why = why; cudaGetLastError(); return SACX_OK; };
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, sacx_rp_kernel) != cudaSuccess) return off("cudaFuncGetAttributes failed");
+  e->rp_smem_bytes = e->h_prog.sm_total * 4;
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if ((size_t)e->rp_smem_bytes + fa.sharedSizeBytes > (size_t)max_optin) return off("shared memory budget exceeded");
+  if (cudaFuncSetAttribute(sacx_rp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->rp_smem_bytes) != cudaSuccess)
+    return off("cannot raise the dynamic shared memory limit");
+  const int nrb = (e->cfg.batch_size + RP_RB - 1) / RP_RB;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sacx_rp_kernel, 256, (size_t)e->rp_smem_bytes) != cudaSuccess || per_sm < 1)
+    return off("row-parallel kernel does not fit on an SM");
+  int n_groups = std::min(e->n_sms / RP_CS, RP_MAX_GROUPS);
+  const char* env = getenv("SACX_RP_GROUPS");
+  if (env && atoi(env) > 0) n_groups = std::min(n_groups, atoi(env));
+  if (n_groups < 1) return off("fewer than 8 SMs");
+  // balanced rounds: with 16 row blocks and 18 possible groups, 16 groups do one round each
+  const int rounds = (nrb + n_groups - 1) / n_groups;
+  n_groups = (nrb + rounds - 1) / rounds;
+  e->rp_grid = n_groups * RP_CS;
+  SACX_CUDA(cudaMalloc((void**)&e->d_rp_part, sizeof(float) * (size_t)RP_MAX_GROUPS * e->h_prog.part_stride));
+  SACX_CUDA(cudaMemset(e->d_rp_part, 0, sizeof(float) * (size_t)RP_MAX_GROUPS * e->h_prog.part_stride));
+  SACX_CUDA(cudaMalloc((void**)&e->d_prog, sizeof(RpProgram)));
+  SACX_CUDA(cudaMemcpy(e->d_prog, &e->h_prog, sizeof(RpProgram), cudaMemcpyHostToDevice));
+  return SACX_OK;
+}
+
 static int engine_init_scalars(Engine* e) {
   AgentScalars s;
   memset(&s, 0, sizeof s);
@@ -418,6 +471,7 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   hp.B_global = cfg->batch_size * e.cfg.dp_world; hp.row0_global = cfg->batch_size * e.cfg.dp_rank;
   hp.seed = cfg->seed;
   if ((rc = e.build_plans())) { delete h; return rc; }
+  if ((rc = engine_setup_rp(&e))) { delete h; return rc; }
   // launch geometry: one CTA per SM; a single agent spreads over the chip, a population gets one CTA per agent
   const size_t gemm_floats = e.large ? CfgLarge::SMEM_FLOATS : CfgSmall::SMEM_FLOATS;
   e.smem_bytes = (int)(SMEM_OPS * sizeof(Op) + WSM_FLOATS * 4 + gemm_floats * 4 + XSM_FLOATS * 4);
@@ -460,6 +514,8 @@ int sacx_agent_destroy(sacx_agent_t h) {
   cudaStreamSynchronize(e.stream);
   if (e.own_arena && e.arena) cudaFree(e.arena);
   if (e.d_plans) cudaFree(e.d_plans);
+  if (e.d_prog) cudaFree(e.d_prog);
+  if (e.d_rp_part) cudaFree(e.d_rp_part);
   if (e.d_barrier) cudaFree(e.d_barrier);
   if (e.pinned_metrics) cudaFreeHost(e.pinned_metrics);
   if (e.pinned_io) cudaFreeHost(e.pinned_io);
@@ -496,10 +552,16 @@ int sacx_agent_layout(sacx_agent_t h, sacx_tensor_desc* out, int32_t capacity, i
 
 int sacx_agent_grid(sacx_agent_t h, int32_t* gx, int32_t* gy, int32_t* smem) {
   if (!h) return fail(SACX_ERR_INVALID, "null agent");
-  if (gx) *gx = h->e.grid_x;
+  if (gx) *gx = h->e.rp ? h->e.rp_grid : h->e.grid_x;
   if (gy) *gy = h->e.grid_y;
-  if (smem) *smem = h->e.smem_bytes;
+  if (smem) *smem = h->e.rp ? h->e.rp_smem_bytes : h->e.smem_bytes;
   return SACX_OK;
+}
+
+int sacx_agent_path(sacx_agent_t h, char* reason, int32_t capacity) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  if (reason && capacity > 0) snprintf(reason, (size_t)capacity, "%s", h->e.rp ? "" : h->e.rp_why.c_str());
+  return h->e.rp ? 1 : 0;
 }
 
 int sacx_agent_reset_state(sacx_agent_t h) {
@@ -551,6 +613,7 @@ static int do_update(sacx_agent_t h, const int64_t* idx, const float* e1, const 
   RunArgs a;
   memset(&a, 0, sizeof a);
   a.idx_ext = (const i64*)idx; a.eps1_ext = e1; a.eps2_ext = e2;
+  if (e.rp && !staged) return engine_launch_rp(&e, n_steps, a);
   return engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, staged);
 }
 
@@ -618,7 +681,7 @@ static int host_update_submit(Engine& e, int slot, const int64_t* idx, const flo
   RunArgs a;
   memset(&a, 0, sizeof a);
   a.idx_ext = d_idx; a.eps1_ext = d_e1; a.eps2_ext = d_e2;
-  rc = engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
+  rc = e.rp ? engine_launch_rp(&e, n_steps, a) : engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
   if (rc) return rc;
   // the step's result travels back right behind the kernel (metrics block of agent 0)
   io.metrics_off = (off + 255) & ~(size_t)255;
@@ -853,16 +916,17 @@ int sacx_debug_profile(sacx_agent_t h, int32_t n_steps, uint64_t* out_host, int6
   Engine& e = h->e;
   int rc = need_ring(e, true);
   if (rc) return rc;
-  const int np = e.h_plans[PLAN_FUSED].n_phases;
-  const size_t words = (size_t)n_steps * np * e.grid_x * 10;
+  const int np = e.rp ? 4 : e.h_plans[PLAN_FUSED].n_phases;
+  const int gx = e.rp ? e.rp_grid : e.grid_x;
+  const size_t words = (size_t)n_steps * np * gx * 10;
   if ((int64_t)words > capacity) return fail(SACX_ERR_INVALID, "debug_profile: output too small");
   unsigned long long* d = nullptr;
   SACX_CUDA(cudaMalloc((void**)&d, words * 8));
   SACX_CUDA(cudaMemset(d, 0, words * 8));
   RunArgs a; memset(&a, 0, sizeof a);
   a.dbg = d;
-  a.dbg2 = d + (size_t)n_steps * np * e.grid_x * 2;
-  rc = engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
+  a.dbg2 = d + (size_t)n_steps * np * gx * 2;
+  rc = e.rp ? engine_launch_rp(&e, n_steps, a) : engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
   if (!rc) {
     cudaError_t ce = cudaStreamSynchronize(e.stream);
     if (ce == cudaSuccess) ce = cudaMemcpy(out_host, d, words * 8, cudaMemcpyDeviceToHost);
@@ -870,7 +934,7 @@ int sacx_debug_profile(sacx_agent_t h, int32_t n_steps, uint64_t* out_host, int6
   }
   cudaFree(d);
   if (n_phases) *n_phases = np;
-  if (n_ctas) *n_ctas = e.grid_x;
+  if (n_ctas) *n_ctas = gx;
   return rc;
 }
 

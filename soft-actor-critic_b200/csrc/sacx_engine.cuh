@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "sacx_kernels.cuh"
+#include "sacx_rowpar.cuh"
 
 namespace sacx {
 
@@ -40,7 +41,7 @@ struct ActSet {                                         // hidden activations of
 };
 
 enum PlanId { PLAN_FUSED = 0, PLAN_SAMPLE, PLAN_TARGET, PLAN_CRITIC, PLAN_CRITIC_GRADS, PLAN_ACTOR, PLAN_ACTOR_GRADS,
-              PLAN_ALPHA, PLAN_POLYAK, PLAN_APPLY_Q, PLAN_APPLY_Q_POLYAK, PLAN_APPLY_PI, PLAN_FUSED_NOGATHER, PLAN_ALPHA_APPLY, N_PLANS };
+              PLAN_ALPHA, PLAN_POLYAK, PLAN_APPLY_Q, PLAN_APPLY_Q_POLYAK, PLAN_APPLY_PI, PLAN_FUSED_NOGATHER, PLAN_ALPHA_APPLY, PLAN_RP, N_PLANS };
 
 struct Ring;
 
@@ -81,6 +82,13 @@ struct Engine {
   long long launches = 0;
   unsigned long long act_calls = 0;
   Hyper hp;
+  // row-parallel cluster path (sacx_rowpar.cuh): single agent, 2+ hidden layers of width 64/128/256
+  bool rp = false;
+  RpProgram h_prog;
+  RpProgram* d_prog = nullptr;
+  float* d_rp_part = nullptr;
+  int rp_grid = 0, rp_smem_bytes = 0;
+  std::string rp_why;
 
   // ---------------------------------------------------------------- layout
   i64 alloc(const std::string& name, int rows, int cols, int ld = -1, int dtype = 0) {
@@ -685,6 +693,205 @@ struct Engine {
     if (k == bwd_stages(n) - 1) pb.add(gemm_dw(n, 0, opt, flags, delta[0], ldd(0), x, ld_x, is_critic));
   }
 
+  // ---- row-parallel program (sacx_rowpar.cuh) -----------------------------------------------------------------------
+  bool rowpar_eligible(std::string& why) const {
+    const char* env = getenv("SACX_ROWPAR");
+    if (env && atoi(env) == 0) { why = "disabled by SACX_ROWPAR=0"; return false; }
+    if (cfg.n_agents != 1) { why = "population mode"; return false; }
+    if (cfg.dp_world > 1) { why = "data-parallel mode"; return false; }
+    if (pi.L() < 2 || q1.L() < 2) { why = "fewer than two hidden layers"; return false; }
+    if (act_needs_z(pi.act_h) || act_needs_z(q1.act_h)) { why = "hidden activation needs saved pre-activations"; return false; }
+    if (cfg.act_dim > RP_MAXA) { why = "action dimension above 8"; return false; }
+    if (2 * cfg.obs_dim + cfg.act_dim + 2 > 256) { why = "observation wider than 123"; return false; }
+    for (const NetLayout* n : {&pi, &q1})
+      for (int l = 1; l <= n->L(); ++l)
+        if (n->dims[l] != 64 && n->dims[l] != 128 && n->dims[l] != 256) { why = "hidden width not 64/128/256"; return false; }
+    if (2 * (q1.L() + 1) + (pi.L() + 1) + 1 > RP_MAX_DW_OPS) { why = "network too deep"; return false; }
+    return true;
+  }
+
+  bool build_rowpar(PB& pb) {
+    RpProgram& P = h_prog;
+    memset(&P, 0, sizeof P);
+    const int O = cfg.obs_dim, A = cfg.act_dim, Lq = q1.L(), Lp = pi.L();
+    bool overflow = false;
+    int wmax = 0;
+    auto step = [&](int row_op) {
+      if (P.n_steps_a + P.n_steps_c >= RP_MAX_STEPS) { overflow = true; return; }
+      RpStep& st = P.steps[P.n_steps_a + P.n_steps_c];
+      st.row_op = row_op; st.job0 = P.n_jobs; st.njobs = 0; st.load0 = P.n_loads; st.nloads = 0;
+    };
+    auto cur = [&]() -> RpStep& { return P.steps[P.n_steps_a + P.n_steps_c]; };
+    auto add_job = [&](const RpJob& j) {
+      if (P.n_jobs >= RP_MAX_JOBS) { overflow = true; return; }
+      P.jobs[P.n_jobs++] = j; cur().njobs++;
+      const int NS = j.N / RP_CS;
+      wmax = std::max(wmax, j.bkm ? j.K * NS : NS * (j.Kp + 4));
+    };
+    auto add_load = [&](i64 off, int ld, int K, int abuf) {
+      if (P.n_loads >= RP_MAX_LOADS) { overflow = true; return; }
+      P.loads[P.n_loads++] = RpLoad{off, ld, K, abuf, 0}; cur().nloads++;
+    };
+    auto fwd = [&](const NetLayout& n, int l, i64 wshift, int a_src, const ActSet& as, int slot) {
+      RpJob j; memset(&j, 0, sizeof j);
+      j.bkm = 0; j.a_src = a_src; j.K = n.dims[l]; j.Kp = (j.K + 7) & ~7; j.N = n.dims[l + 1]; j.act = n.act_h;
+      j.ns_log2 = j.N == 256 ? 5 : (j.N == 128 ? 4 : 3);
+      j.w = n.W[l] + wshift; j.w_ld = j.K; j.bias = n.b[l] + wshift; j.out = as.h[l]; j.out_ld = as.ld[l]; j.aux = -1; j.proj_w = -1;
+      if (l == n.L() - 1) {
+        j.proj_J = n.dims[n.L() + 1]; j.proj_slot = slot; j.proj_w = n.W[n.L()] + wshift; j.proj_sj = n.dims[n.L()]; j.proj_sn = 1;
+      }
+      return j;
+    };
+    // delta_l (full rows in a_src) -> delta_{l-1} slice, through W_l
+    auto bwd = [&](const NetLayout& n, int l, int a_src, const ActSet& as, const i64* delta, int da_slot) {
+      RpJob j; memset(&j, 0, sizeof j);
+      j.bkm = 1; j.a_src = a_src; j.K = n.dims[l + 1]; j.Kp = j.K; j.N = n.dims[l]; j.act = n.act_h;
+      j.ns_log2 = j.N == 256 ? 5 : (j.N == 128 ? 4 : 3);
+      j.w = n.W[l]; j.w_ld = n.dims[l]; j.bias = -1; j.aux = as.h[l - 1]; j.aux_ld = as.ld[l - 1];
+      j.out = delta[l - 1]; j.out_ld = rup4(n.dims[l]); j.proj_w = -1;
+      if (da_slot >= 0) { j.proj_J = A; j.proj_slot = da_slot; j.proj_w = n.W[0] + O; j.proj_sj = 1; j.proj_sn = n.dims[0]; }
+      return j;
+    };
+    const i64 tsh = T0 - q1.begin;
+    // ---------------- phase A: pi(s'), pi(s), Q(s,a) forward; target critics; Bellman target; critics' backward
+    step(RPR_GATHER);
+    add_job(fwd(pi, 0, 0, RPS_XS2, a_pit, RPP_PI_T));
+    add_job(fwd(pi, 0, 0, RPS_XSA, a_pia, RPP_PI_A));
+    for (int c = 0; c < 2; ++c) add_job(fwd(c ? q2 : q1, 0, 0, RPS_XSA, a_q[c], RPP_Q1 + c));
+    P.n_steps_a++;
+    for (int l = 1; l < std::max(Lp, Lq); ++l) {
+      step(RPR_NONE);
+      if (l < Lp) {
+        add_load(a_pit.h[l - 1], a_pit.ld[l - 1], pi.dims[l], 0); add_job(fwd(pi, l, 0, 0, a_pit, RPP_PI_T));
+        add_load(a_pia.h[l - 1], a_pia.ld[l - 1], pi.dims[l], 1); add_job(fwd(pi, l, 0, 1, a_pia, RPP_PI_A));
+      }
+      if (l < Lq)
+        for (int c = 0; c < 2; ++c) {
+          add_load(a_q[c].h[l - 1], a_q[c].ld[l - 1], q1.dims[l], 2 + c);
+          add_job(fwd(c ? q2 : q1, l, 0, 2 + c, a_q[c], RPP_Q1 + c));
+        }
+      P.n_steps_a++;
+    }
+    step(RPR_PI_HEADS);
+    for (int c = 0; c < 2; ++c) add_job(fwd(c ? q2 : q1, 0, tsh, RPS_XS2, a_qt[c], RPP_QT1 + c));
+    P.n_steps_a++;
+    for (int l = 1; l < Lq; ++l) {
+      step(RPR_NONE);
+      for (int c = 0; c < 2; ++c) {
+        add_load(a_qt[c].h[l - 1], a_qt[c].ld[l - 1], q1.dims[l], c);
+        add_job(fwd(c ? q2 : q1, l, tsh, c, a_qt[c], RPP_QT1 + c));
+      }
+      P.n_steps_a++;
+    }
+    step(RPR_TARGET_CRITIC);
+    for (int c = 0; c < 2; ++c) {
+      add_load(a_q[c].h[Lq - 1], a_q[c].ld[Lq - 1], q1.dims[Lq], 2 + c);
+      add_job(bwd(c ? q2 : q1, Lq - 1, 2 + c, a_q[c], d_q[c], -1));
+    }
+    P.n_steps_a++;
+    for (int l = Lq - 2; l >= 1; --l) {
+      step(RPR_NONE);
+      for (int c = 0; c < 2; ++c) {
+        add_load(d_q[c][l], rup4(q1.dims[l + 1]), q1.dims[l + 1], c);
+        add_job(bwd(c ? q2 : q1, l, c, a_q[c], d_q[c], -1));
+      }
+      P.n_steps_a++;
+    }
+    // ---------------- phase C: critics on (s, a~pi), routed dQ back to the action, policy backward
+    step(RPR_RELOAD);
+    for (int c = 0; c < 2; ++c) add_job(fwd(c ? q2 : q1, 0, 0, RPS_XPI, a_q[c], RPP_Q1 + c));
+    P.n_steps_c++;
+    for (int l = 1; l < Lq; ++l) {
+      step(RPR_NONE);
+      for (int c = 0; c < 2; ++c) {
+        add_load(a_q[c].h[l - 1], a_q[c].ld[l - 1], q1.dims[l], c);
+        add_job(fwd(c ? q2 : q1, l, 0, c, a_q[c], RPP_Q1 + c));
+      }
+      P.n_steps_c++;
+    }
+    step(RPR_ACTOR_Q);
+    for (int c = 0; c < 2; ++c) {
+      add_load(a_q[c].h[Lq - 1], a_q[c].ld[Lq - 1], q1.dims[Lq], 2 + c);
+      add_job(bwd(c ? q2 : q1, Lq - 1, 2 + c, a_q[c], d_q[c], Lq - 1 == 1 ? RPP_DA1 + c : -1));
+    }
+    P.n_steps_c++;
+    for (int l = Lq - 2; l >= 1; --l) {
+      step(RPR_NONE);
+      for (int c = 0; c < 2; ++c) {
+        add_load(d_q[c][l], rup4(q1.dims[l + 1]), q1.dims[l + 1], c);
+        add_job(bwd(c ? q2 : q1, l, c, a_q[c], d_q[c], l == 1 ? RPP_DA1 + c : -1));
+      }
+      P.n_steps_c++;
+    }
+    step(RPR_PI_BWD);
+    add_load(a_pia.h[Lp - 1], a_pia.ld[Lp - 1], pi.dims[Lp], 0);
+    add_job(bwd(pi, Lp - 1, 0, a_pia, d_p, -1));
+    P.n_steps_c++;
+    for (int l = Lp - 2; l >= 1; --l) {
+      step(RPR_NONE);
+      add_load(d_p[l], rup4(pi.dims[l + 1]), pi.dims[l + 1], 1);
+      add_job(bwd(pi, l, 1, a_pia, d_p, -1));
+      P.n_steps_c++;
+    }
+    if (overflow) { rp_why = "program tables too small"; return false; }
+    // ---------------- geometry, row-op operands
+    P.O = O; P.A = A; P.Hq = q1.dims[Lq]; P.Hpi = pi.dims[Lp]; P.ld_hq = rup4(P.Hq); P.ld_hpi = rup4(P.Hpi);
+    P.act_q = q1.act_h; P.act_oq = q1.act_o; P.act_pi = pi.act_h; P.act_opi = pi.act_o;
+    P.ab_q[0] = 2; P.ab_q[1] = 3; P.ab_pi = 0;
+    P.x_sa = x_sa; P.x_s2 = x_s2; P.x_pi = x_pi; P.b_r = b_r; P.b_d = b_d; P.b_idx = b_idx; P.b_eps1 = b_eps1; P.b_eps2 = b_eps2;
+    P.b_lp2 = b_lp2; P.b_lp = b_lp; P.b_y = b_y; P.b_ploss = b_ploss; P.b_tz = b_tz; P.b_se = b_se; P.b_mask = b_mask;
+    P.b_headz = b_headz; P.b_dhead = b_dhead;
+    for (int c = 0; c < 2; ++c) {
+      const NetLayout& n = c ? q2 : q1;
+      P.b_tq[c] = b_tq[c]; P.b_q[c] = b_q[c]; P.b_qa[c] = b_qa[c]; P.b_dout[c] = b_dout[c]; P.b_loss[c] = b_loss[c];
+      P.q_bL[c] = n.b[Lq]; P.q_WL[c] = n.W[Lq]; P.qt_bL[c] = n.b[Lq] + tsh; P.dq_last[c] = d_q[c][Lq - 1];
+    }
+    P.pi_bL = pi.b[Lp]; P.pi_WL = pi.W[Lp]; P.dp_last = d_p[Lp - 1];
+    // ---------------- shared-memory layout (floats)
+    int hmax = 0;
+    for (int l = 1; l <= Lp; ++l) hmax = std::max(hmax, pi.dims[l]);
+    for (int l = 1; l <= Lq; ++l) hmax = std::max(hmax, q1.dims[l]);
+    P.lda = hmax + 4; P.abuf_floats = RP_RB * P.lda;
+    P.ldx = ((O + A + 7) & ~7) + 4;
+    P.gldx = ldx;
+    P.wslot_floats = (wmax + 3) & ~3;
+    int off = 0;
+    P.sm_abuf = off; off += RP_NABUF * P.abuf_floats;
+    P.sm_xbuf = off; off += 3 * RP_RB * P.ldx;
+    off = (off + 3) & ~3;
+    P.sm_wslot = off; off += RP_NWSLOT * P.wslot_floats;
+    P.sm_red = off; off += RP_RED;
+    P.sm_otile = off; off += RP_RB * 33 + 3; off &= ~3;
+    P.sm_pw = off; off += 2 * RP_MAXA * 32;
+    off = std::max(off, WSM_FLOATS + CfgSmall::SMEM_FLOATS);      // the dW tiles alias the same region
+    P.sm_total = off;
+    // partial-sum scratch of one group (global memory): [slot][rank][16][J]
+    const int J[RPP_N] = {2 * A, 2 * A, 1, 1, 1, 1, A, A};
+    int poff = 0;
+    for (int i = 0; i < RPP_N; ++i) { P.part_off[i] = poff; poff += RP_CS * RP_RB * J[i]; }
+    P.part_stride = (poff + 31) & ~31;
+    // ---------------- the two tile-parallel phases: dW + Adam (+ Polyak) of the critics, then of the policy
+    const bool keep_large = large;
+    large = false;
+    const int AD = DW_ADAM;
+    pb.phase();
+    for (int l = Lq - 1; l >= 1; --l)
+      for (int c = 0; c < 2; ++c)
+        pb.add(gemm_dw(c ? q2 : q1, l, c ? OPT_Q2 : OPT_Q1, AD | DW_POLYAK, d_q[c][l], rup4(q1.dims[l + 1]), a_q[c].h[l - 1], a_q[c].ld[l - 1], true));
+    for (int c = 0; c < 2; ++c) {
+      pb.add(gemm_dw(c ? q2 : q1, 0, c ? OPT_Q2 : OPT_Q1, AD | DW_POLYAK, d_q[c][0], rup4(q1.dims[1]), x_sa, ldx, true));
+      pb.add(gemm_dw(c ? q2 : q1, Lq, c ? OPT_Q2 : OPT_Q1, AD | DW_POLYAK, b_dout[c], 4, a_q[c].h[Lq - 1], a_q[c].ld[Lq - 1], true));
+    }
+    pb.phase();
+    for (int l = Lp - 1; l >= 1; --l) pb.add(gemm_dw(pi, l, OPT_PI, AD, d_p[l], rup4(pi.dims[l + 1]), a_pia.h[l - 1], a_pia.ld[l - 1], false));
+    pb.add(gemm_dw(pi, 0, OPT_PI, AD, d_p[0], rup4(pi.dims[1]), x_pi, ldx, false));
+    pb.add(gemm_dw(pi, Lp, OPT_PI, AD, b_dhead, 2 * A, a_pia.h[Lp - 1], a_pia.ld[Lp - 1], false));
+    pb.add(op_final(1 | 2 | 4 | 8));
+    large = keep_large;
+    if (pb.overflow || pb.p.n_ops > RP_MAX_DW_OPS) { rp_why = "too many dW ops"; return false; }
+    return true;
+  }
+
   int build_plans() {
     h_plans.assign(N_PLANS, Plan());
     auto put = [&](int id, PB& pb) -> int {
@@ -717,6 +924,8 @@ struct Engine {
     }
     { PB pb; pb.phase(); pb.add(op_prologue(1 << OPT_PI)); pb.phase(); pb.add(op_adam_flat(pi, OPT_PI, false));
       if ((rc = put(PLAN_APPLY_PI, pb))) return rc; }
+    rp = rowpar_eligible(rp_why);
+    if (rp) { PB pb; rp = build_rowpar(pb); if (rp) h_plans[PLAN_RP] = pb.p; }
     return SACX_OK;
   }
 

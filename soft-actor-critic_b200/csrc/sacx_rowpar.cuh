@@ -1,0 +1,799 @@
+// Row-parallel kernel for the single-agent SAC update (latency path).
+//
+// The tile-parallel plan (sacx_run_kernel) spreads every layer over all SMs and therefore needs a grid-wide barrier
+// after each of the ~16 dependent layers of one update; at batch 256 the barriers, the first L2 round trip of every
+// tile and the FFMA K loop add up to ~18K cycles per phase. Here the batch is cut into row blocks of 16 rows (one
+// m16 MMA tile) and a GROUP of 8 CTAs owns a row block through the whole forward/backward chain:
+//   * every layer's output columns are split 8 ways: CTA `rank` computes the 16 x (N/8) slice with 3xTF32
+//     mma.sync.m16n8k8 tensor-core tiles (hi/lo split of both operands, fp32 accumulate: fp32-level accuracy),
+//   * slices are exchanged through L2: each CTA stores its slice, the 8 CTAs meet at a group barrier (one L2 atomic
+//     per CTA + a release flag) and pull the full 16 x N rows back with cp.async,
+//   * the narrow heads (policy 2A outputs, critic 1 output, dQ/da) never travel as activations: the producing tile
+//     projects its slice onto the head weights and only the 8 partial sums per row are exchanged,
+//   * weight slices stream from L2 into a 3-slot shared-memory ring two jobs ahead (they do not depend on data),
+//   * the per-row SAC arithmetic (tanh-Gaussian sample/log-prob, Bellman target, loss gradients, head backward) is
+//     evaluated redundantly by every CTA of the group from the reduced partials -- cheaper than another barrier.
+// Groups are formed in software rather than as hardware thread-block clusters: a cluster of 8 must sit inside one
+// GPC, and only 15 such clusters are co-resident on a B200 at this shared-memory footprint (tools/cluster_probe.cu),
+// one short of the 16 row blocks of a 256-row batch -- the unbalanced second round cost more than the ~1K cycles a
+// software barrier adds over barrier.cluster. Any 128 of the 148 SMs can form 16 groups.
+// Only the weight gradients need all rows: dW + Adam (+ Polyak) stay tile-parallel (the EPI_DW tiles of
+// sacx_gemm.cuh) in two grid-wide phases. One update = 4 grid barriers + 7 group barriers instead of 16 grid
+// barriers. Reference semantics: sac/agent.py:195-327, sac/models.py:73-87.
+#pragma once
+#include "sacx_kernels.cuh"
+
+namespace sacx {
+
+constexpr int RP_CS = 8;                         // CTAs per group = column slices per layer
+constexpr int RP_RB = 16;                        // rows per row block
+constexpr int RP_HMAX = 256;                     // widest hidden layer
+constexpr int RP_NABUF = 4;                      // full-row activation buffers [16][lda], lda = widest hidden + 4 (== 4 mod 32)
+constexpr int RP_NWSLOT = 3;                     // weight slots (forward slice [N/8][K+4] / backward [K][N/8])
+constexpr int RP_RED = 2048;
+constexpr int RP_MAXA = 8;                       // action dimension handled by the row ops
+constexpr int RP_MAX_GROUPS = 32;
+constexpr int RP_MAX_JOBS = 40, RP_MAX_STEPS = 28, RP_MAX_LOADS = 48, RP_MAX_DW_OPS = 16;
+
+enum RpRowOp : int { RPR_NONE = 0, RPR_GATHER, RPR_PI_HEADS, RPR_TARGET_CRITIC, RPR_RELOAD, RPR_ACTOR_Q, RPR_PI_BWD };
+enum RpSrc : int { RPS_ABUF0 = 0, RPS_XSA = 4, RPS_XS2 = 5, RPS_XPI = 6 };
+enum RpSlot : int { RPP_PI_T = 0, RPP_PI_A, RPP_Q1, RPP_Q2, RPP_QT1, RPP_QT2, RPP_DA1, RPP_DA2, RPP_N };
+
+struct RpJob {
+  int bkm;                 // 0 forward: B(k,n) = W[n0+n][k];  1 backward dA: B(k,n) = W[k][n0+n]
+  int a_src;               // RpSrc
+  int K, Kp, N;            // reduction length (padded to 8), full output width (slice NS = N / 8)
+  int ns_log2;             // log2(NS), NS in {8, 16, 32}
+  int act;                 // forward: activation;  backward: activation whose derivative multiplies the result
+  int w_ld;                // leading dimension of W in global memory
+  int out_ld, aux_ld;
+  int proj_J, proj_slot, proj_sj, proj_sn;      // projection of the output slice onto J weight vectors (0: none)
+  i64 w, bias, out, aux, proj_w;                // arena offsets (-1: unused)
+};
+struct RpLoad { i64 off; int ld, K, abuf, pad; };
+struct RpStep { int row_op, job0, njobs, load0, nloads, pad0, pad1, pad2; };
+
+struct RpProgram {
+  int n_steps_a, n_steps_c, n_jobs, n_loads;
+  // shared-memory layout (float offsets into the dynamic region)
+  int sm_abuf, sm_xbuf, ldx, sm_wslot, sm_red, sm_otile, sm_pw, sm_total;
+  int lda, abuf_floats, wslot_floats, gldx;     // gldx: row stride of the batch buffers in the arena
+  // geometry / activations
+  int O, A, Hq, Hpi, ld_hq, ld_hpi, act_q, act_oq, act_pi, act_opi;
+  int ab_q[2], ab_pi, part_stride;             // abuf indices of the delta generators; floats of partial scratch per group
+  int part_off[RPP_N];                         // float offset of each partial slot inside a group's scratch: [rank][16][J]
+  // arena offsets used by the row ops
+  i64 x_sa, x_s2, x_pi, b_r, b_d, b_idx, b_eps1, b_eps2, b_lp2, b_lp, b_y, b_tq[2], b_q[2], b_qa[2], b_dout[2],
+      b_loss[2], b_ploss, b_tz, b_se, b_mask, b_headz, b_dhead;
+  i64 pi_bL, pi_WL, q_bL[2], q_WL[2], qt_bL[2];
+  i64 dq_last[2], dp_last;
+  RpStep steps[RP_MAX_STEPS];
+  RpJob jobs[RP_MAX_JOBS];
+  RpLoad loads[RP_MAX_LOADS];
+};
+
+struct RpRows {            // per-row state of the current row block (every CTA of the group holds a copy)
+  float r[RP_RB], d[RP_RB], lp2[RP_RB], lp[RP_RB], coef[2][RP_RB];
+  float eps1[RP_RB][RP_MAXA], eps2[RP_RB][RP_MAXA], tz[RP_RB][RP_MAXA], se[RP_RB][RP_MAXA], mk[RP_RB][RP_MAXA];
+  float hz[RP_RB][2 * RP_MAXA], dh[RP_RB][2 * RP_MAXA];
+};
+
+// optional event trace of CTA 0 (profiling aid): (tag, clock64) pairs of the launch's last update
+struct RpTrace { unsigned long long* buf; int n, cap; };
+#define RP_TRACE(tag) do { if (c.tr->buf && threadIdx.x == 0 && c.tr->n < c.tr->cap) { \
+  c.tr->buf[2 * c.tr->n] = (unsigned long long)(tag); c.tr->buf[2 * c.tr->n + 1] = clock64(); c.tr->n++; } } while (0)
+
+struct RpCtx {
+  float* base;
+  AgentScalars* scal;
+  const RunArgs* args;
+  const RpProgram* P;
+  RpRows* R;
+  float* part;            // this group's partial scratch (global)
+  unsigned* gbar;         // this group's barrier counter (flag at +32)
+  int rank, step, row0;
+  RpTrace* tr;
+};
+
+#define RP_SMEM extern __shared__ __align__(16) float smem_raw[]
+
+// ---- shared-memory accessors (explicit state space: the helpers receive offsets, not generic pointers) ---------------
+__device__ __forceinline__ uint32_t rp_saddr(const float* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float rp_lds(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+
+// ---- 3xTF32 tensor-core arithmetic ------------------------------------------------------------------------------
+// x = hi + lo with hi = x rounded to TF32 (half-ulp add, then the low 13 bits cleared); the tensor core ignores the low
+// 13 mantissa bits of its inputs, so lo is passed as is (it loses at most 2^-21 |x|)
+__device__ __forceinline__ void rp_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void rp_mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// the three 3xTF32 terms of A(16x8) . B(8x8) go to separate accumulators: no tensor-core instruction waits on the
+// previous one, and the small cross terms are summed before they meet the leading term
+__device__ __forceinline__ void rp_mma3(float (&c0)[4], float (&c1)[4], float (&c2)[4], const float (&a)[4], const float (&b)[2]) {
+  uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rp_split(a[i], ah[i], al[i]);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) rp_split(b[i], bh[i], bl[i]);
+  rp_mma(c0, al, bh);
+  rp_mma(c1, ah, bl);
+  rp_mma(c2, ah, bh);
+}
+
+// ---- group barrier: 8 CTAs, arrivals on one L2 line, release flag on another ----------------------------------------
+__device__ __forceinline__ void rp_group_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += RP_CS;
+    unsigned* flag = counter + 32;
+    unsigned old, v;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    if (old + 1 == epoch) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    } else {
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      } while ((int)(v - epoch) < 0);
+    }
+  }
+  __syncthreads();
+}
+
+// ---- weight slice: global (L2) -> shared-memory slot ----------------------------------------------------------------
+__device__ __forceinline__ void rp_issue_weights(const RpJob& jb, float* __restrict__ slot, const float* __restrict__ base, int rank) {
+  const int NS = 1 << jb.ns_log2, n0g = rank << jb.ns_log2, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* __restrict__ W = base + jb.w;
+  if (!jb.bkm) {
+    const int ldw = jb.Kp + 4;
+    const bool vec = ((jb.K & 3) == 0) && ((jb.w & 3) == 0) && ((jb.w_ld & 3) == 0);
+    if (vec) {
+      const int cpr = jb.Kp >> 2;            // 16-byte chunks per row (the last one may be zero padding)
+      for (int n = warp; n < NS; n += 8) {
+        const float* src = W + (i64)(n0g + n) * jb.w_ld;
+        float* dst = slot + n * ldw;
+        for (int ch = lane; ch < cpr; ch += 32) {
+          const int k = ch << 2;
+          if (k < jb.K) cp_async16(dst + k, src + k, 16);
+          else *reinterpret_cast<float4*>(dst + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
+      for (int n = warp; n < NS; n += 8)
+        for (int k = lane; k < jb.Kp; k += 32)
+          slot[n * ldw + k] = (k < jb.K) ? __ldcg(W + (i64)(n0g + n) * jb.w_ld + k) : 0.f;
+    }
+  } else {
+    // [K][NS], 8-column groups XOR-swizzled by the row so that the (k = t, n = g) fragment reads hit 32 banks
+    const int cl = jb.ns_log2 - 2, sh = 5 - jb.ns_log2;       // chunks per row = NS / 4
+    const int ch = (tid & ((1 << cl) - 1)) << 2;
+    for (int k = tid >> cl; k < jb.K; k += 256 >> cl) {
+      const int sw = ((k & 3) >> sh) << 3;
+      cp_async16(slot + k * NS + (ch ^ sw), W + (i64)k * jb.w_ld + n0g + ch, 16);
+    }
+  }
+}
+
+// full rows of a [B][ld] activation matrix -> activation buffer (rows past the batch are zero)
+__device__ __forceinline__ void rp_issue_load(const RpLoad& ld, float* __restrict__ abuf, int lda, const float* __restrict__ base, int row0, int B) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cpr = ld.K >> 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int m = warp + 8 * h;
+    const bool ok = row0 + m < B;
+    const float* src = base + ld.off + (i64)(row0 + m) * ld.ld;
+    for (int ch = lane; ch < cpr; ch += 32) cp_async16(abuf + m * lda + (ch << 2), ok ? src + (ch << 2) : base, ok ? 16 : 0);
+  }
+}
+
+// ---- one GEMM job: 16 x NS output slice, K reduction split over the warps --------------------------------------------
+__device__ __forceinline__ void rp_job_math(const RpJob& jb, uint32_t As, int lda, uint32_t Bs, float* __restrict__ red) {
+  const int NS = 1 << jb.ns_log2, ntl = jb.ns_log2 - 3, KG = 8 >> ntl;      // n-tiles per slice = NS/8, K groups = 8/NT
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nt = warp & ((1 << ntl) - 1), kg = warp >> ntl, n0 = nt << 3;
+  const int ksteps = jb.Kp >> 3, per = (ksteps + KG - 1) >> (3 - ntl);
+  const int ks0 = kg * per, ks1 = min(ksteps, ks0 + per);
+  float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t a0p = As + 4u * (uint32_t)(g * lda + t), a1p = a0p + 32u * (uint32_t)lda;
+  uint32_t bp, bstep, b4;
+  if (!jb.bkm) {
+    bp = Bs + 4u * (uint32_t)((n0 + g) * (jb.Kp + 4) + t); bstep = 32u; b4 = 16u;
+  } else {
+    const int sw = (t >> (5 - jb.ns_log2)) << 3;
+    bp = Bs + 4u * (uint32_t)(t * NS + ((n0 + g) ^ sw)); bstep = 32u * (uint32_t)NS; b4 = 16u * (uint32_t)NS;
+  }
+  uint32_t ao = 32u * (uint32_t)ks0, bo = bstep * (uint32_t)ks0;
+  int ks = ks0;
+  for (; ks + 1 < ks1; ks += 2) {
+    const float a[4] = {rp_lds(a0p + ao), rp_lds(a1p + ao), rp_lds(a0p + ao + 16u), rp_lds(a1p + ao + 16u)};
+    const float b[2] = {rp_lds(bp + bo), rp_lds(bp + bo + b4)};
+    const float a2[4] = {rp_lds(a0p + ao + 32u), rp_lds(a1p + ao + 32u), rp_lds(a0p + ao + 48u), rp_lds(a1p + ao + 48u)};
+    const float b2[2] = {rp_lds(bp + bo + bstep), rp_lds(bp + bo + bstep + b4)};
+    rp_mma3(c0, c1, c2, a, b);
+    rp_mma3(d0, d1, d2, a2, b2);
+    ao += 64u; bo += 2u * bstep;
+  }
+  if (ks < ks1) {
+    const float a[4] = {rp_lds(a0p + ao), rp_lds(a1p + ao), rp_lds(a0p + ao + 16u), rp_lds(a1p + ao + 16u)};
+    const float b[2] = {rp_lds(bp + bo), rp_lds(bp + bo + b4)};
+    rp_mma3(c0, c1, c2, a, b);
+  }
+  const int RS = NS + 8;
+  float* r = red + kg * 16 * RS;
+  float acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = ((c0[q] + d0[q]) + (c1[q] + d1[q])) + (c2[q] + d2[q]);
+  *reinterpret_cast<float2*>(r + g * RS + n0 + 2 * t) = make_float2(acc[0], acc[1]);
+  *reinterpret_cast<float2*>(r + (g + 8) * RS + n0 + 2 * t) = make_float2(acc[2], acc[3]);
+}
+
+__device__ __forceinline__ void rp_job(const RpJob& jb, const RpCtx& c, int wslot_idx) {
+  RP_SMEM;
+  const RpProgram& P = *c.P;
+  const int tid = threadIdx.x, NS = 1 << jb.ns_log2, n0g = c.rank << jb.ns_log2, RS = NS + 8, KG = 64 >> jb.ns_log2;
+  const int B = c.args->hp.B;
+  const float* As;
+  int lda;
+  if (jb.a_src < RP_NABUF) { As = smem_raw + P.sm_abuf + jb.a_src * P.abuf_floats; lda = P.lda; }
+  else { As = smem_raw + P.sm_xbuf + (jb.a_src - RPS_XSA) * RP_RB * P.ldx; lda = P.ldx; }
+  const float* Bs = smem_raw + P.sm_wslot + wslot_idx * P.wslot_floats;
+  // epilogue operands travel while the tensor cores work
+  const int e = tid * 2, m = e >> jb.ns_log2, n = e & (NS - 1);
+  const bool own = e < RP_RB * NS, rowok = own && (c.row0 + m < B);
+  float2 ep = make_float2(0.f, 0.f);
+  if (own) {
+    if (!jb.bkm) { if (jb.bias >= 0) ep = __ldcg(reinterpret_cast<const float2*>(c.base + jb.bias + n0g + n)); }
+    else if (rowok) ep = __ldcg(reinterpret_cast<const float2*>(c.base + jb.aux + (i64)(c.row0 + m) * jb.aux_ld + n0g + n));
+  }
+  const int J = jb.proj_J;
+  float pwv[2] = {0.f, 0.f};
+  if (J > 0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = tid + 256 * u;
+      if (i < J * NS) pwv[u] = __ldcg(c.base + jb.proj_w + (i64)(i >> jb.ns_log2) * jb.proj_sj + (i64)(n0g + (i & (NS - 1))) * jb.proj_sn);
+    }
+  }
+  float* red = smem_raw + P.sm_red;
+  RP_TRACE(4500);
+  rp_job_math(jb, rp_saddr(As), lda, rp_saddr(Bs), red);
+  RP_TRACE(4600);
+  float* pw = smem_raw + P.sm_pw;
+  if (J > 0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) if (tid + 256 * u < J * NS) pw[tid + 256 * u] = pwv[u];
+  }
+  __syncthreads();
+  RP_TRACE(4650);
+  float* otile = smem_raw + P.sm_otile;
+  if (own) {
+    float2 s = make_float2(0.f, 0.f);
+    for (int q = 0; q < KG; ++q) {
+      const float2 p = *reinterpret_cast<const float2*>(red + (q * 16 + m) * RS + n);
+      s.x += p.x; s.y += p.y;
+    }
+    float2 v;
+    if (!jb.bkm) v = make_float2(act_fwd(jb.act, s.x + ep.x), act_fwd(jb.act, s.y + ep.y));
+    else v = make_float2(s.x * act_dz(jb.act, ep.x), s.y * act_dz(jb.act, ep.y));
+    if (rowok && jb.out >= 0) *reinterpret_cast<float2*>(c.base + jb.out + (i64)(c.row0 + m) * jb.out_ld + n0g + n) = v;
+    if (J > 0) { otile[m * 33 + n] = v.x; otile[m * 33 + n + 1] = v.y; }
+  }
+  if (J > 0) {
+    __syncthreads();
+    if (tid < RP_RB * J) {
+      const int mm = tid / J, j = tid - mm * J;
+      float s = 0.f;
+      const float* o = otile + mm * 33;
+      const float* w = pw + j * NS;
+      for (int nn = 0; nn < NS; ++nn) s = fmaf(o[nn], w[nn], s);
+      // share of CTA `rank`: [rank][m][j] in the group's scratch; the 8 shares are summed in rank order by every reader
+      c.part[P.part_off[jb.proj_slot] + (c.rank * RP_RB + mm) * J + j] = s;
+    }
+  }
+}
+
+// sum of the 8 CTAs' shares of element (m, j) of a partial slot, in rank order (deterministic); loads are independent
+__device__ __forceinline__ float rp_sum_parts(const RpCtx& c, int slot, int J, int m, int j) {
+  const float* p = c.part + c.P->part_off[slot] + m * J + j;
+  float v[RP_CS];
+#pragma unroll
+  for (int r = 0; r < RP_CS; ++r) v[r] = __ldcg(p + r * RP_RB * J);
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < RP_CS; ++r) s += v[r];
+  return s;
+}
+__device__ __forceinline__ float rp_sum8(float v) {     // sum over the 8 lanes that share a row
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+// ---- row ops --------------------------------------------------------------------------------------------------------
+// ring rows -> the three input buffers (a2/a3), the update's normals; rank 0 mirrors the batch into the arena.
+// Warp w owns rows 2w and 2w+1; all ring loads of a thread are in flight before the first is used.
+__device__ __forceinline__ void rp_gather(const RpCtx& c) {
+  RP_SMEM;
+  const RunArgs& a = *c.args;
+  const Hyper& hp = a.hp;
+  const RpProgram& P = *c.P;
+  RpRows& R = *c.R;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, O = P.O, A = P.A, ldx = P.ldx, B = hp.B;
+  const float* __restrict__ ring = a.ring;
+  const i64 cap = a.ring_capacity;
+  float* xsa = smem_raw + P.sm_xbuf, *xs2 = xsa + RP_RB * ldx, *xpi = xs2 + RP_RB * ldx;
+  const bool w0 = c.rank == 0;
+  // lanes 0 / 1: ring slot of rows 2w / 2w+1
+  i64 myslot = -1;
+  if (lane < 2) {
+    const int row = c.row0 + 2 * warp + lane;
+    if (row < B) {
+      const i64 pushes = reinterpret_cast<const RingMeta*>(ring)->pushes;
+      const i64 n = pushes < cap ? pushes : cap;
+      i64 j;
+      if (a.idx_ext) j = a.idx_ext[(i64)c.step * hp.B + row];
+      else j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, hp.seed,
+                                  (unsigned long long)__ldcg(&c.scal->updates), 0u);
+      const i64 oldest = pushes > cap ? pushes - cap : 0;
+      myslot = (oldest + j) % cap;
+      if (w0) reinterpret_cast<i64*>(c.base + P.b_idx)[row] = j;
+    }
+  }
+  const i64 slot0 = __shfl_sync(0xffffffffu, myslot, 0), slot1 = __shfl_sync(0xffffffffu, myslot, 1);
+  // ring loads: per row 2O + A + 2 floats; lane covers columns lane, lane + 32, ...
+  const int W = 2 * O + A + 2;
+  constexpr int MAXC = 8;                 // columns per lane per row (W <= 256)
+  float v0[MAXC], v1[MAXC];
+#pragma unroll
+  for (int u = 0; u < MAXC; ++u) {
+    const int col = lane + 32 * u;
+    v0[u] = 0.f; v1[u] = 0.f;
+    if (col < W) {
+      i64 off;            // field offset of this column for slot s: off + s * stride
+      int stride;
+      if (col < O) { off = a.ring_s + col; stride = O; }
+      else if (col < O + A) { off = a.ring_a + (col - O); stride = A; }
+      else if (col < 2 * O + A) { off = a.ring_s2 + (col - O - A); stride = O; }
+      else if (col == 2 * O + A) { off = a.ring_r; stride = 1; }
+      else { off = a.ring_d; stride = 1; }
+      if (slot0 >= 0) v0[u] = __ldcs(ring + off + slot0 * stride);
+      if (slot1 >= 0) v1[u] = __ldcs(ring + off + slot1 * stride);
+    }
+  }
+  // normals of the update (lanes 16..31: row 2w + (l >> 3), action dim l & 7) while the ring rows travel
+  if (lane >= 16) {
+    const int l = lane - 16, mm = 2 * warp + (l >> 3), j = l & 7, row = c.row0 + mm;
+    float e1 = 0.f, e2 = 0.f;
+    if (row < B && j < A) {
+      if (a.eps1_ext) e1 = a.eps1_ext[((i64)c.step * hp.B + row) * A + j];
+      else e1 = philox_normal(hp.seed, (unsigned long long)__ldcg(&c.scal->updates), 1, (uint32_t)(hp.row0_global + row), (uint32_t)j, 0u);
+      if (a.eps2_ext) e2 = a.eps2_ext[((i64)c.step * hp.B + row) * A + j];
+      else e2 = philox_normal(hp.seed, (unsigned long long)__ldcg(&c.scal->updates), 2, (uint32_t)(hp.row0_global + row), (uint32_t)j, 0u);
+      if (w0) { c.base[P.b_eps1 + (i64)row * A + j] = e1; c.base[P.b_eps2 + (i64)row * A + j] = e2; }
+    }
+    R.eps1[mm][j] = e1; R.eps2[mm][j] = e2;
+  }
+  // padding columns (finite zeros: they meet zero-padded weights in the K loop)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int mm = 2 * warp + h;
+    for (int col = O + lane; col < ldx; col += 32) {
+      if (col >= O + A) xsa[mm * ldx + col] = 0.f;
+      xs2[mm * ldx + col] = 0.f; xpi[mm * ldx + col] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < MAXC; ++u) {
+    const int col = lane + 32 * u;
+    if (col < W) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int mm = 2 * warp + h, row = c.row0 + mm;
+        const float v = h ? v1[u] : v0[u];
+        const bool ok = (h ? slot1 : slot0) >= 0;
+        if (col < O) {
+          xsa[mm * ldx + col] = v; xpi[mm * ldx + col] = v;
+          if (w0 && ok) { c.base[P.x_sa + (i64)row * P.gldx + col] = v; c.base[P.x_pi + (i64)row * P.gldx + col] = v; }
+        } else if (col < O + A) {
+          xsa[mm * ldx + col] = v;
+          if (w0 && ok) c.base[P.x_sa + (i64)row * P.gldx + col] = v;
+        } else if (col < 2 * O + A) {
+          const int k = col - O - A;
+          xs2[mm * ldx + k] = v;
+          if (w0 && ok) c.base[P.x_s2 + (i64)row * P.gldx + k] = v;
+        } else if (col == 2 * O + A) {
+          R.r[mm] = v;
+          if (w0 && ok) c.base[P.b_r + row] = v;
+        } else {
+          R.d[mm] = v;
+          if (w0 && ok) c.base[P.b_d + row] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// policy heads of pi(s') and pi(s) from the reduced partials: rsample, tanh squash, log-prob (models.py:73-87)
+__device__ __forceinline__ void rp_pi_heads(const RpCtx& c) {
+  RP_SMEM;
+  const Hyper& hp = c.args->hp;
+  const RpProgram& P = *c.P;
+  RpRows& R = *c.R;
+  const int tid = threadIdx.x, O = P.O, A = P.A, J = 2 * A, ldx = P.ldx, B = hp.B;
+  float* xs2 = smem_raw + P.sm_xbuf + RP_RB * ldx, *xpi = xs2 + RP_RB * ldx;
+  const bool w0 = c.rank == 0;
+  // warps 0-3: target head (which = 0); warps 4-7: actor head (which = 1); 8 lanes per row
+  const int which = tid >> 7, t = tid & 127, mm = t >> 3, j = t & 7, row = c.row0 + mm;
+  const bool ok = row < B, act_lane = j < A;
+  const int slot = which ? RPP_PI_A : RPP_PI_T;
+  float lp = 0.f;
+  bool bad = false;
+  if (act_lane) {
+    const float bm = __ldcg(c.base + P.pi_bL + j), bl = __ldcg(c.base + P.pi_bL + A + j);
+    const float zm = rp_sum_parts(c, slot, J, mm, j) + bm;
+    const float zl = rp_sum_parts(c, slot, J, mm, A + j) + bl;
+    const float mu = act_fwd(P.act_opi, zm), ls_raw = act_fwd(P.act_opi, zl);
+    const float ls = fminf(fmaxf(ls_raw, hp.log_std_min), hp.log_std_max);
+    const float sd = expf(ls);
+    const float e = which ? R.eps2[mm][j] : R.eps1[mm][j];
+    const float z = mu + e * sd;
+    const float tz = tanhf(z);
+    const float av = tz * hp.action_scale;
+    const float dzm = z - mu;
+    lp = -(dzm * dzm) / (2.f * (sd * sd)) - logf(sd) - 0.91893853320467274178f;
+    lp -= 2.f * (0.69314718055994530942f - z - softplus20(-2.f * z));
+    bad = ok && !(isfinite(mu) && isfinite(sd));
+    if (!which) {
+      xs2[mm * ldx + O + j] = ok ? av : 0.f;
+      if (w0 && ok) c.base[P.x_s2 + (i64)row * P.gldx + O + j] = av;
+    } else {
+      xpi[mm * ldx + O + j] = ok ? av : 0.f;
+      const float mk = (ls_raw >= hp.log_std_min && ls_raw <= hp.log_std_max) ? 1.f : 0.f;
+      if (w0 && ok) {
+        c.base[P.x_pi + (i64)row * P.gldx + O + j] = av;
+        c.base[P.b_tz + (i64)row * A + j] = tz;
+        c.base[P.b_se + (i64)row * A + j] = sd * e;
+        c.base[P.b_mask + (i64)row * A + j] = mk;
+        c.base[P.b_headz + (i64)row * J + j] = zm;
+        c.base[P.b_headz + (i64)row * J + A + j] = zl;
+      }
+    }
+  }
+  lp = rp_sum8(lp);
+  if (j == 0) {
+    if (!which) { R.lp2[mm] = lp; if (w0 && ok) c.base[P.b_lp2 + row] = lp; }
+    else if (w0 && ok) c.base[P.b_lp + row] = lp;
+  }
+  if (bad && w0) atomicOr(&c.scal->nonfinite, 1);
+  __syncthreads();
+}
+
+// in-place delta of the critics' last hidden layer: abuf[m][k] <- coef[m] * W_L[k] * act'(h[m][k]).
+// wl[cc]: this thread's float4 of W_L (every iteration of a thread touches the same 4 columns: 256 % (H/4) == 0)
+__device__ __forceinline__ void rp_delta_critics(const RpCtx& c, const float4 (&wl)[2], bool store) {
+  RP_SMEM;
+  const RpProgram& P = *c.P;
+  const RpRows& R = *c.R;
+  const int tid = threadIdx.x, H = P.Hq, NS = H / RP_CS, n0g = c.rank * NS, B = c.args->hp.B;
+  const int cpr = H >> 2, k = (tid % cpr) << 2, m0 = tid / cpr, mstep = 256 / cpr;
+  const bool mine = store && k >= n0g && k < n0g + NS;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    float* ab = smem_raw + P.sm_abuf + P.ab_q[cc] * P.abuf_floats;
+    const float4 w = wl[cc];
+    for (int mm = m0; mm < RP_RB; mm += mstep) {
+      float4* p = reinterpret_cast<float4*>(ab + mm * P.lda + k);
+      const float4 h = *p;
+      const float co = R.coef[cc][mm];
+      const float4 dv = make_float4(co * w.x * act_dz(P.act_q, h.x), co * w.y * act_dz(P.act_q, h.y), co * w.z * act_dz(P.act_q, h.z),
+                                    co * w.w * act_dz(P.act_q, h.w));
+      *p = dv;
+      if (mine && c.row0 + mm < B) *reinterpret_cast<float4*>(c.base + P.dq_last[cc] + (i64)(c.row0 + mm) * P.ld_hq + k) = dv;
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void rp_load_wl(const RpCtx& c, float4 (&wl)[2]) {
+  const int cpr = c.P->Hq >> 2, k = (threadIdx.x % cpr) << 2;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) wl[cc] = __ldcg(reinterpret_cast<const float4*>(c.base + c.P->q_WL[cc] + k));
+}
+
+// soft Bellman target (agent.py:195-211) and the critics' loss gradient (agent.py:213-236) for the row block
+__device__ __forceinline__ void rp_target_critic(const RpCtx& c) {
+  const Hyper& hp = c.args->hp;
+  const RpProgram& P = *c.P;
+  RpRows& R = *c.R;
+  const int tid = threadIdx.x, B = hp.B;
+  float4 wl[2];
+  rp_load_wl(c, wl);
+  if (tid < RP_RB) {
+    const int mm = tid, row = c.row0 + mm;
+    const bool ok = row < B, w0 = c.rank == 0;
+    const float alpha = __ldcg(&c.scal->alpha_f32);
+    const float bt[2] = {__ldcg(c.base + P.qt_bL[0]), __ldcg(c.base + P.qt_bL[1])};
+    const float bq[2] = {__ldcg(c.base + P.q_bL[0]), __ldcg(c.base + P.q_bL[1])};
+    const float st[2] = {rp_sum_parts(c, RPP_QT1, 1, mm, 0), rp_sum_parts(c, RPP_QT2, 1, mm, 0)};
+    const float sq[2] = {rp_sum_parts(c, RPP_Q1, 1, mm, 0), rp_sum_parts(c, RPP_Q2, 1, mm, 0)};
+    const float tq[2] = {act_fwd(P.act_oq, st[0] + bt[0]), act_fwd(P.act_oq, st[1] + bt[1])};
+    const float y = R.r[mm] + (hp.gamma * (1.f - R.d[mm])) * (fminf(tq[0], tq[1]) - alpha * R.lp2[mm]);
+    if (w0 && ok) { c.base[P.b_y + row] = y; c.base[P.b_tq[0] + row] = tq[0]; c.base[P.b_tq[1] + row] = tq[1]; }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const float z = sq[cc] + bq[cc];
+      const float q = act_fwd(P.act_oq, z);
+      const float diff = q - y;
+      const float dout = (2.f * diff / (float)hp.B_global) * act_dz2(P.act_oq, z, q);
+      R.coef[cc][mm] = ok ? dout : 0.f;
+      if (w0 && ok) { c.base[P.b_q[cc] + row] = q; c.base[P.b_dout[cc] + (i64)row * 4] = dout; c.base[P.b_loss[cc] + row] = diff * diff; }
+    }
+  }
+  __syncthreads();
+  rp_delta_critics(c, wl, true);
+}
+
+// phase C entry: the row block's (s, a~pi) rows and the saved head quantities come back from the arena
+__device__ __forceinline__ void rp_reload(const RpCtx& c) {
+  RP_SMEM;
+  const RpProgram& P = *c.P;
+  RpRows& R = *c.R;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, O = P.O, A = P.A, ldx = P.ldx, B = c.args->hp.B;
+  float* xpi = smem_raw + P.sm_xbuf + 2 * RP_RB * ldx;
+  // warp w: rows 2w, 2w+1 of x_pi; loads first
+  constexpr int MAXC = 9;                 // columns per lane (ldx <= 260)
+  float v[2][MAXC];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int row = c.row0 + 2 * warp + h;
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) {
+      const int col = lane + 32 * u;
+      v[h][u] = (col < O + A && row < B) ? __ldcg(c.base + P.x_pi + (i64)row * P.gldx + col) : 0.f;
+    }
+  }
+  float tz = 0.f, se = 0.f, mk = 0.f, hz0 = 0.f, hz1 = 0.f, lpv = 0.f;
+  const int mm = tid >> 3, j = tid & 7;
+  if (tid < RP_RB * RP_MAXA) {
+    const int row = c.row0 + mm;
+    if (row < B && j < A) {
+      tz = __ldcg(c.base + P.b_tz + (i64)row * A + j);
+      se = __ldcg(c.base + P.b_se + (i64)row * A + j);
+      mk = __ldcg(c.base + P.b_mask + (i64)row * A + j);
+      hz0 = __ldcg(c.base + P.b_headz + (i64)row * 2 * A + j);
+      hz1 = __ldcg(c.base + P.b_headz + (i64)row * 2 * A + A + j);
+    }
+  } else if (tid < 128 + RP_RB) {
+    const int row = c.row0 + tid - 128;
+    if (row < B) lpv = __ldcg(c.base + P.b_lp + row);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) {
+      const int col = lane + 32 * u;
+      if (col < ldx) xpi[(2 * warp + h) * ldx + col] = v[h][u];
+    }
+  if (tid < RP_RB * RP_MAXA) {
+    R.tz[mm][j] = tz; R.se[mm][j] = se; R.mk[mm][j] = mk;
+    if (j < A) { R.hz[mm][j] = hz0; R.hz[mm][A + j] = hz1; }
+  } else if (tid < 128 + RP_RB) {
+    R.lp[tid - 128] = lpv;
+  }
+  __syncthreads();
+}
+
+// critics on (s, a~pi): min, policy loss rows, routed dQ (agent.py:238-260)
+__device__ __forceinline__ void rp_actor_q(const RpCtx& c) {
+  const Hyper& hp = c.args->hp;
+  const RpProgram& P = *c.P;
+  RpRows& R = *c.R;
+  const int tid = threadIdx.x, B = hp.B;
+  float4 wl[2];
+  rp_load_wl(c, wl);
+  if (tid < RP_RB) {
+    const int mm = tid, row = c.row0 + mm;
+    const bool ok = row < B, w0 = c.rank == 0;
+    const float alpha = __ldcg(&c.scal->alpha_f32);
+    const float bq[2] = {__ldcg(c.base + P.q_bL[0]), __ldcg(c.base + P.q_bL[1])};
+    const float sq[2] = {rp_sum_parts(c, RPP_Q1, 1, mm, 0), rp_sum_parts(c, RPP_Q2, 1, mm, 0)};
+    const float z[2] = {sq[0] + bq[0], sq[1] + bq[1]};
+    const float q[2] = {act_fwd(P.act_oq, z[0]), act_fwd(P.act_oq, z[1])};
+    const float w1 = q[0] < q[1] ? 1.f : (q[0] == q[1] ? 0.5f : 0.f);      // torch.min backward, ties split
+    const float g[2] = {-w1 / (float)hp.B_global, -(1.f - w1) / (float)hp.B_global};
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) R.coef[cc][mm] = ok ? g[cc] * act_dz2(P.act_oq, z[cc], q[cc]) : 0.f;
+    if (w0 && ok) {
+      c.base[P.b_qa[0] + row] = q[0]; c.base[P.b_qa[1] + row] = q[1];
+      c.base[P.b_ploss + row] = alpha * R.lp[mm] - fminf(q[0], q[1]);
+    }
+  }
+  __syncthreads();
+  rp_delta_critics(c, wl, false);
+}
+
+// dQ/da from the layer-0 partials, closed-form head backward, delta of the policy's last hidden layer
+__device__ __forceinline__ void rp_pi_bwd(const RpCtx& c) {
+  RP_SMEM;
+  const Hyper& hp = c.args->hp;
+  const RpProgram& P = *c.P;
+  RpRows& R = *c.R;
+  const int tid = threadIdx.x, A = P.A, J = 2 * A, B = hp.B;
+  const int H = P.Hpi, NS = H / RP_CS, n0g = c.rank * NS, cpr = H >> 2;
+  const int k = (tid % cpr) << 2, m0 = tid / cpr, mstep = 256 / cpr;
+  // this thread's 4 columns of the policy's output layer W_L [2A][H], in flight while the head backward runs
+  float4 wl[2 * RP_MAXA];
+#pragma unroll
+  for (int j = 0; j < 2 * RP_MAXA; ++j)
+    wl[j] = (j < J) ? __ldcg(reinterpret_cast<const float4*>(c.base + P.pi_WL + (i64)j * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid < RP_RB * RP_MAXA) {
+    const int mm = tid >> 3, j = tid & 7, row = c.row0 + mm;
+    if (j < A) {
+      const bool ok = row < B;
+      const float alpha = __ldcg(&c.scal->alpha_f32);
+      const float da = rp_sum_parts(c, RPP_DA1, A, mm, j) + rp_sum_parts(c, RPP_DA2, A, mm, j);
+      const float ab = alpha / (float)hp.B_global;
+      const float tz = R.tz[mm][j], se = R.se[mm][j], mk = R.mk[mm][j];
+      const float dz = ab * (2.f * tz) + da * (hp.action_scale * (1.f - tz * tz));
+      float dmu = dz, dls = (se * dz - ab) * mk;
+      if (P.act_opi != SACX_ACT_IDENTITY) {
+        const float zm = R.hz[mm][j], zl = R.hz[mm][A + j];
+        dmu *= act_dz2(P.act_opi, zm, act_fwd(P.act_opi, zm));
+        dls *= act_dz2(P.act_opi, zl, act_fwd(P.act_opi, zl));
+      }
+      if (!ok) { dmu = 0.f; dls = 0.f; }
+      R.dh[mm][j] = dmu; R.dh[mm][A + j] = dls;
+      if (c.rank == 0 && ok) { c.base[P.b_dhead + (i64)row * J + j] = dmu; c.base[P.b_dhead + (i64)row * J + A + j] = dls; }
+    }
+  }
+  __syncthreads();
+  float* ab = smem_raw + P.sm_abuf + P.ab_pi * P.abuf_floats;
+  const bool mine = k >= n0g && k < n0g + NS;
+  for (int mm = m0; mm < RP_RB; mm += mstep) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 2 * RP_MAXA; ++j) {
+      if (j < J) {
+        const float gj = R.dh[mm][j];
+        s.x = fmaf(gj, wl[j].x, s.x); s.y = fmaf(gj, wl[j].y, s.y); s.z = fmaf(gj, wl[j].z, s.z); s.w = fmaf(gj, wl[j].w, s.w);
+      }
+    }
+    float4* p = reinterpret_cast<float4*>(ab + mm * P.lda + k);
+    const float4 h = *p;
+    const float4 dv = make_float4(s.x * act_dz(P.act_pi, h.x), s.y * act_dz(P.act_pi, h.y), s.z * act_dz(P.act_pi, h.z), s.w * act_dz(P.act_pi, h.w));
+    *p = dv;
+    if (mine && c.row0 + mm < B) *reinterpret_cast<float4*>(c.base + P.dp_last + (i64)(c.row0 + mm) * P.ld_hpi + k) = dv;
+  }
+  __syncthreads();
+}
+
+// ---- the step interpreter ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, unsigned& gepoch) {
+  RP_SMEM;
+  const RpProgram& P = *c.P;
+  const int jbeg = P.steps[s0].job0, jend = P.steps[s1 - 1].job0 + P.steps[s1 - 1].njobs;
+  float* wring = smem_raw + P.sm_wslot;
+  const int B = c.args->hp.B;
+  for (int j = jbeg; j < jbeg + 2; ++j) {
+    if (j < jend) rp_issue_weights(P.jobs[j], wring + (j % RP_NWSLOT) * P.wslot_floats, c.base, c.rank);
+    cp_async_commit();
+  }
+  for (int s = s0; s < s1; ++s) {
+    const RpStep st = P.steps[s];
+    for (int l = st.load0; l < st.load0 + st.nloads; ++l)
+      rp_issue_load(P.loads[l], smem_raw + P.sm_abuf + P.loads[l].abuf * P.abuf_floats, P.lda, c.base, c.row0, B);
+    cp_async_commit();
+    RP_TRACE(1000 + s);
+    if (st.nloads > 0 || s == s0) { cp_async_wait<0>(); __syncthreads(); }
+    RP_TRACE(2000 + st.row_op);
+    switch (st.row_op) {
+      case RPR_GATHER: rp_gather(c); break;
+      case RPR_PI_HEADS: rp_pi_heads(c); break;
+      case RPR_TARGET_CRITIC: rp_target_critic(c); break;
+      case RPR_RELOAD: rp_reload(c); break;
+      case RPR_ACTOR_Q: rp_actor_q(c); break;
+      case RPR_PI_BWD: rp_pi_bwd(c); break;
+      default: break;
+    }
+    RP_TRACE(3000);
+    for (int j = st.job0; j < st.job0 + st.njobs; ++j) {
+      if (j + 2 < jend) rp_issue_weights(P.jobs[j + 2], wring + ((j + 2) % RP_NWSLOT) * P.wslot_floats, c.base, c.rank);
+      cp_async_commit();
+      RP_TRACE(3500);
+      cp_async_wait<2>();
+      RP_TRACE(3600);
+      __syncthreads();
+      RP_TRACE(4000 + j);
+      const RpJob jb = P.jobs[j];
+      rp_job(jb, c, j % RP_NWSLOT);
+      RP_TRACE(5000 + j);
+    }
+    if (s + 1 < s1) rp_group_barrier(c.gbar, gepoch);
+    RP_TRACE(6000 + s);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+// grid = n_groups x 8 CTAs (cooperative launch: all co-resident). gplan: phase 0 = critics' dW + Adam + Polyak tiles,
+// phase 1 = policy dW + Adam tiles and the final op (loss means, temperature step, update counter).
+__global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict__ gplan, const RpProgram* __restrict__ gprog, const RunArgs args) {
+  RP_SMEM;
+  __shared__ RpProgram sprog;
+  __shared__ RpRows rows;
+  __shared__ Op sops[RP_MAX_DW_OPS];
+  __shared__ Phase sphase[2];
+  __shared__ RpTrace trace;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const int* src = reinterpret_cast<const int*>(gprog);
+    int* dst = reinterpret_cast<int*>(&sprog);
+    for (int i = tid; i < (int)(sizeof(RpProgram) / 4); i += 256) dst[i] = src[i];
+    const int nops = min(gplan->n_ops, RP_MAX_DW_OPS);
+    const int* osrc = reinterpret_cast<const int*>(gplan->ops);
+    int* odst = reinterpret_cast<int*>(sops);
+    for (int i = tid; i < nops * (int)(sizeof(Op) / 4); i += 256) odst[i] = osrc[i];
+    if (tid < 2) sphase[tid] = gplan->phases[tid];
+    if (tid == 0) { trace.buf = nullptr; trace.n = 0; trace.cap = 0; }
+  }
+  __syncthreads();
+  const int rank = blockIdx.x % RP_CS, gid = blockIdx.x / RP_CS, ngr = gridDim.x / RP_CS;
+  float* base = args.arena;
+  AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
+  const int B = args.hp.B, nrb = (B + RP_RB - 1) / RP_RB;
+  RpCtx c{base, scal, &args, &sprog, &rows, args.rp_part + (i64)gid * sprog.part_stride, args.barrier + 64 * (1 + gid), rank, 0, 0, &trace};
+  // dW phases reuse the tile code of the tile-parallel kernel; their shared memory aliases the row-parallel buffers
+  float* wsm = smem_raw;
+  float* gsm = smem_raw + WSM_FLOATS;
+  RowCtx rc{base, scal, &args, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};
+  EpiCtx ec{base, scal, &args.hp, nullptr, gsm + CfgSmall::SMEM_FLOATS};
+  unsigned epoch = 0, gepoch = 0;
+  unsigned* counter = args.barrier;
+  const int sa = sprog.n_steps_a, sc = sprog.n_steps_c;
+  for (int step = 0; step < args.n_steps; ++step) {
+    c.step = step; rc.step = step;
+    if (tid == 0 && args.dbg2 && blockIdx.x == 0 && step + 1 == args.n_steps) { trace.buf = args.dbg2 + 1; trace.cap = 1000; trace.n = 0; }
+    // optional per-phase timestamps: [step][4 phases][CTA][arrive, release]
+    unsigned long long* dbg = (args.dbg && tid == 0) ? args.dbg + ((size_t)step * 4 * gridDim.x + blockIdx.x) * 2 : nullptr;
+    const size_t dstride = (size_t)gridDim.x * 2;
+    if (blockIdx.x == 0 && tid == 0) {
+      Op po; po.mode = 7;
+      op_prologue(po, rc);
+    }
+    for (int ph = 0; ph < 4; ++ph) {
+      if ((ph & 1) == 0) {          // row-parallel phases: A (target, critics' forward/backward), C (actor)
+        const int s0 = ph ? sa : 0, s1 = ph ? sa + sc : sa;
+        for (int rb = gid; rb < nrb; rb += ngr) { c.row0 = rb * RP_RB; rp_run_steps(c, s0, s1, gepoch); }
+      } else {                      // tile-parallel phases: dW + Adam (+ Polyak) of the critics (B) / the policy (D)
+        const Phase p = sphase[ph >> 1];
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+          int oi = p.op0;
+          while (oi + 1 < p.op0 + p.nops && t >= sops[oi + 1].tile0) ++oi;
+          const Op& op = sops[oi];
+          const int lt = t - op.tile0;
+          if (op.type == OP_GEMM) gemm_tile<CfgSmall>(op, ec, lt, gsm);
+          else if (op.type == OP_FINAL) { if (warp == 0) op_final(op, rc, lane); }
+        }
+      }
+      const bool very_last = (ph == 3) && (step + 1 == args.n_steps);
+      RP_TRACE(7000 + ph);
+      if (dbg) dbg[ph * dstride] = clock64();
+      if (!very_last) group_barrier(counter, epoch, args.barrier_mode);
+      if (dbg) dbg[ph * dstride + 1] = clock64();
+    }
+  }
+  if (tid == 0 && trace.buf) args.dbg2[0] = (unsigned long long)trace.n;
+}
+
+}  // namespace sacx

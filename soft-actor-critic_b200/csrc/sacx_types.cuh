@@ -112,6 +112,7 @@ struct RunArgs {
   unsigned long long* dbg;   // optional [n_steps][n_phases][gridDim.x][2] clock64 at barrier arrive / release
   unsigned long long* dbg2;  // optional [n_steps][n_phases][gridDim.x][8] intra-tile timestamps of the CTA's last GEMM tile
   int barrier_mode, pad_;
+  float* rp_part;            // row-parallel kernel: partial-sum scratch [groups][part_stride]
   Hyper hp;
 };
 

@@ -102,6 +102,14 @@ class UpdateEngine:
         E.check(self.lib.sacx_agent_grid(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def path(self) -> Tuple[str, str]:
+        """("rowpar" | "tiles", reason): which kernel runs ``update`` (include/sacx.h: sacx_agent_path)."""
+        buf = C.create_string_buffer(128)
+        rc = self.lib.sacx_agent_path(self.h, buf, 128)
+        if rc < 0:
+            E.check(rc)
+        return ("rowpar" if rc == 1 else "tiles"), buf.value.decode()
+
     def sync(self) -> None:
         E.check(self.lib.sacx_sync(self.h))
 

@@ -211,10 +211,12 @@ def test_fused_update_free_running_vs_reference(name):
                     assert abs((v64 * v64).sum() - g[key + "#chk"][1]) <= 1e-4 * g[key + "#chk"][1] + 1e-12
 
 
-def test_fused_equals_per_phase_launches():
-    """The persistent cooperative kernel and one-launch-per-phase execute the same op table: identical bits."""
+def test_fused_equals_per_phase_launches(monkeypatch):
+    """The persistent cooperative tile-parallel kernel and one-launch-per-phase execute the same op table: identical
+    bits. (SACX_ROWPAR=0: the row-parallel kernel is a different summation order, compared in test_gpu_rowpar.py.)"""
     from sac.replay_buffer import ReplayBuffer
 
+    monkeypatch.setenv("SACX_ROWPAR", "0")
     g = Golden("bipedal")
     res = []
     for staged in (False, True):

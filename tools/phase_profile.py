@@ -46,6 +46,14 @@ for p in range(P):
 tot = np.median(release[2:, -2, 0] - release[1:-1, -2, 0]) if steps > 3 else 0
 print("cycles per update (CTA0, release-to-release of phase P-2):", int(tot), "=", tot / 1.965e3, "us")
 
+if eng.path()[0] == "rowpar":
+    tr = buf[steps * P * G * 2:]
+    n = int(tr[0])
+    ev = tr[1: 1 + 2 * n].reshape(n, 2).astype(np.int64)
+    print(f"event trace of CTA 0, last update ({n} events): tag  +cycles-since-previous  cycles-since-first")
+    for i in range(n):
+        print(f"  {ev[i, 0]:5d} {ev[i, 1] - ev[max(i - 1, 0), 1]:8d} {ev[i, 1] - ev[0, 1]:9d}")
+    sys.exit(0)
 t2 = buf[steps * P * G * 2: steps * P * G * 10].reshape(steps, P, G, 8).astype(np.int64)
 print("intra-tile (CTA's last GEMM tile), median over steps and CTAs that ran a GEMM tile: load0  kloop  reduce  epilogue  total")
 for p in range(P):
