@@ -854,15 +854,14 @@ struct Engine {
     P.lda = hmax + 4; P.abuf_floats = RP_RB * P.lda;
     P.ldx = ((O + A + 7) & ~7) + 4;
     P.gldx = ldx;
-    P.wslot_floats = (wmax + 3) & ~3;
+    P.wslot_floats = ((wmax + 3) & ~3) + 1024;      // + epilogue operand [16][32] + projection weights [16][32]
     int off = 0;
     P.sm_abuf = off; off += RP_NABUF * P.abuf_floats;
     P.sm_xbuf = off; off += 3 * RP_RB * P.ldx;
     off = (off + 3) & ~3;
     P.sm_wslot = off; off += RP_NWSLOT * P.wslot_floats;
     P.sm_red = off; off += RP_RED;
-    P.sm_otile = off; off += RP_RB * 33 + 3; off &= ~3;
-    P.sm_pw = off; off += 2 * RP_MAXA * 32;
+    P.sm_otile = off; P.sm_pw = off;
     off = std::max(off, WSM_FLOATS + CfgSmall::SMEM_FLOATS);      // the dW tiles alias the same region
     P.sm_total = off;
     // partial-sum scratch of one group (global memory): [slot][rank][16][J]

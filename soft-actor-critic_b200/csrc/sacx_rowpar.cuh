@@ -80,6 +80,7 @@ struct RpRows {            // per-row state of the current row block (every CTA 
 
 // optional event trace of CTA 0 (profiling aid): (tag, clock64) pairs of the launch's last update
 struct RpTrace { unsigned long long* buf; int n, cap; };
+
 #define RP_TRACE(tag) do { if (c.tr->buf && threadIdx.x == 0 && c.tr->n < c.tr->cap) { \
   c.tr->buf[2 * c.tr->n] = (unsigned long long)(tag); c.tr->buf[2 * c.tr->n + 1] = clock64(); c.tr->n++; } } while (0)
 
@@ -103,6 +104,10 @@ __device__ __forceinline__ float rp_lds(uint32_t a) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
+}
+
+__device__ __forceinline__ void rp_cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rp_saddr(smem_dst)), "l"(gsrc) : "memory");
 }
 
 // ---- 3xTF32 tensor-core arithmetic ------------------------------------------------------------------------------
@@ -149,10 +154,19 @@ __device__ __forceinline__ void rp_group_barrier(unsigned* counter, unsigned& ep
   __syncthreads();
 }
 
-// ---- weight slice: global (L2) -> shared-memory slot ----------------------------------------------------------------
-__device__ __forceinline__ void rp_issue_weights(const RpJob& jb, float* __restrict__ slot, const float* __restrict__ base, int rank) {
-  const int NS = 1 << jb.ns_log2, n0g = rank << jb.ns_log2, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+// ---- everything job j needs, global (L2) -> its shared-memory slot, two jobs ahead of its use --------------------------
+// slot = [weight slice | epilogue operand (bias[NS] or aux[16][NS]) | projection weights [J][NS]], all by cp.async (one
+// commit group per job, committed by the caller). (1-D bulk copies were tried: ~90 cycles of issue per row copy on the
+// single TMA queue -- 3.5K cycles for a 32-row slice -- against ~1.4K for 8 cp.async per thread.)
+__device__ __forceinline__ void rp_issue_job(const RpJob& jb, float* __restrict__ slot, const RpCtx& c) {
+  const RpProgram& P = *c.P;
+  const float* __restrict__ base = c.base;
+  const int NS = 1 << jb.ns_log2, n0g = c.rank << jb.ns_log2, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ W = base + jb.w;
+  float* eps = slot + P.wslot_floats - 1024;
+  float* pws = slot + P.wslot_floats - 512;
+  const int J = jb.proj_J, cl = jb.ns_log2 - 2;            // chunks per NS-wide row = NS / 4 = 1 << cl
+  const int B = c.args->hp.B;
   if (!jb.bkm) {
     const int ldw = jb.Kp + 4;
     const bool vec = ((jb.K & 3) == 0) && ((jb.w & 3) == 0) && ((jb.w_ld & 3) == 0);
@@ -172,13 +186,33 @@ __device__ __forceinline__ void rp_issue_weights(const RpJob& jb, float* __restr
         for (int k = lane; k < jb.Kp; k += 32)
           slot[n * ldw + k] = (k < jb.K) ? __ldcg(W + (i64)(n0g + n) * jb.w_ld + k) : 0.f;
     }
+    if (tid < (1 << cl)) cp_async16(eps + (tid << 2), base + jb.bias + n0g + (tid << 2), 16);
   } else {
     // [K][NS], 8-column groups XOR-swizzled by the row so that the (k = t, n = g) fragment reads hit 32 banks
-    const int cl = jb.ns_log2 - 2, sh = 5 - jb.ns_log2;       // chunks per row = NS / 4
+    const int sh = 5 - jb.ns_log2;
     const int ch = (tid & ((1 << cl) - 1)) << 2;
-    for (int k = tid >> cl; k < jb.K; k += 256 >> cl) {
+    const float* src = W + n0g + ch + (i64)(tid >> cl) * jb.w_ld;
+    const i64 sstep = (i64)(256 >> cl) * jb.w_ld;
+    for (int k = tid >> cl; k < jb.K; k += 256 >> cl, src += sstep) {
       const int sw = ((k & 3) >> sh) << 3;
-      cp_async16(slot + k * NS + (ch ^ sw), W + (i64)k * jb.w_ld + n0g + ch, 16);
+      cp_async16(slot + k * NS + (ch ^ sw), src, 16);
+    }
+    if (tid < (RP_RB << cl)) {          // aux: saved activations of this CTA's own slice, [16][NS]
+      const int m = tid >> cl, cc = (tid & ((1 << cl) - 1)) << 2;
+      const bool ok = c.row0 + m < B;
+      cp_async16(eps + m * NS + cc, ok ? base + jb.aux + (i64)(c.row0 + m) * jb.aux_ld + n0g + cc : base, ok ? 16 : 0);
+    }
+  }
+  if (J > 0) {
+    if (jb.proj_sn == 1) {
+      const int i = tid - 128;           // threads 128.. : J rows of NS contiguous floats
+      if (i >= 0 && i < (J << cl)) {
+        const int j = i >> cl, cc = (i & ((1 << cl) - 1)) << 2;
+        cp_async16(pws + j * NS + cc, base + jb.proj_w + (i64)j * jb.proj_sj + n0g + cc, 16);
+      }
+    } else {
+      for (int i = tid; i < J * NS; i += 256)
+        rp_cp_async4(pws + i, base + jb.proj_w + (i64)(i >> jb.ns_log2) * jb.proj_sj + (i64)(n0g + (i & (NS - 1))) * jb.proj_sn);
     }
   }
 }
@@ -247,70 +281,71 @@ __device__ __forceinline__ void rp_job(const RpJob& jb, const RpCtx& c, int wslo
   if (jb.a_src < RP_NABUF) { As = smem_raw + P.sm_abuf + jb.a_src * P.abuf_floats; lda = P.lda; }
   else { As = smem_raw + P.sm_xbuf + (jb.a_src - RPS_XSA) * RP_RB * P.ldx; lda = P.ldx; }
   const float* Bs = smem_raw + P.sm_wslot + wslot_idx * P.wslot_floats;
-  // epilogue operands travel while the tensor cores work
-  const int e = tid * 2, m = e >> jb.ns_log2, n = e & (NS - 1);
-  const bool own = e < RP_RB * NS, rowok = own && (c.row0 + m < B);
-  float2 ep = make_float2(0.f, 0.f);
-  if (own) {
-    if (!jb.bkm) { if (jb.bias >= 0) ep = __ldcg(reinterpret_cast<const float2*>(c.base + jb.bias + n0g + n)); }
-    else if (rowok) ep = __ldcg(reinterpret_cast<const float2*>(c.base + jb.aux + (i64)(c.row0 + m) * jb.aux_ld + n0g + n));
-  }
-  const int J = jb.proj_J;
-  float pwv[2] = {0.f, 0.f};
-  if (J > 0) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int i = tid + 256 * u;
-      if (i < J * NS) pwv[u] = __ldcg(c.base + jb.proj_w + (i64)(i >> jb.ns_log2) * jb.proj_sj + (i64)(n0g + (i & (NS - 1))) * jb.proj_sn);
-    }
-  }
+  const float* eps = Bs + P.wslot_floats - 1024;
+  const float* pws = Bs + P.wslot_floats - 512;
   float* red = smem_raw + P.sm_red;
   RP_TRACE(4500);
   rp_job_math(jb, rp_saddr(As), lda, rp_saddr(Bs), red);
   RP_TRACE(4600);
-  float* pw = smem_raw + P.sm_pw;
-  if (J > 0) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) if (tid + 256 * u < J * NS) pw[tid + 256 * u] = pwv[u];
-  }
   __syncthreads();
   RP_TRACE(4650);
-  float* otile = smem_raw + P.sm_otile;
-  if (own) {
+  // thread owns outputs (m, n) and (m, n + 1) of the 16 x NS slice; the NS / 2 lanes of a row sit in one warp
+  const int e = tid * 2, m = e >> jb.ns_log2, n = e & (NS - 1);
+  if (e < RP_RB * NS) {               // warp-uniform
     float2 s = make_float2(0.f, 0.f);
     for (int q = 0; q < KG; ++q) {
       const float2 p = *reinterpret_cast<const float2*>(red + (q * 16 + m) * RS + n);
       s.x += p.x; s.y += p.y;
     }
     float2 v;
-    if (!jb.bkm) v = make_float2(act_fwd(jb.act, s.x + ep.x), act_fwd(jb.act, s.y + ep.y));
-    else v = make_float2(s.x * act_dz(jb.act, ep.x), s.y * act_dz(jb.act, ep.y));
-    if (rowok && jb.out >= 0) *reinterpret_cast<float2*>(c.base + jb.out + (i64)(c.row0 + m) * jb.out_ld + n0g + n) = v;
-    if (J > 0) { otile[m * 33 + n] = v.x; otile[m * 33 + n + 1] = v.y; }
-  }
-  if (J > 0) {
-    __syncthreads();
-    if (tid < RP_RB * J) {
-      const int mm = tid / J, j = tid - mm * J;
-      float s = 0.f;
-      const float* o = otile + mm * 33;
-      const float* w = pw + j * NS;
-      for (int nn = 0; nn < NS; ++nn) s = fmaf(o[nn], w[nn], s);
-      // share of CTA `rank`: [rank][m][j] in the group's scratch; the 8 shares are summed in rank order by every reader
-      c.part[P.part_off[jb.proj_slot] + (c.rank * RP_RB + mm) * J + j] = s;
+    if (!jb.bkm) {
+      const float2 bb = *reinterpret_cast<const float2*>(eps + n);
+      v = make_float2(act_fwd(jb.act, s.x + bb.x), act_fwd(jb.act, s.y + bb.y));
+    } else {
+      const float2 ax = *reinterpret_cast<const float2*>(eps + m * NS + n);
+      v = make_float2(s.x * act_dz(jb.act, ax.x), s.y * act_dz(jb.act, ax.y));
+    }
+    if (c.row0 + m < B && jb.out >= 0) *reinterpret_cast<float2*>(c.base + jb.out + (i64)(c.row0 + m) * jb.out_ld + n0g + n) = v;
+    const int J = jb.proj_J;
+    if (J > 0) {
+      // projection of the row's slice onto J weight vectors: butterfly over the row's lanes (fixed order: deterministic);
+      // share of CTA `rank` goes to [rank][m][j] of the group's scratch, summed in rank order by every reader
+      const int lpr = NS >> 1, r = (tid & 31) & (lpr - 1);
+      float* dst = c.part + P.part_off[jb.proj_slot] + (c.rank * RP_RB + m) * J;
+      for (int j0 = 0; j0 < J; j0 += 8) {
+        float p[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          p[jj] = 0.f;
+          if (j0 + jj < J) {
+            const float2 w = *reinterpret_cast<const float2*>(pws + (j0 + jj) * NS + n);
+            p[jj] = fmaf(v.x, w.x, v.y * w.y);
+          }
+        }
+        for (int o = lpr >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) p[jj] += __shfl_xor_sync(0xffffffffu, p[jj], o);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          if (j0 + jj < J && r == ((j0 + jj) & (lpr - 1))) dst[j0 + jj] = p[jj];
+      }
     }
   }
 }
 
-// sum of the 8 CTAs' shares of element (m, j) of a partial slot, in rank order (deterministic); loads are independent
-__device__ __forceinline__ float rp_sum_parts(const RpCtx& c, int slot, int J, int m, int j) {
+// the 8 CTAs' shares of element (m, j) of a partial slot: loads first (independent L2 requests; __ldcg is a volatile asm,
+// so a sum between two groups of loads would serialise their round trips), summed later in rank order (deterministic)
+struct RpParts { float v[RP_CS]; };
+__device__ __forceinline__ void rp_load_parts(const RpCtx& c, int slot, int J, int m, int j, RpParts& o) {
   const float* p = c.part + c.P->part_off[slot] + m * J + j;
-  float v[RP_CS];
 #pragma unroll
-  for (int r = 0; r < RP_CS; ++r) v[r] = __ldcg(p + r * RP_RB * J);
+  for (int r = 0; r < RP_CS; ++r) o.v[r] = __ldcg(p + r * RP_RB * J);
+}
+__device__ __forceinline__ float rp_add_parts(const RpParts& o) {
   float s = 0.f;
 #pragma unroll
-  for (int r = 0; r < RP_CS; ++r) s += v[r];
+  for (int r = 0; r < RP_CS; ++r) s += o.v[r];
   return s;
 }
 __device__ __forceinline__ float rp_sum8(float v) {     // sum over the 8 lanes that share a row
@@ -323,7 +358,7 @@ __device__ __forceinline__ float rp_sum8(float v) {     // sum over the 8 lanes 
 // ---- row ops --------------------------------------------------------------------------------------------------------
 // ring rows -> the three input buffers (a2/a3), the update's normals; rank 0 mirrors the batch into the arena.
 // Warp w owns rows 2w and 2w+1; all ring loads of a thread are in flight before the first is used.
-__device__ __forceinline__ void rp_gather(const RpCtx& c) {
+__device__ __noinline__ void rp_gather(const RpCtx& c) {
   RP_SMEM;
   const RunArgs& a = *c.args;
   const Hyper& hp = a.hp;
@@ -426,7 +461,7 @@ __device__ __forceinline__ void rp_gather(const RpCtx& c) {
 }
 
 // policy heads of pi(s') and pi(s) from the reduced partials: rsample, tanh squash, log-prob (models.py:73-87)
-__device__ __forceinline__ void rp_pi_heads(const RpCtx& c) {
+__device__ __noinline__ void rp_pi_heads(const RpCtx& c) {
   RP_SMEM;
   const Hyper& hp = c.args->hp;
   const RpProgram& P = *c.P;
@@ -441,9 +476,12 @@ __device__ __forceinline__ void rp_pi_heads(const RpCtx& c) {
   float lp = 0.f;
   bool bad = false;
   if (act_lane) {
+    RpParts pm, pl;
+    rp_load_parts(c, slot, J, mm, j, pm);
+    rp_load_parts(c, slot, J, mm, A + j, pl);
     const float bm = __ldcg(c.base + P.pi_bL + j), bl = __ldcg(c.base + P.pi_bL + A + j);
-    const float zm = rp_sum_parts(c, slot, J, mm, j) + bm;
-    const float zl = rp_sum_parts(c, slot, J, mm, A + j) + bl;
+    const float zm = rp_add_parts(pm) + bm;
+    const float zl = rp_add_parts(pl) + bl;
     const float mu = act_fwd(P.act_opi, zm), ls_raw = act_fwd(P.act_opi, zl);
     const float ls = fminf(fmaxf(ls_raw, hp.log_std_min), hp.log_std_max);
     const float sd = expf(ls);
@@ -502,6 +540,7 @@ __device__ __forceinline__ void rp_delta_critics(const RpCtx& c, const float4 (&
       *p = dv;
       if (mine && c.row0 + mm < B) *reinterpret_cast<float4*>(c.base + P.dq_last[cc] + (i64)(c.row0 + mm) * P.ld_hq + k) = dv;
     }
+    RP_TRACE(2910 + cc);
   }
   __syncthreads();
 }
@@ -512,21 +551,25 @@ __device__ __forceinline__ void rp_load_wl(const RpCtx& c, float4 (&wl)[2]) {
 }
 
 // soft Bellman target (agent.py:195-211) and the critics' loss gradient (agent.py:213-236) for the row block
-__device__ __forceinline__ void rp_target_critic(const RpCtx& c) {
+__device__ __noinline__ void rp_target_critic(const RpCtx& c) {
   const Hyper& hp = c.args->hp;
   const RpProgram& P = *c.P;
   RpRows& R = *c.R;
   const int tid = threadIdx.x, B = hp.B;
   float4 wl[2];
   rp_load_wl(c, wl);
+  RP_TRACE(2901);
   if (tid < RP_RB) {
     const int mm = tid, row = c.row0 + mm;
     const bool ok = row < B, w0 = c.rank == 0;
+    RpParts pt[2], pq[2];
+    rp_load_parts(c, RPP_QT1, 1, mm, 0, pt[0]); rp_load_parts(c, RPP_QT2, 1, mm, 0, pt[1]);
+    rp_load_parts(c, RPP_Q1, 1, mm, 0, pq[0]); rp_load_parts(c, RPP_Q2, 1, mm, 0, pq[1]);
     const float alpha = __ldcg(&c.scal->alpha_f32);
     const float bt[2] = {__ldcg(c.base + P.qt_bL[0]), __ldcg(c.base + P.qt_bL[1])};
     const float bq[2] = {__ldcg(c.base + P.q_bL[0]), __ldcg(c.base + P.q_bL[1])};
-    const float st[2] = {rp_sum_parts(c, RPP_QT1, 1, mm, 0), rp_sum_parts(c, RPP_QT2, 1, mm, 0)};
-    const float sq[2] = {rp_sum_parts(c, RPP_Q1, 1, mm, 0), rp_sum_parts(c, RPP_Q2, 1, mm, 0)};
+    const float st[2] = {rp_add_parts(pt[0]), rp_add_parts(pt[1])};
+    const float sq[2] = {rp_add_parts(pq[0]), rp_add_parts(pq[1])};
     const float tq[2] = {act_fwd(P.act_oq, st[0] + bt[0]), act_fwd(P.act_oq, st[1] + bt[1])};
     const float y = R.r[mm] + (hp.gamma * (1.f - R.d[mm])) * (fminf(tq[0], tq[1]) - alpha * R.lp2[mm]);
     if (w0 && ok) { c.base[P.b_y + row] = y; c.base[P.b_tq[0] + row] = tq[0]; c.base[P.b_tq[1] + row] = tq[1]; }
@@ -540,12 +583,14 @@ __device__ __forceinline__ void rp_target_critic(const RpCtx& c) {
       if (w0 && ok) { c.base[P.b_q[cc] + row] = q; c.base[P.b_dout[cc] + (i64)row * 4] = dout; c.base[P.b_loss[cc] + row] = diff * diff; }
     }
   }
+  RP_TRACE(2902);
   __syncthreads();
+  RP_TRACE(2903);
   rp_delta_critics(c, wl, true);
 }
 
 // phase C entry: the row block's (s, a~pi) rows and the saved head quantities come back from the arena
-__device__ __forceinline__ void rp_reload(const RpCtx& c) {
+__device__ __noinline__ void rp_reload(const RpCtx& c) {
   RP_SMEM;
   const RpProgram& P = *c.P;
   RpRows& R = *c.R;
@@ -595,7 +640,7 @@ __device__ __forceinline__ void rp_reload(const RpCtx& c) {
 }
 
 // critics on (s, a~pi): min, policy loss rows, routed dQ (agent.py:238-260)
-__device__ __forceinline__ void rp_actor_q(const RpCtx& c) {
+__device__ __noinline__ void rp_actor_q(const RpCtx& c) {
   const Hyper& hp = c.args->hp;
   const RpProgram& P = *c.P;
   RpRows& R = *c.R;
@@ -605,9 +650,11 @@ __device__ __forceinline__ void rp_actor_q(const RpCtx& c) {
   if (tid < RP_RB) {
     const int mm = tid, row = c.row0 + mm;
     const bool ok = row < B, w0 = c.rank == 0;
+    RpParts pq[2];
+    rp_load_parts(c, RPP_Q1, 1, mm, 0, pq[0]); rp_load_parts(c, RPP_Q2, 1, mm, 0, pq[1]);
     const float alpha = __ldcg(&c.scal->alpha_f32);
     const float bq[2] = {__ldcg(c.base + P.q_bL[0]), __ldcg(c.base + P.q_bL[1])};
-    const float sq[2] = {rp_sum_parts(c, RPP_Q1, 1, mm, 0), rp_sum_parts(c, RPP_Q2, 1, mm, 0)};
+    const float sq[2] = {rp_add_parts(pq[0]), rp_add_parts(pq[1])};
     const float z[2] = {sq[0] + bq[0], sq[1] + bq[1]};
     const float q[2] = {act_fwd(P.act_oq, z[0]), act_fwd(P.act_oq, z[1])};
     const float w1 = q[0] < q[1] ? 1.f : (q[0] == q[1] ? 0.5f : 0.f);      // torch.min backward, ties split
@@ -624,7 +671,7 @@ __device__ __forceinline__ void rp_actor_q(const RpCtx& c) {
 }
 
 // dQ/da from the layer-0 partials, closed-form head backward, delta of the policy's last hidden layer
-__device__ __forceinline__ void rp_pi_bwd(const RpCtx& c) {
+__device__ __noinline__ void rp_pi_bwd(const RpCtx& c) {
   RP_SMEM;
   const Hyper& hp = c.args->hp;
   const RpProgram& P = *c.P;
@@ -641,8 +688,10 @@ __device__ __forceinline__ void rp_pi_bwd(const RpCtx& c) {
     const int mm = tid >> 3, j = tid & 7, row = c.row0 + mm;
     if (j < A) {
       const bool ok = row < B;
+      RpParts d1, d2;
+      rp_load_parts(c, RPP_DA1, A, mm, j, d1); rp_load_parts(c, RPP_DA2, A, mm, j, d2);
       const float alpha = __ldcg(&c.scal->alpha_f32);
-      const float da = rp_sum_parts(c, RPP_DA1, A, mm, j) + rp_sum_parts(c, RPP_DA2, A, mm, j);
+      const float da = rp_add_parts(d1) + rp_add_parts(d2);
       const float ab = alpha / (float)hp.B_global;
       const float tz = R.tz[mm][j], se = R.se[mm][j], mk = R.mk[mm][j];
       const float dz = ab * (2.f * tz) + da * (hp.action_scale * (1.f - tz * tz));
@@ -679,23 +728,30 @@ __device__ __forceinline__ void rp_pi_bwd(const RpCtx& c) {
 }
 
 // ---- the step interpreter ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, unsigned& gepoch) {
+struct RpSync {            // barrier state that lives across phases and updates
+  unsigned gepoch;         // group barrier epoch
+};
+
+__device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, RpSync& sy) {
   RP_SMEM;
   const RpProgram& P = *c.P;
   const int jbeg = P.steps[s0].job0, jend = P.steps[s1 - 1].job0 + P.steps[s1 - 1].njobs;
   float* wring = smem_raw + P.sm_wslot;
   const int B = c.args->hp.B;
   for (int j = jbeg; j < jbeg + 2; ++j) {
-    if (j < jend) rp_issue_weights(P.jobs[j], wring + (j % RP_NWSLOT) * P.wslot_floats, c.base, c.rank);
+    if (j < jend) rp_issue_job(P.jobs[j], wring + (j % RP_NWSLOT) * P.wslot_floats, c);
     cp_async_commit();
   }
   for (int s = s0; s < s1; ++s) {
     const RpStep st = P.steps[s];
-    for (int l = st.load0; l < st.load0 + st.nloads; ++l)
-      rp_issue_load(P.loads[l], smem_raw + P.sm_abuf + P.loads[l].abuf * P.abuf_floats, P.lda, c.base, c.row0, B);
-    cp_async_commit();
     RP_TRACE(1000 + s);
-    if (st.nloads > 0 || s == s0) { cp_async_wait<0>(); __syncthreads(); }
+    if (st.nloads > 0) {
+      for (int l = st.load0; l < st.load0 + st.nloads; ++l)
+        rp_issue_load(P.loads[l], smem_raw + P.sm_abuf + P.loads[l].abuf * P.abuf_floats, P.lda, c.base, c.row0, B);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+    }
     RP_TRACE(2000 + st.row_op);
     switch (st.row_op) {
       case RPR_GATHER: rp_gather(c); break;
@@ -708,18 +764,19 @@ __device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, uns
     }
     RP_TRACE(3000);
     for (int j = st.job0; j < st.job0 + st.njobs; ++j) {
-      if (j + 2 < jend) rp_issue_weights(P.jobs[j + 2], wring + ((j + 2) % RP_NWSLOT) * P.wslot_floats, c.base, c.rank);
-      cp_async_commit();
+      const int sl = j % RP_NWSLOT;
+      cp_async_wait<1>();                      // this thread's share of job j has landed (job j + 1 may still be in flight)
+      __syncthreads();                         // ... everyone's has; and everyone is done with job j - 1
       RP_TRACE(3500);
-      cp_async_wait<2>();
-      RP_TRACE(3600);
-      __syncthreads();
+      // slot of job j + 2 == slot of job j - 1: free now
+      if (j + 2 < jend) rp_issue_job(P.jobs[j + 2], wring + ((j + 2) % RP_NWSLOT) * P.wslot_floats, c);
+      cp_async_commit();
       RP_TRACE(4000 + j);
       const RpJob jb = P.jobs[j];
-      rp_job(jb, c, j % RP_NWSLOT);
+      rp_job(jb, c, sl);
       RP_TRACE(5000 + j);
     }
-    if (s + 1 < s1) rp_group_barrier(c.gbar, gepoch);
+    if (s + 1 < s1) rp_group_barrier(c.gbar, sy.gepoch);
     RP_TRACE(6000 + s);
   }
   cp_async_wait<0>();
@@ -758,7 +815,8 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   float* gsm = smem_raw + WSM_FLOATS;
   RowCtx rc{base, scal, &args, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};
   EpiCtx ec{base, scal, &args.hp, nullptr, gsm + CfgSmall::SMEM_FLOATS};
-  unsigned epoch = 0, gepoch = 0;
+  unsigned epoch = 0;
+  RpSync sy{0u};
   unsigned* counter = args.barrier;
   const int sa = sprog.n_steps_a, sc = sprog.n_steps_c;
   for (int step = 0; step < args.n_steps; ++step) {
@@ -774,7 +832,7 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
     for (int ph = 0; ph < 4; ++ph) {
       if ((ph & 1) == 0) {          // row-parallel phases: A (target, critics' forward/backward), C (actor)
         const int s0 = ph ? sa : 0, s1 = ph ? sa + sc : sa;
-        for (int rb = gid; rb < nrb; rb += ngr) { c.row0 = rb * RP_RB; rp_run_steps(c, s0, s1, gepoch); }
+        for (int rb = gid; rb < nrb; rb += ngr) { c.row0 = rb * RP_RB; rp_run_steps(c, s0, s1, sy); }
       } else {                      // tile-parallel phases: dW + Adam (+ Polyak) of the critics (B) / the policy (D)
         const Phase p = sphase[ph >> 1];
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
