@@ -155,6 +155,10 @@ int sacx_agent_grid(sacx_agent_t h, int32_t* ctas_per_agent, int32_t* agent_slot
 /* which kernel executes sacx_update: 1 = row-parallel cluster kernel (8-CTA clusters own 16-row blocks, 3xTF32 tensor-core
  * tiles), 0 = tile-parallel persistent kernel (any shape). reason (may be NULL) receives a short text when 0. */
 int sacx_agent_path(sacx_agent_t h, char* reason, int32_t capacity);
+/* 1 when the MLP GEMMs of this agent run on the tcgen05 tensor-core path (single agent, batch >= SACX_TC_MIN_BATCH,
+ * default 4096: 3xTF32 tiles with TMEM accumulators, TMA-staged operands; sacx_tc.cuh), 0 otherwise (reason, may be NULL,
+ * says why). tc_launches (may be NULL) receives the number of tensor-core kernel launches so far. */
+int sacx_agent_tc(sacx_agent_t h, char* reason, int32_t capacity, int64_t* tc_launches);
 
 /* replaces SAC.training_step (agent.py:302-327), n_steps consecutive updates in ONE launch of the
  * persistent fused kernel: gather -> target -> critic Adam x2 -> actor Adam -> alpha -> Polyak.

@@ -130,6 +130,51 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
     ++e->launches;
     return SACX_OK;
   };
+  if (e->tc && !per_phase) {
+    bool any = false;
+    for (int p = pb; p < pe; ++p) any = any || !e->tc_phases[plan_id][p].groups.empty();
+    if (any) {
+      // tensor-core plan walk: runs of phases without TC ops go through the persistent kernel (cooperative when the run
+      // has more than one phase); a phase with TC ops launches the tcgen05 kernel per group of <= 4 GEMMs (+ the dW
+      // reduce/optimiser kernel) and, when it also holds row ops, the persistent kernel with the TC GEMMs masked out
+      const i64 nb = (i64)e->cfg.n_agents * e->cfg.batch_size;
+      for (int s = 0; s < n_steps; ++s) {
+        if (proto.idx_ext) a.idx_ext = proto.idx_ext + s * nb;
+        if (proto.eps1_ext) a.eps1_ext = proto.eps1_ext + s * nb * e->cfg.act_dim;
+        if (proto.eps2_ext) a.eps2_ext = proto.eps2_ext + s * nb * e->cfg.act_dim;
+        int p = pb;
+        while (p < pe) {
+          Engine::TcPhase& tp = e->tc_phases[plan_id][p];
+          if (tp.groups.empty()) {
+            int q = p + 1;
+            while (q < pe && e->tc_phases[plan_id][q].groups.empty()) ++q;
+            a.tc_skip = 0;
+            int rc = launch(p, q, 1, dim3(e->grid_x, e->grid_y), e->grid_x > 1 && q - p > 1);
+            if (rc) return rc;
+            p = q;
+            continue;
+          }
+          if (tp.other_ops) {
+            a.tc_skip = 1;
+            int rc = launch(p, p + 1, 1, dim3(e->grid_x, e->grid_y), false);
+            if (rc) return rc;
+            a.tc_skip = 0;
+          }
+          for (Engine::TcGroup& g : tp.groups) {
+            sacx_tc_kernel<<<g.grid, TC_THREADS, TC_SMEM_BYTES, e->stream>>>(g.p, g.maps);
+            ++e->launches; ++e->tc_launches;
+            if (g.has_red) {
+              tc_dw_reduce_kernel<<<dim3(g.red_blocks, g.red.n_ops), 256, 0, e->stream>>>(g.red);
+              ++e->launches;
+            }
+          }
+          SACX_CUDA(cudaGetLastError());
+          ++p;
+        }
+      }
+      return SACX_OK;
+    }
+  }
   if (per_phase) {
     // one launch per phase, no in-kernel barrier: grid.x covers the phase's tiles, grid.y the agents
     for (int s = 0; s < n_steps; ++s) {
@@ -203,6 +248,121 @@ static int engine_setup_rp(Engine* e) {
   SACX_CUDA(cudaMemset(e->d_rp_part, 0, sizeof(float) * (size_t)RP_MAX_GROUPS * e->h_prog.part_stride));
   SACX_CUDA(cudaMalloc((void**)&e->d_prog, sizeof(RpProgram)));
   SACX_CUDA(cudaMemcpy(e->d_prog, &e->h_prog, sizeof(RpProgram), cudaMemcpyHostToDevice));
+  return SACX_OK;
+}
+
+// ---- tensor-core path setup: mark the eligible GEMM ops of every plan, encode their TMA descriptors ------------------------
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp32 tensor [outer][inner] with row stride ld (floats); out-of-range box elements read as zero / are not written
+static bool tc_encode(TcEncodeFn enc, CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_in, uint32_t box_out, bool atom32) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_in, box_out};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int engine_setup_tc(Engine* e) {
+  e->tc = e->tc_wanted(e->tc_why);
+  if (!e->tc) return SACX_OK;
+  auto off = [&](const std::string& why) { e->tc = false; e->tc_why = why; e->tc_phases.clear(); cudaGetLastError(); return SACX_OK; };
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+    return off("cuTensorMapEncodeTiled is not available");
+  TcEncodeFn enc = (TcEncodeFn)fn;
+  if (cudaFuncSetAttribute(sacx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+    return off("cannot raise the dynamic shared memory limit of the tensor-core kernel");
+  auto rup = [](int x, int m) { return (x + m - 1) / m * m; };
+  // pass 0 sizes the scratch (dW partial tiles), pass 1 builds descriptors against the allocated scratch
+  for (int pass = 0; pass < 2; ++pass) {
+    size_t need = 0;
+    bool ok = true;
+    e->tc_phases.assign(N_PLANS, std::vector<Engine::TcPhase>());
+    for (int id = 0; id < N_PLANS; ++id) {
+      Plan& pl = e->h_plans[id];
+      if (id == PLAN_RP) continue;
+      e->tc_phases[id].resize(pl.n_phases);
+      for (int ph = 0; ph < pl.n_phases; ++ph) {
+        Engine::TcPhase& tp = e->tc_phases[id][ph];
+        std::vector<int> elig;
+        for (int i = pl.phases[ph].op0; i < pl.phases[ph].op0 + pl.phases[ph].nops; ++i) {
+          if (e->tc_op_eligible(pl.ops[i])) { elig.push_back(i); pl.ops[i].cfg |= 2; }
+          else tp.other_ops = true;
+        }
+        size_t so = 0;                       // scratch offset inside this phase (floats)
+        for (size_t g0 = 0; g0 < elig.size(); g0 += TC_MAX_OPS) {
+          tp.groups.emplace_back();
+          Engine::TcGroup& g = tp.groups.back();
+          memset(&g.p, 0, sizeof g.p); memset(&g.maps, 0, sizeof g.maps); memset(&g.red, 0, sizeof g.red);
+          g.p.arena = e->arena; g.p.scratch = e->d_tc_scratch;
+          g.red.arena = e->arena; g.red.scratch = e->d_tc_scratch; g.red.scal_off = e->scal_off; g.red.hp = e->hp;
+          int tiles = 0;
+          for (size_t k = g0; k < std::min(elig.size(), g0 + TC_MAX_OPS); ++k) {
+            const Op& o = pl.ops[elig[k]];
+            const int j = g.p.n_ops++;
+            TcOp& t = g.p.ops[j];
+            t.kind = o.epi; t.act = o.act; t.M = o.M; t.N = o.N; t.K = o.K;
+            t.n_mma = rup(o.N, 16);
+            t.a_bytes = TC_A_BYTES;
+            t.m_tiles = (o.M + TC_BM - 1) / TC_BM;
+            t.splits = 1; t.k_per_split = rup(o.K, TC_BK);
+            t.bias = o.bias; t.bias_part = -1;
+            const float* A = e->arena + o.a;
+            const float* Bm = e->arena + o.b;
+            if (o.epi == EPI_FWD || o.epi == EPI_DACT) {
+              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.K, o.M, o.a_sm, TC_BK, TC_BM, false);
+              ok = ok && tc_encode(enc, &g.maps.c[j], e->arena + o.c, o.N, o.M, o.ldc, 32, TC_BM, false);
+              if (o.epi == EPI_FWD) {
+                t.b_rows = t.n_mma; t.b_bytes = t.n_mma * TC_BK * 4;
+                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.K, o.N, o.b_sn, TC_BK, t.n_mma, false);
+              } else {
+                t.b_mn = 1; t.b_rows = (t.n_mma + 31) / 32; t.b_bytes = t.b_rows * TC_SLAB; t.has_aux = 1;
+                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, true);
+                ok = ok && tc_encode(enc, &g.maps.aux[j], e->arena + o.aux, o.N, o.M, o.ld_aux, 32, TC_BM, false);
+              }
+            } else {
+              t.a_mn = t.b_mn = 1;
+              t.b_rows = (t.n_mma + 31) / 32; t.b_bytes = t.b_rows * TC_SLAB;
+              t.k_per_split = std::min(1024, std::max(256, rup((o.K + 63) / 64, TC_BK)));
+              t.splits = (o.K + t.k_per_split - 1) / t.k_per_split;
+              const int m_pad = t.m_tiles * TC_BM, n_ld = rup(o.N, 4);
+              TcRedOp& r = g.red.ops[g.red.n_ops++];
+              r.op = o; r.splits = t.splits; r.m_pad = m_pad; r.n_ld = n_ld;
+              r.part = (i64)so; so += (size_t)t.splits * m_pad * n_ld;
+              r.bias_part = (i64)so; so += (size_t)t.splits * m_pad * TC_SPLIT_WARPS;
+              t.bias_part = o.pb >= 0 ? r.bias_part : -1;
+              g.has_red = true;
+              g.red_blocks = std::max(g.red_blocks, std::min(1024, (o.M * (o.N / 4) + o.M + 255) / 256));
+              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.M, o.K, o.a_sk, 32, TC_BK, true);
+              ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, true);
+              if (pass == 1)
+                ok = ok && tc_encode(enc, &g.maps.c[j], e->d_tc_scratch + r.part, n_ld, (uint64_t)t.splits * m_pad, n_ld, 32, TC_BM, false);
+            }
+            t.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)t.a_mn << 15) | ((uint32_t)t.b_mn << 16) |
+                      ((uint32_t)(t.n_mma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            t.tile0 = tiles; t.ntiles = t.m_tiles * t.splits;
+            tiles += t.ntiles;
+          }
+          g.p.total_tiles = tiles;
+          g.grid = std::max(1, std::min(tiles, e->n_sms));
+        }
+        need = std::max(need, so);
+      }
+    }
+    if (!ok) return off("cuTensorMapEncodeTiled rejected an operand layout");
+    if (pass == 0) {
+      e->tc_scratch_floats = need + 64;
+      SACX_CUDA(cudaMalloc((void**)&e->d_tc_scratch, e->tc_scratch_floats * sizeof(float)));
+      SACX_CUDA(cudaMemset(e->d_tc_scratch, 0, e->tc_scratch_floats * sizeof(float)));
+    }
+  }
   return SACX_OK;
 }
 
@@ -451,6 +611,7 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   Engine& e = h->e;
   e.cfg = *cfg;
   if (e.cfg.dp_world <= 0) { e.cfg.dp_world = 1; e.cfg.dp_rank = 0; }
+  { const char* mb = getenv("SACX_TC_MIN_BATCH"); if (mb && atoi(mb) > 0) e.tc_min_batch = atoi(mb); }
   int dev = 0;
   SACX_CUDA(cudaGetDevice(&dev));
   SACX_CUDA(cudaDeviceGetAttribute(&e.n_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -497,6 +658,7 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
     SACX_CUDA(cudaMemset(e.arena, 0, total));
     e.own_arena = true;
   }
+  if ((rc = engine_setup_tc(&e))) { delete h; return rc; }
   SACX_CUDA(cudaMalloc((void**)&e.d_plans, sizeof(Plan) * N_PLANS));
   SACX_CUDA(cudaMemcpy(e.d_plans, e.h_plans.data(), sizeof(Plan) * N_PLANS, cudaMemcpyHostToDevice));
   SACX_CUDA(cudaMalloc((void**)&e.d_barrier, sizeof(unsigned) * 64 * 4096));
@@ -516,6 +678,7 @@ int sacx_agent_destroy(sacx_agent_t h) {
   if (e.d_plans) cudaFree(e.d_plans);
   if (e.d_prog) cudaFree(e.d_prog);
   if (e.d_rp_part) cudaFree(e.d_rp_part);
+  if (e.d_tc_scratch) cudaFree(e.d_tc_scratch);
   if (e.d_barrier) cudaFree(e.d_barrier);
   if (e.pinned_metrics) cudaFreeHost(e.pinned_metrics);
   if (e.pinned_io) cudaFreeHost(e.pinned_io);
@@ -562,6 +725,13 @@ int sacx_agent_path(sacx_agent_t h, char* reason, int32_t capacity) {
   if (!h) return fail(SACX_ERR_INVALID, "null agent");
   if (reason && capacity > 0) snprintf(reason, (size_t)capacity, "%s", h->e.rp ? "" : h->e.rp_why.c_str());
   return h->e.rp ? 1 : 0;
+}
+
+int sacx_agent_tc(sacx_agent_t h, char* reason, int32_t capacity, int64_t* tc_launches) {
+  if (!h) return fail(SACX_ERR_INVALID, "null agent");
+  if (reason && capacity > 0) snprintf(reason, (size_t)capacity, "%s", h->e.tc ? "" : h->e.tc_why.c_str());
+  if (tc_launches) *tc_launches = h->e.tc_launches;
+  return h->e.tc ? 1 : 0;
 }
 
 int sacx_agent_reset_state(sacx_agent_t h) {

@@ -11,6 +11,7 @@
 
 #include "sacx_kernels.cuh"
 #include "sacx_rowpar.cuh"
+#include "sacx_tc.cuh"
 
 namespace sacx {
 
@@ -89,6 +90,16 @@ struct Engine {
   float* d_rp_part = nullptr;
   int rp_grid = 0, rp_smem_bytes = 0;
   std::string rp_why;
+  // tensor-core path (sacx_tc.cuh): single agent at large batch; per plan phase the TC-eligible GEMM ops in groups of <= 4
+  struct TcGroup { TcParams p; TcMaps maps; int grid = 0; bool has_red = false; TcRedParams red; int red_blocks = 0; };
+  struct TcPhase { std::vector<TcGroup> groups; bool other_ops = false; };
+  bool tc = false;
+  int tc_min_batch = 4096;
+  std::string tc_why;
+  std::vector<std::vector<TcPhase>> tc_phases;       // [plan][phase]
+  float* d_tc_scratch = nullptr;
+  size_t tc_scratch_floats = 0;
+  long long tc_launches = 0;
 
   // ---------------------------------------------------------------- layout
   i64 alloc(const std::string& name, int rows, int cols, int ld = -1, int dtype = 0) {
@@ -699,6 +710,7 @@ struct Engine {
     if (env && atoi(env) == 0) { why = "disabled by SACX_ROWPAR=0"; return false; }
     if (cfg.n_agents != 1) { why = "population mode"; return false; }
     if (cfg.dp_world > 1) { why = "data-parallel mode"; return false; }
+    { std::string w; if (tc_wanted(w)) { why = "large batch runs the tensor-core path"; return false; } }
     if (pi.L() < 2 || q1.L() < 2) { why = "fewer than two hidden layers"; return false; }
     if (act_needs_z(pi.act_h) || act_needs_z(q1.act_h)) { why = "hidden activation needs saved pre-activations"; return false; }
     if (cfg.act_dim > RP_MAXA) { why = "action dimension above 8"; return false; }
@@ -926,6 +938,31 @@ struct Engine {
     rp = rowpar_eligible(rp_why);
     if (rp) { PB pb; rp = build_rowpar(pb); if (rp) h_plans[PLAN_RP] = pb.p; }
     return SACX_OK;
+  }
+
+  // ---- tensor-core path ------------------------------------------------------------------------------------------------
+  bool tc_op_eligible(const Op& o) const {
+    if (o.type != OP_GEMM || o.mode != 0 || o.i[4] != 0 || o.zout >= 0) return false;
+    auto al = [](i64 x) { return x >= 0 && (x & 3) == 0; };
+    if (o.N < 16 || o.N > TC_NMAX || (o.N & 3)) return false;
+    if (o.epi == EPI_FWD)
+      return o.M >= tc_min_batch && o.a_sk == 1 && o.b_sk == 1 && !(o.a_sm & 3) && !(o.b_sn & 3) && !(o.ldc & 3) && al(o.a) && al(o.b) &&
+             al(o.c) && al(o.bias) && o.K >= 4;
+    if (o.epi == EPI_DACT)
+      return o.M >= tc_min_batch && o.a_sk == 1 && o.b_sn == 1 && !(o.a_sm & 3) && !(o.b_sk & 3) && !(o.ldc & 3) && !(o.ld_aux & 3) &&
+             al(o.a) && al(o.b) && al(o.c) && al(o.aux) && !(o.K & 3);
+    if (o.epi == EPI_DW)
+      return o.K >= tc_min_batch && o.M >= 32 && !(o.M & 3) && o.a_sm == 1 && o.b_sn == 1 && !(o.a_sk & 3) && !(o.b_sk & 3) && al(o.a) &&
+             al(o.b) && al(o.p) && al(o.pm) && al(o.pv) && al(o.pg) && (o.pt < 0 || al(o.pt));
+    return false;
+  }
+  bool tc_wanted(std::string& why) const {
+    const char* env = getenv("SACX_TC");
+    if (env && atoi(env) == 0) { why = "disabled by SACX_TC=0"; return false; }
+    if (cfg.n_agents != 1) { why = "population mode"; return false; }
+    if (cfg.batch_size < tc_min_batch) { why = "batch below the tensor-core threshold"; return false; }
+    if (act_needs_z(pi.act_h) || act_needs_z(q1.act_h)) { why = "hidden activation needs saved pre-activations"; return false; }
+    return true;
   }
 
   int max_phase_tiles() const {

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
           const Op& op = ops[oi];
           const int lt = t - op.tile0;
           switch (op.type) {
-            case OP_GEMM: gemm_tile<C>(op, ec, lt, gsm); break;
+            case OP_GEMM: if (!(args.tc_skip && (op.cfg & 2))) gemm_tile<C>(op, ec, lt, gsm); break;
             case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
             case OP_PI_HEAD: tile_pi_head(op, rc, lt); __syncthreads(); break;
             case OP_Q_ROW: tile_q_row(op, rc, lt); __syncthreads(); break;

@@ -111,7 +111,8 @@ struct RunArgs {
   i64 scal_off;
   unsigned long long* dbg;   // optional [n_steps][n_phases][gridDim.x][2] clock64 at barrier arrive / release
   unsigned long long* dbg2;  // optional [n_steps][n_phases][gridDim.x][8] intra-tile timestamps of the CTA's last GEMM tile
-  int barrier_mode, pad_;
+  int barrier_mode;
+  int tc_skip;               // 1: GEMM ops marked for the tensor-core path (op.cfg & 2) are run by sacx_tc_kernel, skip them here
   float* rp_part;            // row-parallel kernel: partial-sum scratch [groups][part_stride]
   Hyper hp;
 };

@@ -95,6 +95,7 @@ SYMBOLS = {
     "sacx_agent_refresh_alpha": (C.c_int, [_P]),
     "sacx_agent_grid": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32)]),
     "sacx_agent_path": (C.c_int, [_P, C.c_char_p, _I32]),
+    "sacx_agent_tc": (C.c_int, [_P, C.c_char_p, _I32, C.POINTER(_I64)]),
     "sacx_update": (C.c_int, [_P, _P, _P, _P, _I32]),
     "sacx_update_host": (C.c_int, [_P, _P, _P, _P, _I32, C.POINTER(SacxMetrics)]),
     "sacx_update_staged": (C.c_int, [_P, _P, _P, _P, _I32]),

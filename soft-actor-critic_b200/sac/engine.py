@@ -110,6 +110,15 @@ class UpdateEngine:
             E.check(rc)
         return ("rowpar" if rc == 1 else "tiles"), buf.value.decode()
 
+    def tensor_core(self) -> Tuple[bool, str, int]:
+        """(enabled, reason when not, tensor-core kernel launches so far) -- include/sacx.h: sacx_agent_tc."""
+        buf = C.create_string_buffer(128)
+        n = C.c_int64(0)
+        rc = self.lib.sacx_agent_tc(self.h, buf, 128, C.byref(n))
+        if rc < 0:
+            E.check(rc)
+        return rc == 1, buf.value.decode(), int(n.value)
+
     def sync(self) -> None:
         E.check(self.lib.sacx_sync(self.h))
 

@@ -43,9 +43,9 @@ __device__ __forceinline__ uint64_t umma_desc(const void* smem_ptr) {
   return addr | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // MN-major operand staged as 32-wide (128 B) slabs of [BK rows (k) x 128 B]; lbo / sbo in bytes (probed from the host)
-__device__ __forceinline__ uint64_t umma_desc_mn(const void* smem_ptr, uint32_t lbo, uint32_t sbo) {
+__device__ __forceinline__ uint64_t umma_desc_mn(const void* smem_ptr, uint32_t lbo, uint32_t sbo, uint32_t lt) {
   const uint64_t addr = (smem_u32(smem_ptr) & 0x3FFFF) >> 4;
-  return addr | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  return addr | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | ((uint64_t)lt << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -57,7 +57,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 __global__ void __launch_bounds__(128, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ D, int M, int N, int K,
-               int mode, uint32_t lbo, uint32_t sbo, uint32_t kstep) {
+               int mode, uint32_t lbo, uint32_t sbo, uint32_t kstep, uint32_t lt) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[NS], empty[NS], acc_full;
   __shared__ uint32_t tmem_base_s;
@@ -103,8 +103,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < BK / UMMA_K; ++k)
       {
-        const uint64_t ad = mode >= 2 ? umma_desc_mn(a + k * kstep, lbo, sbo) : umma_desc(a + k * UMMA_K * 4);
-        const uint64_t bd = mode >= 1 ? umma_desc_mn(b + k * kstep, lbo, sbo) : umma_desc(b + k * UMMA_K * 4);
+        const uint64_t ad = mode >= 2 ? umma_desc_mn(a + k * kstep, lbo, sbo, lt) : umma_desc(a + k * UMMA_K * 4);
+        const uint64_t bd = mode >= 1 ? umma_desc_mn(b + k * kstep, lbo, sbo, lt) : umma_desc(b + k * UMMA_K * 4);
         umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0);
       }
       umma_commit(&empty[s]);          // smem slot is free once these MMAs have read it
@@ -138,13 +138,13 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool make_map(EncodeFn enc, CUtensorMap* map, float* base, int rows, int cols, int box_rows, int box_cols = BK) {
+static bool make_map(EncodeFn enc, CUtensorMap* map, float* base, int rows, int cols, int box_rows, int box_cols = BK, CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); return false; }
   return true;
 }
@@ -152,7 +152,9 @@ static bool make_map(EncodeFn enc, CUtensorMap* map, float* base, int rows, int 
 int main(int argc, char** argv) {
   const int M = argc > 1 ? atoi(argv[1]) : 8192, N = argc > 2 ? atoi(argv[2]) : 256, K = argc > 3 ? atoi(argv[3]) : 256;
   const int mode = argc > 4 ? atoi(argv[4]) : 0;
-  const uint32_t lbo = argc > 5 ? atoi(argv[5]) : 4096, sbo = argc > 6 ? atoi(argv[6]) : 1024, kstep = argc > 7 ? atoi(argv[7]) : 1024;
+  const uint32_t lbo = argc > 5 ? atoi(argv[5]) : 4096, sbo = argc > 6 ? atoi(argv[6]) : 512, kstep = argc > 7 ? atoi(argv[7]) : 1024;
+  const uint32_t lt = argc > 8 ? atoi(argv[8]) : 1;
+  const CUtensorMapSwizzle swmn = lt == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   if (M % BM || N % BN || K % BK) { printf("M, N, K must be multiples of %d, %d, %d\n", BM, BN, BK); return 1; }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -175,12 +177,12 @@ int main(int argc, char** argv) {
   cudaMemcpy(dB, (mode >= 1 ? tB : hB).data(), hB.size() * 4, cudaMemcpyHostToDevice);
   cudaMemset(dD, 0, (size_t)M * N * 4);
   CUtensorMap mapA, mapB;
-  if (!(mode >= 2 ? make_map(enc, &mapA, dA, K, M, BK, 32) : make_map(enc, &mapA, dA, M, K, BM))) return 1;
-  if (!(mode >= 1 ? make_map(enc, &mapB, dB, K, N, BK, 32) : make_map(enc, &mapB, dB, N, K, BN))) return 1;
+  if (!(mode >= 2 ? make_map(enc, &mapA, dA, K, M, BK, 32, swmn) : make_map(enc, &mapA, dA, M, K, BM))) return 1;
+  if (!(mode >= 1 ? make_map(enc, &mapB, dB, K, N, BK, 32, swmn) : make_map(enc, &mapB, dB, N, K, BN))) return 1;
   const int smem = NS * STAGE + 1024;
   cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   dim3 grid(M / BM, N / BN);
-  tc_gemm_kernel<<<grid, 128, smem>>>(mapA, mapB, dD, M, N, K, mode, lbo, sbo, kstep);
+  tc_gemm_kernel<<<grid, 128, smem>>>(mapA, mapB, dD, M, N, K, mode, lbo, sbo, kstep, lt);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
   std::vector<float> hD((size_t)M * N);
@@ -196,15 +198,15 @@ int main(int argc, char** argv) {
       max_rel = fmax(max_rel, fabs(d));
     }
   }
-  printf("mode %d lbo %u sbo %u kstep %u | ", mode, lbo, sbo, kstep);
+  printf("mode %d lbo %u sbo %u kstep %u lt %u | ", mode, lbo, sbo, kstep, lt);
   printf("tcgen05 tf32 GEMM %dx%dx%d: rel-L2 error vs fp64 = %.3e (tf32 inputs: ~5e-4 expected), max abs err %.3e\n", M, N, K,
          sqrt(err_norm / ref_norm), max_rel);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int i = 0; i < 5; ++i) tc_gemm_kernel<<<grid, 128, smem>>>(mapA, mapB, dD, M, N, K, mode, lbo, sbo, kstep);
+  for (int i = 0; i < 5; ++i) tc_gemm_kernel<<<grid, 128, smem>>>(mapA, mapB, dD, M, N, K, mode, lbo, sbo, kstep, lt);
   cudaEventRecord(e0);
   const int reps = 50;
-  for (int i = 0; i < reps; ++i) tc_gemm_kernel<<<grid, 128, smem>>>(mapA, mapB, dD, M, N, K, mode, lbo, sbo, kstep);
+  for (int i = 0; i < reps; ++i) tc_gemm_kernel<<<grid, 128, smem>>>(mapA, mapB, dD, M, N, K, mode, lbo, sbo, kstep, lt);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms;
