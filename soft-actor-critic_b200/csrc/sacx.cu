@@ -131,8 +131,8 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
     return SACX_OK;
   };
   if (e->tc && !per_phase) {
-    bool any = false;
-    for (int p = pb; p < pe; ++p) any = any || !e->tc_phases[plan_id][p].groups.empty();
+    bool any = false;      // something to gain: a tensor-core GEMM, or a GEMM-free phase for the light row kernel
+    for (int p = pb; p < pe; ++p) any = any || !e->tc_phases[plan_id][p].groups.empty() || e->tc_phases[plan_id][p].light;
     if (any) {
       // tensor-core plan walk: runs of phases without TC ops go through the persistent kernel (cooperative when the run
       // has more than one phase); a phase with TC ops launches the tcgen05 kernel per group of <= 4 GEMMs (+ the dW
@@ -142,12 +142,21 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
         if (proto.idx_ext) a.idx_ext = proto.idx_ext + s * nb;
         if (proto.eps1_ext) a.eps1_ext = proto.eps1_ext + s * nb * e->cfg.act_dim;
         if (proto.eps2_ext) a.eps2_ext = proto.eps2_ext + s * nb * e->cfg.act_dim;
+        auto launch_rows = [&](int p) -> int {
+          a.phase_begin = p; a.phase_end = p + 1; a.n_steps = 1; a.tc_skip = 1;
+          const int tiles = std::max(1, hp.phases[p].ntiles);
+          sacx_rows_kernel<<<dim3(std::min(tiles, e->n_sms * e->rows_ctas_per_sm), 1), 256, e->rows_smem_bytes, e->stream>>>(
+              dplan, a, e->rows_tsm_floats);
+          ++e->launches;
+          return SACX_OK;
+        };
         int p = pb;
         while (p < pe) {
           Engine::TcPhase& tp = e->tc_phases[plan_id][p];
           if (tp.groups.empty()) {
+            if (tp.light) { launch_rows(p); ++p; continue; }
             int q = p + 1;
-            while (q < pe && e->tc_phases[plan_id][q].groups.empty()) ++q;
+            while (q < pe && e->tc_phases[plan_id][q].groups.empty() && !e->tc_phases[plan_id][q].light) ++q;
             a.tc_skip = 0;
             int rc = launch(p, q, 1, dim3(e->grid_x, e->grid_y), e->grid_x > 1 && q - p > 1);
             if (rc) return rc;
@@ -155,10 +164,13 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
             continue;
           }
           if (tp.other_ops) {
-            a.tc_skip = 1;
-            int rc = launch(p, p + 1, 1, dim3(e->grid_x, e->grid_y), false);
-            if (rc) return rc;
-            a.tc_skip = 0;
+            if (tp.light) launch_rows(p);
+            else {
+              a.tc_skip = 1;
+              int rc = launch(p, p + 1, 1, dim3(e->grid_x, e->grid_y), false);
+              if (rc) return rc;
+              a.tc_skip = 0;
+            }
           }
           for (Engine::TcGroup& g : tp.groups) {
             sacx_tc_kernel<<<g.grid, TC_THREADS, TC_SMEM_BYTES, e->stream>>>(g.p, g.maps);
@@ -280,6 +292,18 @@ static int engine_setup_tc(Engine* e) {
   if (cudaFuncSetAttribute(sacx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
     return off("cannot raise the dynamic shared memory limit of the tensor-core kernel");
   auto rup = [](int x, int m) { return (x + m - 1) / m * m; };
+  {  // light row kernel: staging area for the widest head (falls back to global reads beyond 48 KB)
+    const int A = e->cfg.act_dim, Kp = e->pi.dims[e->pi.L()], Kq = e->q1.dims[e->q1.L()], H0 = e->q1.dims[1];
+    int need = std::max(std::max(2 * A * Kp + 2 * A, 4 * Kq), 2 * A * H0 + 2 * A * Kp);
+    e->rows_tsm_floats = std::min(rup(need, 4), 12288);
+    e->rows_smem_bytes = (WSM_FLOATS + e->rows_tsm_floats) * 4;
+    if (cudaFuncSetAttribute(sacx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->rows_smem_bytes) != cudaSuccess)
+      return off("cannot size the row kernel's shared memory");
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sacx_rows_kernel, 256, (size_t)e->rows_smem_bytes) != cudaSuccess || per_sm < 1)
+      return off("row kernel does not fit on an SM");
+    e->rows_ctas_per_sm = per_sm;
+  }
   // pass 0 sizes the scratch (dW partial tiles), pass 1 builds descriptors against the allocated scratch
   for (int pass = 0; pass < 2; ++pass) {
     size_t need = 0;
@@ -294,7 +318,11 @@ static int engine_setup_tc(Engine* e) {
         std::vector<int> elig;
         for (int i = pl.phases[ph].op0; i < pl.phases[ph].op0 + pl.phases[ph].nops; ++i) {
           if (e->tc_op_eligible(pl.ops[i])) { elig.push_back(i); pl.ops[i].cfg |= 2; }
-          else tp.other_ops = true;
+          else {
+            tp.other_ops = true;
+            const int ty = pl.ops[i].type;
+            if (ty == OP_GEMM || ty == OP_DW_HEAD || ty == OP_LOAD_EXT || ty == OP_NONE) tp.light = false;
+          }
         }
         size_t so = 0;                       // scratch offset inside this phase (floats)
         for (size_t g0 = 0; g0 < elig.size(); g0 += TC_MAX_OPS) {

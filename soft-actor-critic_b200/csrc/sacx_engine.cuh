@@ -92,7 +92,7 @@ struct Engine {
   std::string rp_why;
   // tensor-core path (sacx_tc.cuh): single agent at large batch; per plan phase the TC-eligible GEMM ops in groups of <= 4
   struct TcGroup { TcParams p; TcMaps maps; int grid = 0; bool has_red = false; TcRedParams red; int red_blocks = 0; };
-  struct TcPhase { std::vector<TcGroup> groups; bool other_ops = false; };
+  struct TcPhase { std::vector<TcGroup> groups; bool other_ops = false; bool light = true; };   // light: no FFMA GEMM tile left in the phase
   bool tc = false;
   int tc_min_batch = 4096;
   std::string tc_why;
@@ -100,6 +100,7 @@ struct Engine {
   float* d_tc_scratch = nullptr;
   size_t tc_scratch_floats = 0;
   long long tc_launches = 0;
+  int rows_tsm_floats = 0, rows_smem_bytes = 0, rows_ctas_per_sm = 1;
 
   // ---------------------------------------------------------------- layout
   i64 alloc(const std::string& name, int rows, int cols, int ld = -1, int dtype = 0) {
@@ -952,7 +953,7 @@ struct Engine {
       return o.M >= tc_min_batch && o.a_sk == 1 && o.b_sn == 1 && !(o.a_sm & 3) && !(o.b_sk & 3) && !(o.ldc & 3) && !(o.ld_aux & 3) &&
              al(o.a) && al(o.b) && al(o.c) && al(o.aux) && !(o.K & 3);
     if (o.epi == EPI_DW)
-      return o.K >= tc_min_batch && o.M >= 32 && !(o.M & 3) && o.a_sm == 1 && o.b_sn == 1 && !(o.a_sk & 3) && !(o.b_sk & 3) && al(o.a) &&
+      return o.K >= tc_min_batch && o.M >= 1 && o.a_sm == 1 && o.b_sn == 1 && !(o.a_sk & 3) && !(o.b_sk & 3) && al(o.a) &&
              al(o.b) && al(o.p) && al(o.pm) && al(o.pv) && al(o.pg) && (o.pt < 0 || al(o.pt));
     return false;
   }

@@ -88,10 +88,10 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
           switch (op.type) {
             case OP_GEMM: if (!(args.tc_skip && (op.cfg & 2))) gemm_tile<C>(op, ec, lt, gsm); break;
             case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
-            case OP_PI_HEAD: tile_pi_head(op, rc, lt); __syncthreads(); break;
-            case OP_Q_ROW: tile_q_row(op, rc, lt); __syncthreads(); break;
-            case OP_ACTOR_Q: tile_actor_q(op, rc, lt); __syncthreads(); break;
-            case OP_ACTOR_BWD: tile_actor_bwd(op, rc, lt); __syncthreads(); break;
+            case OP_PI_HEAD: tile_pi_head<0>(op, rc, lt); __syncthreads(); break;
+            case OP_Q_ROW: tile_q_row<0>(op, rc, lt); __syncthreads(); break;
+            case OP_ACTOR_Q: tile_actor_q<0>(op, rc, lt); __syncthreads(); break;
+            case OP_ACTOR_BWD: tile_actor_bwd<0>(op, rc, lt); __syncthreads(); break;
             case OP_PROLOGUE: if (tid == 0) op_prologue(op, rc); break;
             case OP_FINAL: if (warp == 0) op_final(op, rc, lane); break;
             case OP_DW_HEAD: tile_dw_head(op, fcx, lt, gsm); break;
@@ -108,6 +108,53 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
         }
         if (!very_last) group_barrier(counter, epoch, args.barrier_mode);
         if (dbg) dbg[1] = clock64();
+      }
+    }
+  }
+}
+
+// Light kernel for the phases of a large-batch plan that hold no FFMA GEMM tile (row ops, gather, flat optimiser ops): the
+// persistent kernel above needs 255 registers and ~200 KB of shared memory, i.e. one CTA (8 rows in flight) per SM; at
+// batch 65536 the row phases are then bound by the latency of a tile's dependent loads. Same tile functions (their
+// own copy, V = 1), 3 CTAs per SM. One phase per launch, single agent or blockIdx.y = agent.
+constexpr int ROWS_SMEM_OPS = 8;
+__global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restrict__ gplan, const RunArgs args, int tsm_floats) {
+  extern __shared__ __align__(16) float rows_raw[];
+  __shared__ Op sops[ROWS_SMEM_OPS];
+  __shared__ float fred[8];
+  float* wsm = rows_raw;
+  float* tsm = rows_raw + WSM_FLOATS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Phase ph = gplan->phases[args.phase_begin];
+  const bool cached = ph.nops <= ROWS_SMEM_OPS;
+  if (cached) {
+    const int words = ph.nops * (int)(sizeof(Op) / 4);
+    const int* src = reinterpret_cast<const int*>(gplan->ops + ph.op0);
+    int* dst = reinterpret_cast<int*>(sops);
+    for (int i = tid; i < words; i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  const Op* ops = cached ? (sops - ph.op0) : gplan->ops;
+  for (int agent = blockIdx.y; agent < args.n_agents; agent += gridDim.y) {
+    float* base = args.arena + (i64)agent * args.agent_stride;
+    AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
+    RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, tsm, tsm_floats, nullptr};
+    for (int t = blockIdx.x; t < ph.ntiles; t += gridDim.x) {
+      int oi = ph.op0;
+      while (oi + 1 < ph.op0 + ph.nops && t >= ops[oi + 1].tile0) ++oi;
+      const Op& op = ops[oi];
+      const int lt = t - op.tile0;
+      switch (op.type) {
+        case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
+        case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); __syncthreads(); break;
+        case OP_Q_ROW: tile_q_row<1>(op, rc, lt); __syncthreads(); break;
+        case OP_ACTOR_Q: tile_actor_q<1>(op, rc, lt); __syncthreads(); break;
+        case OP_ACTOR_BWD: tile_actor_bwd<1>(op, rc, lt); __syncthreads(); break;
+        case OP_PROLOGUE: if (tid == 0) op_prologue(op, rc); break;
+        case OP_FINAL: op_final_impl<true>(op, rc, tid, fred); break;      // all 256 threads: B terms per mean
+        case OP_POLYAK: op_polyak(op, rc, lt); break;
+        case OP_ADAM_FLAT: op_adam_flat(op, rc, lt); break;
+        default: break;        // GEMM ops of this phase run on the tensor-core kernel
       }
     }
   }

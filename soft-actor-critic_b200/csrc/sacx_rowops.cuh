@@ -125,6 +125,7 @@ __device__ __forceinline__ void op_gather(const Op& op, const RowCtx& c, int row
 // ---------------------------------------------------------------- OP_PI_HEAD
 // o[0]=h(last hidden) o[1]=W_L o[2]=b_L o[3]=X(dest, action at col obs+j) o[4]=lp o[5]=eps buf
 // o[6]=tz o[7]=se o[8]=mask o[9]=headz (each -1 when not saved)   i[0]=ldh i[1]=K i[2]=ldx   mode: 1 target / 2 actor
+template <int V>
 __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int tile) {
   SACX_RSTAMP(0);
   const RunArgs& a = *c.args;
@@ -204,6 +205,7 @@ __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int til
 // target: o[0..1]=hqt(last hidden) o[2..3]=Wt_L o[4..5]=bt_L o[6]=r o[7]=d o[8]=lp2 o[9]=y o[10..11]=tq
 // critic: o[12..13]=hq(last hidden) o[14..15]=aux(z or h) o[16..17]=W_L o[18..19]=b_L o[20..21]=q out o[22..23]=dout
 //         o[24..25]=delta(last hidden) o[26..27]=lossrow          i[0]=ldh i[1]=K      (y read from o[9] or y_ext)
+template <int V>
 __device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile) {
   SACX_RSTAMP(0);
   const Hyper& hp = c.args->hp;
@@ -307,6 +309,7 @@ __device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile)
 
 // ---------------------------------------------------------------- OP_ACTOR_Q
 // o[0..1]=hq(last hidden) o[2..3]=aux o[4..5]=W_L o[6..7]=b_L o[8]=lp o[9..10]=q out o[13..14]=delta o[15]=plossrow
+template <int V>
 __device__ __noinline__ void tile_actor_q(const Op& op, const RowCtx& c, int tile) {
   SACX_RSTAMP(0);
   const Hyper& hp = c.args->hp;
@@ -384,6 +387,7 @@ __device__ __noinline__ void tile_actor_q(const Op& op, const RowCtx& c, int til
 // o[0..1]=delta0 of critics [B,H0q] o[2..3]=W_0 of critics [H0q, obs+act]
 // o[4]=tz o[5]=se o[6]=mask o[7]=headz o[8]=dhead out o[9]=Wpi_L o[11]=aux pi(last hidden) o[12]=delta pi(last hidden)
 // i[0]=ld delta0  i[1]=H0q  i[2]=ldW0 (=obs+act)  i[3]=ld pi hidden  i[4]=Kpi
+template <int V>
 __device__ __noinline__ void tile_actor_bwd(const Op& op, const RowCtx& c, int tile) {
   SACX_RSTAMP(0);
   const Hyper& hp = c.args->hp;
@@ -506,19 +510,39 @@ __device__ __forceinline__ void op_prologue(const Op& op, const RowCtx& c) {
   }
 }
 
-// ---------------------------------------------------------------- OP_FINAL (one warp)
+// ---------------------------------------------------------------- OP_FINAL (one warp; CTA = true: the whole CTA, large batch)
 // mode bits: 1 critic loss means, 2 policy loss mean, 4 temperature step, 8 count the update, 16/32 see below
 // o[0..1]=lossrow o[2]=plossrow o[3]=lp o[4..5]=q o[6]=y
-__device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane) {
+// sum over the callers (a warp, or all 256 threads through `red`), same value in every thread
+template <bool CTA>
+__device__ __forceinline__ float final_sum(float v, float* red) {
+  v = warp_sum(v);
+  if (!CTA) return v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+template <bool CTA>
+__device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int lane, float* red) {
   const Hyper& hp = c.args->hp;
   float* base = c.base;
   AgentScalars* s = c.scal;
   const int B = hp.B;
   const float invB = 1.f / (float)hp.B_global;
+  constexpr int NT = CTA ? 256 : 32;
   auto mean_of = [&](const float* p) {
-    float acc = 0.f;
-    for (int b = lane; b < B; b += 32) acc += __ldcg(p + b);
-    return warp_sum(acc) * invB;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int b = lane;
+    for (; b + 3 * NT < B; b += 4 * NT) {        // four independent loads in flight per thread
+      acc[0] += __ldcg(p + b); acc[1] += __ldcg(p + b + NT); acc[2] += __ldcg(p + b + 2 * NT); acc[3] += __ldcg(p + b + 3 * NT);
+    }
+    for (; b < B; b += NT) acc[0] += __ldcg(p + b);
+    return final_sum<CTA>((acc[0] + acc[1]) + (acc[2] + acc[3]), red) * invB;
   };
   if (op.mode & 1) {
     const float l1 = mean_of(base + op.o[0]), l2 = mean_of(base + op.o[1]);
@@ -536,14 +560,15 @@ __device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane
     const float* lp = c.args->lp_ext ? c.args->lp_ext : base + op.o[3];
     float acc = 0.f, accl = 0.f;
     const float la32 = (float)s->log_alpha;
-    for (int b = lane; b < B; b += 32) {
+    for (int b = lane; b < B; b += NT) {
       const float t = __ldcg(lp + b) + hp.target_entropy;
       acc += t;
       accl += la32 * t;
     }
-    const float mean_t = warp_sum(acc) * invB;           // f32 mean, as in the reference
-    const float mean_lt = warp_sum(accl) * invB;
+    const float mean_t = final_sum<CTA>(acc, red) * invB;           // f32 mean, as in the reference
+    const float mean_lt = final_sum<CTA>(accl, red) * invB;
     if (lane == 0) { s->dp_mean_t = mean_t; s->dp_mean_lt = mean_lt; }
+    if (CTA) __syncthreads();
   }
   if ((op.mode & (4 | 32)) && lane == 0) {
     const float mean_t = s->dp_mean_t, mean_lt = s->dp_mean_lt;
@@ -567,6 +592,7 @@ __device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane
   }
   if ((op.mode & 8) && lane == 0) s->updates += 1;
 }
+__device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane) { op_final_impl<false>(op, c, lane, nullptr); }
 
 // ---------------------------------------------------------------- OP_POLYAK / OP_ADAM_FLAT (elementwise tiles)
 constexpr int FLAT_TILE = 256 * 8;
