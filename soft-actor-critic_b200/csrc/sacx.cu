@@ -145,7 +145,7 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
         auto launch_rows = [&](int p) -> int {
           a.phase_begin = p; a.phase_end = p + 1; a.n_steps = 1; a.tc_skip = 1;
           const int tiles = std::max(1, hp.phases[p].ntiles);
-          sacx_rows_kernel<<<dim3(std::min(tiles, e->n_sms * e->rows_ctas_per_sm), 1), 256, e->rows_smem_bytes, e->stream>>>(
+          sacx_rows_kernel<<<dim3(std::min(tiles, e->n_sms * e->rows_ctas_per_sm), std::min(e->cfg.n_agents, 65535)), 256, e->rows_smem_bytes, e->stream>>>(
               dplan, a, e->rows_tsm_floats);
           ++e->launches;
           return SACX_OK;
@@ -176,7 +176,7 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
             sacx_tc_kernel<<<g.grid, TC_THREADS, TC_SMEM_BYTES, e->stream>>>(g.p, g.maps);
             ++e->launches; ++e->tc_launches;
             if (g.has_red) {
-              tc_dw_reduce_kernel<<<dim3(g.red_blocks, g.red.n_ops), 256, 0, e->stream>>>(g.red);
+              tc_dw_reduce_kernel<<<dim3(g.red_blocks, g.red.n_ops, e->cfg.n_agents), 256, 0, e->stream>>>(g.red);
               ++e->launches;
             }
           }
@@ -269,13 +269,14 @@ typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D fp32 tensor [outer][inner] with row stride ld (floats); out-of-range box elements read as zero / are not written
+// (the third dimension is the agent: slices `agent_stride` floats apart)
 static bool tc_encode(TcEncodeFn enc, CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                      uint32_t box_in, uint32_t box_out, bool atom32) {
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 4};
-  cuuint32_t box[2] = {box_in, box_out};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      uint32_t box_in, uint32_t box_out, bool atom32, uint64_t n_agents, uint64_t agent_stride) {
+  cuuint64_t dims[3] = {inner, outer, n_agents};
+  cuuint64_t strides[2] = {ld * 4, std::max<uint64_t>(agent_stride, 4) * 4};
+  cuuint32_t box[3] = {box_in, box_out, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -292,6 +293,8 @@ static int engine_setup_tc(Engine* e) {
   if (cudaFuncSetAttribute(sacx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
     return off("cannot raise the dynamic shared memory limit of the tensor-core kernel");
   auto rup = [](int x, int m) { return (x + m - 1) / m * m; };
+  const uint64_t NA = (uint64_t)e->cfg.n_agents, AS = (uint64_t)e->stride;
+  uint64_t sstride = 4;                  // scratch floats per agent (known after pass 0)
   {  // light row kernel: staging area for the widest head (falls back to global reads beyond 48 KB)
     const int A = e->cfg.act_dim, Kp = e->pi.dims[e->pi.L()], Kq = e->q1.dims[e->q1.L()], H0 = e->q1.dims[1];
     int need = std::max(std::max(2 * A * Kp + 2 * A, 4 * Kq), 2 * A * H0 + 2 * A * Kp);
@@ -330,7 +333,9 @@ static int engine_setup_tc(Engine* e) {
           Engine::TcGroup& g = tp.groups.back();
           memset(&g.p, 0, sizeof g.p); memset(&g.maps, 0, sizeof g.maps); memset(&g.red, 0, sizeof g.red);
           g.p.arena = e->arena; g.p.scratch = e->d_tc_scratch;
+          g.p.n_agents = (int)NA; g.p.agent_stride = (i64)AS; g.p.scratch_stride = (i64)sstride;
           g.red.arena = e->arena; g.red.scratch = e->d_tc_scratch; g.red.scal_off = e->scal_off; g.red.hp = e->hp;
+          g.red.agent_stride = (i64)AS; g.red.scratch_stride = (i64)sstride;
           int tiles = 0;
           for (size_t k = g0; k < std::min(elig.size(), g0 + TC_MAX_OPS); ++k) {
             const Op& o = pl.ops[elig[k]];
@@ -345,15 +350,15 @@ static int engine_setup_tc(Engine* e) {
             const float* A = e->arena + o.a;
             const float* Bm = e->arena + o.b;
             if (o.epi == EPI_FWD || o.epi == EPI_DACT) {
-              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.K, o.M, o.a_sm, TC_BK, TC_BM, false);
-              ok = ok && tc_encode(enc, &g.maps.c[j], e->arena + o.c, o.N, o.M, o.ldc, 32, TC_BM, false);
+              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.K, o.M, o.a_sm, TC_BK, TC_BM, false, NA, AS);
+              ok = ok && tc_encode(enc, &g.maps.c[j], e->arena + o.c, o.N, o.M, o.ldc, 32, TC_BM, false, NA, AS);
               if (o.epi == EPI_FWD) {
                 t.b_rows = t.n_mma; t.b_bytes = t.n_mma * TC_BK * 4;
-                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.K, o.N, o.b_sn, TC_BK, t.n_mma, false);
+                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.K, o.N, o.b_sn, TC_BK, t.n_mma, false, NA, AS);
               } else {
                 t.b_mn = 1; t.b_rows = (t.n_mma + 31) / 32; t.b_bytes = t.b_rows * TC_SLAB; t.has_aux = 1;
-                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, true);
-                ok = ok && tc_encode(enc, &g.maps.aux[j], e->arena + o.aux, o.N, o.M, o.ld_aux, 32, TC_BM, false);
+                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, true, NA, AS);
+                ok = ok && tc_encode(enc, &g.maps.aux[j], e->arena + o.aux, o.N, o.M, o.ld_aux, 32, TC_BM, false, NA, AS);
               }
             } else {
               t.a_mn = t.b_mn = 1;
@@ -368,25 +373,27 @@ static int engine_setup_tc(Engine* e) {
               t.bias_part = o.pb >= 0 ? r.bias_part : -1;
               g.has_red = true;
               g.red_blocks = std::max(g.red_blocks, std::min(1024, (o.M * (o.N / 4) + o.M + 255) / 256));
-              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.M, o.K, o.a_sk, 32, TC_BK, true);
-              ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, true);
+              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.M, o.K, o.a_sk, 32, TC_BK, true, NA, AS);
+              ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, true, NA, AS);
               if (pass == 1)
-                ok = ok && tc_encode(enc, &g.maps.c[j], e->d_tc_scratch + r.part, n_ld, (uint64_t)t.splits * m_pad, n_ld, 32, TC_BM, false);
+                ok = ok && tc_encode(enc, &g.maps.c[j], e->d_tc_scratch + r.part, n_ld, (uint64_t)t.splits * m_pad, n_ld, 32, TC_BM, false, NA, sstride);
             }
             t.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)t.a_mn << 15) | ((uint32_t)t.b_mn << 16) |
                       ((uint32_t)(t.n_mma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             t.tile0 = tiles; t.ntiles = t.m_tiles * t.splits;
             tiles += t.ntiles;
           }
-          g.p.total_tiles = tiles;
-          g.grid = std::max(1, std::min(tiles, e->n_sms));
+          g.p.tiles_per_agent = tiles;
+          g.p.total_tiles = tiles * (int)NA;
+          g.grid = std::max(1, std::min(g.p.total_tiles, e->n_sms));
         }
         need = std::max(need, so);
       }
     }
     if (!ok) return off("cuTensorMapEncodeTiled rejected an operand layout");
     if (pass == 0) {
-      e->tc_scratch_floats = need + 64;
+      sstride = (uint64_t)((need + 63) / 64 * 64 + 64);
+      e->tc_scratch_floats = (size_t)sstride * NA;
       SACX_CUDA(cudaMalloc((void**)&e->d_tc_scratch, e->tc_scratch_floats * sizeof(float)));
       SACX_CUDA(cudaMemset(e->d_tc_scratch, 0, e->tc_scratch_floats * sizeof(float)));
     }
@@ -640,6 +647,7 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   e.cfg = *cfg;
   if (e.cfg.dp_world <= 0) { e.cfg.dp_world = 1; e.cfg.dp_rank = 0; }
   { const char* mb = getenv("SACX_TC_MIN_BATCH"); if (mb && atoi(mb) > 0) e.tc_min_batch = atoi(mb); }
+  e.tc_min_m = e.cfg.n_agents > 1 ? 128 : e.tc_min_batch;
   int dev = 0;
   SACX_CUDA(cudaGetDevice(&dev));
   SACX_CUDA(cudaDeviceGetAttribute(&e.n_sms, cudaDevAttrMultiProcessorCount, dev));

@@ -94,7 +94,8 @@ struct Engine {
   struct TcGroup { TcParams p; TcMaps maps; int grid = 0; bool has_red = false; TcRedParams red; int red_blocks = 0; };
   struct TcPhase { std::vector<TcGroup> groups; bool other_ops = false; bool light = true; };   // light: no FFMA GEMM tile left in the phase
   bool tc = false;
-  int tc_min_batch = 4096;
+  int tc_min_batch = 4096;         // single agent: smallest batch that takes the tensor-core path
+  int tc_min_m = 4096;             // smallest GEMM row count per agent (population: 128, one row tile)
   std::string tc_why;
   std::vector<std::vector<TcPhase>> tc_phases;       // [plan][phase]
   float* d_tc_scratch = nullptr;
@@ -947,21 +948,27 @@ struct Engine {
     auto al = [](i64 x) { return x >= 0 && (x & 3) == 0; };
     if (o.N < 16 || o.N > TC_NMAX || (o.N & 3)) return false;
     if (o.epi == EPI_FWD)
-      return o.M >= tc_min_batch && o.a_sk == 1 && o.b_sk == 1 && !(o.a_sm & 3) && !(o.b_sn & 3) && !(o.ldc & 3) && al(o.a) && al(o.b) &&
+      return o.M >= tc_min_m && o.a_sk == 1 && o.b_sk == 1 && !(o.a_sm & 3) && !(o.b_sn & 3) && !(o.ldc & 3) && al(o.a) && al(o.b) &&
              al(o.c) && al(o.bias) && o.K >= 4;
     if (o.epi == EPI_DACT)
-      return o.M >= tc_min_batch && o.a_sk == 1 && o.b_sn == 1 && !(o.a_sm & 3) && !(o.b_sk & 3) && !(o.ldc & 3) && !(o.ld_aux & 3) &&
+      return o.M >= tc_min_m && o.a_sk == 1 && o.b_sn == 1 && !(o.a_sm & 3) && !(o.b_sk & 3) && !(o.ldc & 3) && !(o.ld_aux & 3) &&
              al(o.a) && al(o.b) && al(o.c) && al(o.aux) && !(o.K & 3);
     if (o.epi == EPI_DW)
-      return o.K >= tc_min_batch && o.M >= 1 && o.a_sm == 1 && o.b_sn == 1 && !(o.a_sk & 3) && !(o.b_sk & 3) && al(o.a) &&
+      return o.K >= tc_min_m && o.M >= 1 && o.a_sm == 1 && o.b_sn == 1 && !(o.a_sk & 3) && !(o.b_sk & 3) && al(o.a) &&
              al(o.b) && al(o.p) && al(o.pm) && al(o.pv) && al(o.pg) && (o.pt < 0 || al(o.pt));
     return false;
   }
   bool tc_wanted(std::string& why) const {
     const char* env = getenv("SACX_TC");
     if (env && atoi(env) == 0) { why = "disabled by SACX_TC=0"; return false; }
-    if (cfg.n_agents != 1) { why = "population mode"; return false; }
-    if (cfg.batch_size < tc_min_batch) { why = "batch below the tensor-core threshold"; return false; }
+    if (cfg.n_agents == 1 && cfg.batch_size < tc_min_batch) { why = "batch below the tensor-core threshold"; return false; }
+    if (cfg.n_agents > 1) {      // population: every agent contributes >= one 128-row tile; enough agents to fill the chip
+      const char* pe = getenv("SACX_TC_POP");
+      if (pe && atoi(pe) == 0) { why = "disabled by SACX_TC_POP=0"; return false; }
+      if (cfg.batch_size < 128 || (long long)cfg.n_agents * cfg.batch_size < 4LL * tc_min_batch) {
+        why = "population too small for the tensor-core path"; return false;
+      }
+    }
     if (act_needs_z(pi.act_h) || act_needs_z(q1.act_h)) { why = "hidden activation needs saved pre-activations"; return false; }
     return true;
   }

@@ -56,7 +56,9 @@ struct TcOp {
 };
 
 struct TcParams {
-  int n_ops, total_tiles;
+  int n_ops, total_tiles;          // total_tiles = n_agents * tiles_per_agent (agent-major)
+  int n_agents, tiles_per_agent;
+  i64 agent_stride, scratch_stride;   // floats between two agents' arenas / scratch blocks
   float* arena;
   float* scratch;
   TcOp ops[TC_MAX_OPS];
@@ -84,13 +86,14 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* b, uint32_t parity) {
                  : "=r"(done) : "r"(tc_smem(b)), "r"(parity) : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void tc_tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(tc_smem(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem(bar)), "r"(c0), "r"(c1) : "memory");
+// every tensor map is 3-D: (inner, rows, agent); a single agent is the degenerate case with one slice
+__device__ __forceinline__ void tc_tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(tc_smem(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tc_tma_store(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem(src)), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void tc_tma_store(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -128,10 +131,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// tile -> (op, m tile, split)
-struct TcTile { int op, mt, split, m0, k0, nkb; };
+// tile -> (agent, op, m tile, split)
+struct TcTile { int agent, op, mt, split, m0, k0, nkb; };
 __device__ __forceinline__ TcTile tc_decode(const TcParams& P, int tile) {
   TcTile t;
+  t.agent = tile / P.tiles_per_agent;
+  tile -= t.agent * P.tiles_per_agent;
   t.op = 0;
 #pragma unroll
   for (int i = 1; i < TC_MAX_OPS; ++i)
@@ -186,12 +191,12 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           tc_mbar_expect_tx(&full[s], (uint32_t)(o.a_bytes + o.b_bytes));
           uint8_t* st = smem + s * TC_STAGE_BYTES;
           const int k = t.k0 + kb * TC_BK;
-          if (!o.a_mn) tc_tma_load(st, ma, &full[s], k, t.m0);
+          if (!o.a_mn) tc_tma_load(st, ma, &full[s], k, t.m0, t.agent);
           else
-            for (int j = 0; j < TC_BM / 32; ++j) tc_tma_load(st + j * TC_SLAB, ma, &full[s], t.m0 + 32 * j, k);
-          if (!o.b_mn) tc_tma_load(st + TC_A_BYTES, mb, &full[s], k, 0);
+            for (int j = 0; j < TC_BM / 32; ++j) tc_tma_load(st + j * TC_SLAB, ma, &full[s], t.m0 + 32 * j, k, t.agent);
+          if (!o.b_mn) tc_tma_load(st + TC_A_BYTES, mb, &full[s], k, 0, t.agent);
           else
-            for (int j = 0; j < o.b_rows; ++j) tc_tma_load(st + TC_A_BYTES + j * TC_SLAB, mb, &full[s], 32 * j, k);
+            for (int j = 0; j < o.b_rows; ++j) tc_tma_load(st + TC_A_BYTES + j * TC_SLAB, mb, &full[s], 32 * j, k, t.agent);
         }
       }
     }
@@ -281,7 +286,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         }
         // per-warp shares go straight to the scratch ([row block][warp][128]); tc_dw_reduce_kernel sums them in a fixed order
         if (rr == 0) {
-          float* dst = P.scratch + o.bias_part + ((i64)(t.split * o.m_tiles + t.mt) * TC_SPLIT_WARPS + sw) * TC_BM;
+          float* dst = P.scratch + t.agent * P.scratch_stride + o.bias_part + ((i64)(t.split * o.m_tiles + t.mt) * TC_SPLIT_WARPS + sw) * TC_BM;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<float4*>(dst + j * 32 + c * 8 + hbit * 4) = make_float4(bs[j][0], bs[j][1], bs[j][2], bs[j][3]);
@@ -302,12 +307,16 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       const int ncols = (o.N + 31) & ~31;
       for (int c0 = 0; c0 < ncols; c0 += 32, ++chunk) {
         uint8_t* sb = stg + (chunk & 1) * TC_STG_BYTES;
+        // bias of this 32-column chunk: one coalesced load per warp, in flight across the barriers and the TMEM load,
+        // handed out by shuffles (every thread needs all 32 values: it owns a row)
+        float bl = 0.f;
+        if (o.kind == EPI_FWD && c0 + lane < o.N) bl = __ldg(P.arena + t.agent * P.agent_stride + o.bias + c0 + lane);
         if (tid == 0) tc_bulk_wait_read<1>();               // the store that last read this buffer has drained it
         tc_bar(1, TC_EPI_WARPS * 32);
         if (o.has_aux) {
           if (tid == 0) {
             tc_mbar_expect_tx(&aux_bar, TC_STG_BYTES);
-            tc_tma_load(sb, &maps.aux[t.op], &aux_bar, c0, t.m0);
+            tc_tma_load(sb, &maps.aux[t.op], &aux_bar, c0, t.m0, t.agent);
           }
           tc_mbar_wait(&aux_bar, auxn & 1);
           ++auxn;
@@ -315,27 +324,28 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         uint32_t v[32];
         tc_ld32(tmem_base + buf * TC_NMAX + c0 + ((uint32_t)(warp * 32) << 16), v);
         float4* srow = reinterpret_cast<float4*>(sb + row * 128);
+        const int act = o.act;
 #pragma unroll
         for (int qd = 0; qd < 8; ++qd) {
           float4 a = make_float4(__uint_as_float(v[4 * qd]), __uint_as_float(v[4 * qd + 1]), __uint_as_float(v[4 * qd + 2]),
                                  __uint_as_float(v[4 * qd + 3]));
-          const int n = c0 + 4 * qd;
           float4* slot = srow + (qd ^ (row & 7));
           if (o.kind == EPI_FWD) {
-            if (n < o.N) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(P.arena + o.bias + n));
-              a = make_float4(act_fwd(o.act, a.x + b.x), act_fwd(o.act, a.y + b.y), act_fwd(o.act, a.z + b.z), act_fwd(o.act, a.w + b.w));
-            }
+            a.x += __shfl_sync(0xffffffffu, bl, 4 * qd); a.y += __shfl_sync(0xffffffffu, bl, 4 * qd + 1);
+            a.z += __shfl_sync(0xffffffffu, bl, 4 * qd + 2); a.w += __shfl_sync(0xffffffffu, bl, 4 * qd + 3);
+            if (act == SACX_ACT_RELU) a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+            else a = make_float4(act_fwd(act, a.x), act_fwd(act, a.y), act_fwd(act, a.z), act_fwd(act, a.w));
           } else if (o.kind == EPI_DACT) {
             const float4 h = *slot;
-            a = make_float4(a.x * act_dz(o.act, h.x), a.y * act_dz(o.act, h.y), a.z * act_dz(o.act, h.z), a.w * act_dz(o.act, h.w));
+            if (act == SACX_ACT_RELU) a = make_float4(h.x > 0.f ? a.x : 0.f, h.y > 0.f ? a.y : 0.f, h.z > 0.f ? a.z : 0.f, h.w > 0.f ? a.w : 0.f);
+            else a = make_float4(a.x * act_dz(act, h.x), a.y * act_dz(act, h.y), a.z * act_dz(act, h.z), a.w * act_dz(act, h.w));
           }
           *slot = a;
         }
         tc_fence_async();
         tc_bar(1, TC_EPI_WARPS * 32);
         if (tid == 0) {
-          tc_tma_store(&maps.c[t.op], sb, c0, crow);
+          tc_tma_store(&maps.c[t.op], sb, c0, crow, t.agent);
           tc_bulk_commit();
         }
       }
@@ -363,7 +373,7 @@ struct TcRedParams {
   int n_ops, pad;
   float* arena;
   const float* scratch;
-  i64 scal_off;
+  i64 scal_off, agent_stride, scratch_stride;
   Hyper hp;
   TcRedOp ops[TC_MAX_OPS];
 };
@@ -371,7 +381,8 @@ struct TcRedParams {
 __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant__ TcRedParams R) {
   const TcRedOp& r = R.ops[blockIdx.y];
   const Op& op = r.op;
-  float* base = R.arena;
+  float* base = R.arena + (i64)blockIdx.z * R.agent_stride;
+  const float* scratch = R.scratch + (i64)blockIdx.z * R.scratch_stride;
   const AgentScalars* scal = reinterpret_cast<const AgentScalars*>(base + R.scal_off);
   const int n4 = op.N >> 2;
   const i64 total = (i64)op.M * n4 + op.M;           // weight float4s, then one bias element per output row
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant
     if (e < (i64)op.M * n4) {
       const int m = (int)(e / n4), n = (int)(e % n4) * 4;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* p = R.scratch + r.part + (i64)m * r.n_ld + n;
+      const float* p = scratch + r.part + (i64)m * r.n_ld + n;
       for (int s = 0; s < r.splits; ++s) {
         const float4 x = __ldcs(reinterpret_cast<const float4*>(p + (i64)s * r.m_pad * r.n_ld));
         g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
@@ -410,7 +421,7 @@ __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant
     } else if (op.pb >= 0) {
       const int m = (int)(e - (i64)op.M * n4);
       float g = 0.f;
-      const float* bp = R.scratch + r.bias_part + (i64)(m / TC_BM) * TC_SPLIT_WARPS * TC_BM + (m % TC_BM);
+      const float* bp = scratch + r.bias_part + (i64)(m / TC_BM) * TC_SPLIT_WARPS * TC_BM + (m % TC_BM);
       for (int s = 0; s < r.splits; ++s)
         for (int w = 0; w < TC_SPLIT_WARPS; ++w) g += __ldcs(bp + ((i64)s * (r.m_pad / TC_BM) * TC_SPLIT_WARPS + w) * TC_BM);
       if (op.flags & DW_STORE_GRAD) base[op.pbg + m] = g;

@@ -177,3 +177,37 @@ def test_tc_multi_step_launch_and_device_rng(monkeypatch):
     assert np.array_equal(a.view("block.params").cpu().numpy(), b.view("block.params").cpu().numpy())
     assert a.metrics()["updates"] == 3 and b.metrics()["updates"] == 3
     assert a.metrics()["nonfinite"] == 0
+
+
+def test_tc_population_matches_ffma_population(monkeypatch):
+    """Population mode (BASELINE config 3 shape: obs 4, act 1, 2x256, batch 256): 64 independent agents through the
+    tensor-core path (3-D tensor maps: agent = third coordinate; one launch per phase covers every agent) against the
+    one-CTA-per-agent FFMA kernel. Per-agent state after two device-RNG updates: every agent within the parameter bar
+    except at most a few hit by an fp32-order flip; no agent may be far off."""
+    from sac.population import SACPopulation
+    obs, act, B, n = 4, 1, 256, 64
+    cfg = base_config(hidden=(256, 256), batch=B, capacity=2000, rng="device")
+    res = {}
+    for tc in (True, False):
+        monkeypatch.setenv("SACX_TC", "1" if tc else "0")
+        monkeypatch.setenv("SACX_TC_MIN_BATCH", "4096")
+        pop = SACPopulation(obs, act, cfg, n, reference_init=False)
+        on, why, _ = pop.engine.tensor_core()
+        assert on == tc, (on, why)
+        s, a, r, s2, d = (torch.from_numpy(x).cuda() for x in __import__("helpers").synth_transitions(1500, obs, act, 3))
+        pop.push_device_all(s, a, r, s2, d.float())
+        pop.engine.update(None, None, None, 2)
+        pop.engine.sync()
+        if tc:
+            assert pop.engine.tensor_core()[2] > 0
+        res[tc] = {k: pop.engine.population_view(k).cpu().numpy().copy() for k in ("block.params", "block.targets", "block.m", "out.y")}
+        ups = [pop.engine.metrics(ag)["updates"] for ag in (0, n - 1)]
+        assert ups == [2, 2] and pop.engine.metrics(0)["nonfinite"] == 0
+    from helpers import rel_l2
+    for k, bar in (("out.y", 1e-4), ("block.params", 2e-4), ("block.targets", 2e-5)):
+        errs = np.array([rel_l2(res[True][k][ag], res[False][k][ag]) for ag in range(n)])
+        assert np.median(errs) < bar / 4, (k, np.median(errs))
+        assert (errs > bar).sum() <= 3, (k, np.sort(errs)[-5:])
+        assert errs.max() < 100 * bar, (k, errs.max())
+    # agents are independent: different seeds -> different parameters
+    assert not np.array_equal(res[True]["block.params"][0], res[True]["block.params"][1])
