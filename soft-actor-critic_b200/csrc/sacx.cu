@@ -145,7 +145,10 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
         auto launch_rows = [&](int p) -> int {
           a.phase_begin = p; a.phase_end = p + 1; a.n_steps = 1; a.tc_skip = 1;
           const int tiles = std::max(1, hp.phases[p].ntiles);
-          sacx_rows_kernel<<<dim3(std::min(tiles, e->n_sms * e->rows_ctas_per_sm), std::min(e->cfg.n_agents, 65535)), 256, e->rows_smem_bytes, e->stream>>>(
+          // ~8 waves of CTAs over the chip; a CTA keeps to one agent and walks its tiles, so head weights are staged once
+          const int na = e->cfg.n_agents, slots = e->n_sms * e->rows_ctas_per_sm;
+          const int gx = na == 1 ? std::min(tiles, slots) : std::min(tiles, std::max(1, (8 * slots + na - 1) / na));
+          sacx_rows_kernel<<<dim3(gx, std::min(na, 65535)), 256, e->rows_smem_bytes, e->stream>>>(
               dplan, a, e->rows_tsm_floats);
           ++e->launches;
           return SACX_OK;
@@ -268,16 +271,19 @@ typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// 2-D fp32 tensor [outer][inner] with row stride ld (floats); out-of-range box elements read as zero / are not written
+// fp32 tensor [outer][inner] with row stride ld (floats); out-of-range box elements read as zero / are not written.
+// swz: 0 = 128B swizzle (epilogue tiles, 32-float rows), 1 = 128B swizzle with 32B atoms (MN-major operands), 2 = 64B
+// swizzle (K-major operands, 16-float rows)
 // (the third dimension is the agent: slices `agent_stride` floats apart)
 static bool tc_encode(TcEncodeFn enc, CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                      uint32_t box_in, uint32_t box_out, bool atom32, uint64_t n_agents, uint64_t agent_stride) {
+                      uint32_t box_in, uint32_t box_out, int swz, uint64_t n_agents, uint64_t agent_stride) {
   cuuint64_t dims[3] = {inner, outer, n_agents};
   cuuint64_t strides[2] = {ld * 4, std::max<uint64_t>(agent_stride, 4) * 4};
   cuuint32_t box[3] = {box_in, box_out, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             swz == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -324,7 +330,10 @@ static int engine_setup_tc(Engine* e) {
           else {
             tp.other_ops = true;
             const int ty = pl.ops[i].type;
-            if (ty == OP_GEMM || ty == OP_DW_HEAD || ty == OP_LOAD_EXT || ty == OP_NONE) tp.light = false;
+            const Op& oo = pl.ops[i];
+            const bool small_fwd = ty == OP_GEMM && oo.epi == EPI_FWD && oo.K <= SMALLK_MAX && oo.zout < 0 && oo.mode == 0 && oo.i[4] == 0 &&
+                                   oo.a_sk == 1 && oo.b_sk == 1 && oo.cfg >= 1;      // the light kernel's small_fwd_tile (64x64 tile grid)
+            if ((ty == OP_GEMM && !small_fwd) || ty == OP_DW_HEAD || ty == OP_LOAD_EXT || ty == OP_NONE) tp.light = false;
           }
         }
         size_t so = 0;                       // scratch offset inside this phase (floats)
@@ -334,6 +343,7 @@ static int engine_setup_tc(Engine* e) {
           memset(&g.p, 0, sizeof g.p); memset(&g.maps, 0, sizeof g.maps); memset(&g.red, 0, sizeof g.red);
           g.p.arena = e->arena; g.p.scratch = e->d_tc_scratch;
           g.p.n_agents = (int)NA; g.p.agent_stride = (i64)AS; g.p.scratch_stride = (i64)sstride;
+          { const char* dv = getenv("SACX_TC_DBG"); g.p.dbg = dv ? atoi(dv) : 0; }
           g.red.arena = e->arena; g.red.scratch = e->d_tc_scratch; g.red.scal_off = e->scal_off; g.red.hp = e->hp;
           g.red.agent_stride = (i64)AS; g.red.scratch_stride = (i64)sstride;
           int tiles = 0;
@@ -350,15 +360,15 @@ static int engine_setup_tc(Engine* e) {
             const float* A = e->arena + o.a;
             const float* Bm = e->arena + o.b;
             if (o.epi == EPI_FWD || o.epi == EPI_DACT) {
-              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.K, o.M, o.a_sm, TC_BK, TC_BM, false, NA, AS);
-              ok = ok && tc_encode(enc, &g.maps.c[j], e->arena + o.c, o.N, o.M, o.ldc, 32, TC_BM, false, NA, AS);
+              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.K, o.M, o.a_sm, TC_BK, TC_BM, 2, NA, AS);
+              ok = ok && tc_encode(enc, &g.maps.c[j], e->arena + o.c, o.N, o.M, o.ldc, 32, TC_BM, 0, NA, AS);
               if (o.epi == EPI_FWD) {
                 t.b_rows = t.n_mma; t.b_bytes = t.n_mma * TC_BK * 4;
-                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.K, o.N, o.b_sn, TC_BK, t.n_mma, false, NA, AS);
+                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.K, o.N, o.b_sn, TC_BK, t.n_mma, 2, NA, AS);
               } else {
                 t.b_mn = 1; t.b_rows = (t.n_mma + 31) / 32; t.b_bytes = t.b_rows * TC_SLAB; t.has_aux = 1;
-                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, true, NA, AS);
-                ok = ok && tc_encode(enc, &g.maps.aux[j], e->arena + o.aux, o.N, o.M, o.ld_aux, 32, TC_BM, false, NA, AS);
+                ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, 1, NA, AS);
+                ok = ok && tc_encode(enc, &g.maps.aux[j], e->arena + o.aux, o.N, o.M, o.ld_aux, 32, TC_BM, 0, NA, AS);
               }
             } else {
               t.a_mn = t.b_mn = 1;
@@ -372,11 +382,11 @@ static int engine_setup_tc(Engine* e) {
               r.bias_part = (i64)so; so += (size_t)t.splits * m_pad * TC_SPLIT_WARPS;
               t.bias_part = o.pb >= 0 ? r.bias_part : -1;
               g.has_red = true;
-              g.red_blocks = std::max(g.red_blocks, std::min(1024, (o.M * (o.N / 4) + o.M + 255) / 256));
-              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.M, o.K, o.a_sk, 32, TC_BK, true, NA, AS);
-              ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, true, NA, AS);
+              g.red_blocks = std::max(g.red_blocks, std::min(1024, (o.M * ((o.N + 3) / 4) + o.M + 255) / 256));
+              ok = ok && tc_encode(enc, &g.maps.a[j], A, o.M, o.K, o.a_sk, 32, TC_BK, 1, NA, AS);
+              ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.N, o.K, o.b_sk, 32, TC_BK, 1, NA, AS);
               if (pass == 1)
-                ok = ok && tc_encode(enc, &g.maps.c[j], e->d_tc_scratch + r.part, n_ld, (uint64_t)t.splits * m_pad, n_ld, 32, TC_BM, false, NA, sstride);
+                ok = ok && tc_encode(enc, &g.maps.c[j], e->d_tc_scratch + r.part, n_ld, (uint64_t)t.splits * m_pad, n_ld, 32, TC_BM, 0, NA, sstride);
             }
             t.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)t.a_mn << 15) | ((uint32_t)t.b_mn << 16) |
                       ((uint32_t)(t.n_mma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);

@@ -946,7 +946,8 @@ struct Engine {
   bool tc_op_eligible(const Op& o) const {
     if (o.type != OP_GEMM || o.mode != 0 || o.i[4] != 0 || o.zout >= 0) return false;
     auto al = [](i64 x) { return x >= 0 && (x & 3) == 0; };
-    if (o.N < 16 || o.N > TC_NMAX || (o.N & 3)) return false;
+    if (o.N > TC_NMAX) return false;
+    if (o.epi != EPI_DW && (o.N < 16 || (o.N & 3))) return false;      // dW: any width (B operand rows are 16B-aligned batch rows)
     if (o.epi == EPI_FWD)
       return o.M >= tc_min_m && o.a_sk == 1 && o.b_sk == 1 && !(o.a_sm & 3) && !(o.b_sn & 3) && !(o.ldc & 3) && al(o.a) && al(o.b) &&
              al(o.c) && al(o.bias) && o.K >= 4;
@@ -955,7 +956,7 @@ struct Engine {
              al(o.a) && al(o.b) && al(o.c) && al(o.aux) && !(o.K & 3);
     if (o.epi == EPI_DW)
       return o.K >= tc_min_m && o.M >= 1 && o.a_sm == 1 && o.b_sn == 1 && !(o.a_sk & 3) && !(o.b_sk & 3) && al(o.a) &&
-             al(o.b) && al(o.p) && al(o.pm) && al(o.pv) && al(o.pg) && (o.pt < 0 || al(o.pt));
+             al(o.b) && o.p >= 0;
     return false;
   }
   bool tc_wanted(std::string& why) const {

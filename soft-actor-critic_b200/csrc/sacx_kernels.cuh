@@ -117,6 +117,35 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
 // persistent kernel above needs 255 registers and ~200 KB of shared memory, i.e. one CTA (8 rows in flight) per SM; at
 // batch 65536 the row phases are then bound by the latency of a tile's dependent loads. Same tile functions (their
 // own copy, V = 1), 3 CTAs per SM. One phase per launch, single agent or blockIdx.y = agent.
+// forward layer with a very short reduction (first layer of a low-dimensional observation: K = obs (+ act) <= 32 with rows
+// TMA cannot address, e.g. K = 5): 64x64 tile of the op's tile grid, thread = one output column x 16 rows, the weight row
+// in registers, the input rows as warp-wide broadcast loads. Memory-bound on the output write.
+constexpr int SMALLK_MAX = 32;
+__device__ __forceinline__ bool small_fwd_ok(const Op& o) {
+  return o.type == OP_GEMM && o.epi == EPI_FWD && o.K <= SMALLK_MAX && o.zout < 0 && o.mode == 0 && o.i[4] == 0 && o.a_sk == 1 && o.b_sk == 1 &&
+         o.cfg >= 1;
+}
+__device__ __forceinline__ void small_fwd_tile(const Op& op, float* __restrict__ base, int tile) {
+  const int tm = tile / op.tiles_n, tn = tile % op.tiles_n;
+  const int n = tn * 64 + (threadIdx.x & 63), m0 = tm * 64 + (threadIdx.x >> 6) * 16;
+  if (n >= op.N) return;
+  float w[SMALLK_MAX];
+#pragma unroll
+  for (int k = 0; k < SMALLK_MAX; ++k) w[k] = (k < op.K) ? __ldg(base + op.b + (i64)n * op.b_sn + k) : 0.f;
+  const float bias = __ldg(base + op.bias + n);
+#pragma unroll 4
+  for (int r = 0; r < 16; ++r) {
+    const int m = m0 + r;
+    if (m >= op.M) break;
+    const float* x = base + op.a + (i64)m * op.a_sm;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < SMALLK_MAX; ++k)
+      if (k < op.K) s = fmaf(__ldcg(x + k), w[k], s);
+    base[op.c + (i64)m * op.ldc + n] = act_fwd(op.act, s + bias);
+  }
+}
+
 constexpr int ROWS_SMEM_OPS = 8;
 __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restrict__ gplan, const RunArgs args, int tsm_floats) {
   extern __shared__ __align__(16) float rows_raw[];
@@ -139,12 +168,17 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
     float* base = args.arena + (i64)agent * args.agent_stride;
     AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
     RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, tsm, tsm_floats, nullptr};
+    int last_oi = -1;
+    rc.pf_rows = 2 * (int)gridDim.x * ROWS_PER_TILE;
     for (int t = blockIdx.x; t < ph.ntiles; t += gridDim.x) {
       int oi = ph.op0;
       while (oi + 1 < ph.op0 + ph.nops && t >= ops[oi + 1].tile0) ++oi;
       const Op& op = ops[oi];
       const int lt = t - op.tile0;
+      rc.fresh = (oi != last_oi);          // head weights are staged once per (agent, op) run of tiles, not once per 8 rows
+      last_oi = oi;
       switch (op.type) {
+        case OP_GEMM: if (!(op.cfg & 2) && small_fwd_ok(op)) small_fwd_tile(op, base, lt); break;
         case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
         case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); __syncthreads(); break;
         case OP_Q_ROW: tile_q_row<1>(op, rc, lt); __syncthreads(); break;

@@ -28,6 +28,8 @@ struct RowCtx {
   float* tsm;          // CTA-wide shared staging area (aliases the GEMM ring), tsm_floats floats
   int tsm_floats;
   unsigned long long* t;   // optional timestamps (profiling aid)
+  int pf_rows = 0;         // light kernel: row distance to the tile this CTA runs two iterations from now (L2 prefetch), 0 = off
+  int fresh = 1;           // 0: this CTA's previous tile belonged to the same op and agent -> the staged weights in tsm are still valid
 };
 #define SACX_RSTAMP(i) do { if (c.t && threadIdx.x == 0) c.t[i] = clock64(); } while (0)
 
@@ -57,6 +59,10 @@ __device__ __forceinline__ void row_load(RowReg& r, const float* __restrict__ p,
     const int k = (lane + 32 * i) * 4;
     r.v[i] = (k < K) ? __ldcg(reinterpret_cast<const float4*>(p + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+// pull a future row (K floats) into L2: the large-batch row kernels are bound by HBM latency x bytes in flight
+__device__ __forceinline__ void row_prefetch(const float* p, int K, int lane) {
+  if (lane * 32 < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + lane * 32));
 }
 // dot(row in registers, w in shared memory)
 __device__ __forceinline__ float row_dot_partial(const RowReg& r, const float* __restrict__ w, int K, int lane) {
@@ -150,10 +156,13 @@ __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int til
                                (uint32_t)lane, (uint32_t)c.agent);
   }
   if (staged) {
-    stage_vec(Ws, Wg, 2 * A * K);
-    for (int i = threadIdx.x; i < 2 * A; i += 256) bs[i] = __ldcg(base + op.o[2] + i);
+    if (c.fresh) {
+      stage_vec(Ws, Wg, 2 * A * K);
+      for (int i = threadIdx.x; i < 2 * A; i += 256) bs[i] = __ldcg(base + op.o[2] + i);
+    }
     if (fast && in) row_load(hr, h, K, lane);
-    stage_finish();
+    if (V == 1 && c.pf_rows && row + c.pf_rows < hp.B) row_prefetch(h + (i64)c.pf_rows * op.i[0], K, lane);
+    if (c.fresh) stage_finish();
   }
   SACX_RSTAMP(1); SACX_RSTAMP(2); SACX_RSTAMP(3);
   if (!in) { SACX_RSTAMP(4); return; }
@@ -238,17 +247,27 @@ __device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile)
     }
   }
   if (staged) {
-    if (do_t) { stage_vec(Ws, base + op.o[2], K); stage_vec(Ws + K, base + op.o[3], K); }
-    if (do_c) { stage_vec(Ws + 2 * K, base + op.o[16], K); stage_vec(Ws + 3 * K, base + op.o[17], K); }
+    if (c.fresh) {
+      if (do_t) { stage_vec(Ws, base + op.o[2], K); stage_vec(Ws + K, base + op.o[3], K); }
+      if (do_c) { stage_vec(Ws + 2 * K, base + op.o[16], K); stage_vec(Ws + 3 * K, base + op.o[17], K); }
+    }
     if (fast && in) {
       if (do_t) { row_load(ht[0], hp_t[0], K, lane); row_load(ht[1], hp_t[1], K, lane); }
+      if (V == 1 && c.pf_rows && row + c.pf_rows < hp.B) {
+        const i64 pf = (i64)c.pf_rows * ld;
+        if (do_t) { row_prefetch(hp_t[0] + pf, K, lane); row_prefetch(hp_t[1] + pf, K, lane); }
+        if (do_c) {
+          row_prefetch(hp_c[0] + pf, K, lane); row_prefetch(hp_c[1] + pf, K, lane);
+          if (!aux_is_h) { row_prefetch(ax_c[0] + pf, K, lane); row_prefetch(ax_c[1] + pf, K, lane); }
+        }
+      }
       if (do_c) {
         row_load(hc[0], hp_c[0], K, lane); row_load(hc[1], hp_c[1], K, lane);
         if (!aux_is_h) { row_load(ac[0], ax_c[0], K, lane); row_load(ac[1], ax_c[1], K, lane); }
         else { ac[0] = hc[0]; ac[1] = hc[1]; }
       }
     }
-    stage_finish();
+    if (c.fresh) stage_finish();
   }
   SACX_RSTAMP(1); SACX_RSTAMP(2); SACX_RSTAMP(3);
   if (!in) { SACX_RSTAMP(4); return; }
@@ -332,14 +351,21 @@ __device__ __noinline__ void tile_actor_q(const Op& op, const RowCtx& c, int til
     lp_ = __ldcg(base + op.o[8] + row);
   }
   if (staged) {
-    stage_vec(Ws, base + op.o[4], K);
-    stage_vec(Ws + K, base + op.o[5], K);
+    if (c.fresh) {
+      stage_vec(Ws, base + op.o[4], K);
+      stage_vec(Ws + K, base + op.o[5], K);
+    }
     if (fast && in) {
       row_load(hr[0], hq[0], K, lane); row_load(hr[1], hq[1], K, lane);
+      if (V == 1 && c.pf_rows && row + c.pf_rows < hp.B) {
+        const i64 pf = (i64)c.pf_rows * ld;
+        row_prefetch(hq[0] + pf, K, lane); row_prefetch(hq[1] + pf, K, lane);
+        if (!aux_is_h) { row_prefetch(ax[0] + pf, K, lane); row_prefetch(ax[1] + pf, K, lane); }
+      }
       if (!aux_is_h) { row_load(ar[0], ax[0], K, lane); row_load(ar[1], ax[1], K, lane); }
       else { ar[0] = hr[0]; ar[1] = hr[1]; }
     }
-    stage_finish();
+    if (c.fresh) stage_finish();
   }
   SACX_RSTAMP(1); SACX_RSTAMP(2); SACX_RSTAMP(3);
   if (!in) { SACX_RSTAMP(4); return; }
@@ -418,13 +444,19 @@ __device__ __noinline__ void tile_actor_bwd(const Op& op, const RowCtx& c, int t
     }
   }
   if (staged) {
-    for (int i = threadIdx.x; i < 2 * A * H0; i += 256) {
-      const int n = i / (A * H0), j = (i / H0) % A, k = i % H0;
-      Wa[i] = __ldcg(base + op.o[2 + n] + (i64)k * op.i[2] + O + j);
+    if (c.fresh) {
+      for (int i = threadIdx.x; i < 2 * A * H0; i += 256) {
+        const int n = i / (A * H0), j = (i / H0) % A, k = i % H0;
+        Wa[i] = __ldcg(base + op.o[2 + n] + (i64)k * op.i[2] + O + j);
+      }
+      stage_vec(Wp, base + op.o[9], 2 * A * Kp);
     }
-    stage_vec(Wp, base + op.o[9], 2 * A * Kp);
     if (fast && in) { row_load(dr[0], d0[0], H0, lane); row_load(dr[1], d0[1], H0, lane); row_load(ap, auxp, Kp, lane); }
-    stage_finish();
+    if (V == 1 && c.pf_rows && row + c.pf_rows < hp.B) {
+      row_prefetch(d0[0] + (i64)c.pf_rows * op.i[0], H0, lane); row_prefetch(d0[1] + (i64)c.pf_rows * op.i[0], H0, lane);
+      row_prefetch(auxp + (i64)c.pf_rows * op.i[3], Kp, lane);
+    }
+    if (c.fresh) stage_finish();
   }
   SACX_RSTAMP(1); SACX_RSTAMP(2); SACX_RSTAMP(3);
   if (!in) { SACX_RSTAMP(4); return; }

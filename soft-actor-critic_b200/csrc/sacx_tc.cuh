@@ -3,12 +3,13 @@
 //
 // One persistent CTA per SM walks the tiles of up to four GEMM ops of one plan phase (sacx_types.cuh: Op). A tile is
 // 128 rows x N (N <= 256: the whole layer width, so the A operand -- the 64 MB activation matrix at batch 65536 -- is
-// read from HBM exactly once) and the reduction runs in blocks of 32. Three shapes, all C = A . B^T with K the
+// read from HBM exactly once) and the reduction runs in blocks of 16 (four 48 KB stages hide the TMA -> split -> MMA
+// chain better than two 96 KB ones: measured 1.7x on the K = 256 layers). Three shapes, all C = A . B^T with K the
 // reduction index (reference: sac/models.py:30-33,73-77 forward; the autograd backward of sac/agent.py:230,235,256):
 //   EPI_FWD   h = act(x W^T + b)          A = x  [batch][in]   K-major     B = W [out][in]    K-major
 //   EPI_DACT  dx = (dy W) * act'(h)       A = dy [batch][out]  K-major     B = W [out][in]    MN-major (n = in)
 //   EPI_DW    dW = dy^T x (+ db = 1^T dy) A = dy [batch][out]  MN-major    B = x [batch][in]  MN-major, batch range split
-// K-major tiles use the 128-byte TMA/UMMA swizzle; MN-major fp32 tiles need the 128B-swizzle-with-32B-atoms layout
+// K-major tiles (16 floats = 64 B rows) use the 64-byte TMA/UMMA swizzle; MN-major fp32 tiles need the 128B-swizzle-with-32B-atoms layout
 // (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B / UMMA layout type 1, LBO = slab stride, SBO = 512 B: tools/tc_gemm_bench.cu
 // validated all three against fp64 on a B200).
 //
@@ -18,27 +19,29 @@
 // accumulator; the dropped lo.lo term is ~2^-22 relative.
 //
 // Warp roles (448 threads): 0-3 epilogue (TMEM -> registers -> swizzled smem -> TMA store; DACT pulls act'(h) tiles
-// in by TMA as well), 4 TMA producer, 5 MMA issuer + TMEM owner, 6-13 splitters. Two 96 KB operand stages, two
+// in by TMA as well), 4 TMA producer, 5 MMA issuer + TMEM owner, 6-13 splitters. Four 48 KB operand stages, two
 // 256-column TMEM accumulators (epilogue of tile i overlaps the main loop of tile i+1), two 16 KB staging buffers.
 // dW partial tiles ([split][out][in]) and bias partials go to a scratch buffer; tc_dw_reduce_kernel sums the
 // splits in a fixed order and applies the same fused optimiser epilogue as the FFMA tiles (Adam, Polyak).
 #pragma once
 #include <cuda.h>
 
+#include <cstdio>
+
 #include "sacx_gemm.cuh"
 
 namespace sacx {
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_NMAX = 256, TC_STAGES = 2, TC_MAX_OPS = 4;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                 // 16 KB
-constexpr int TC_B_BYTES = TC_NMAX * TC_BK * 4;               // 32 KB
+constexpr int TC_BM = 128, TC_BK = 16, TC_NMAX = 256, TC_STAGES = 4, TC_MAX_OPS = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;                 // 8 KB
+constexpr int TC_B_BYTES = TC_NMAX * TC_BK * 4;               // 16 KB
 constexpr int TC_HALF = TC_A_BYTES + TC_B_BYTES;              // hi (or lo) part of one stage
-constexpr int TC_STAGE_BYTES = 2 * TC_HALF;                   // 96 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_HALF;                   // 48 KB
 constexpr int TC_STG_BYTES = TC_BM * 32 * 4;                  // epilogue staging chunk: 128 rows x 32 columns
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES;      // 224 KB; + ~3 KB static = the 227 KB limit
 constexpr int TC_THREADS = 448;
 constexpr int TC_EPI_WARPS = 4, TC_SPLIT_WARPS = 8, TC_SPLIT_THREADS = 256;
-constexpr int TC_SLAB = 32 * TC_BK * 4;                       // MN-major slab: 32 k-rows x 128 B
+constexpr int TC_SLAB = 32 * TC_BK * 4;                       // MN-major slab: 16 k-rows x 128 B
 
 struct TcOp {
   int kind, act;
@@ -58,6 +61,7 @@ struct TcOp {
 struct TcParams {
   int n_ops, total_tiles;          // total_tiles = n_agents * tiles_per_agent (agent-major)
   int n_agents, tiles_per_agent;
+  int dbg, pad;                    // SACX_TC_DBG (timing experiments only): 1 no split, 2 one MMA per k-step, 4 no output store
   i64 agent_stride, scratch_stride;   // floats between two agents' arenas / scratch blocks
   float* arena;
   float* scratch;
@@ -106,8 +110,8 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // shared-memory matrix descriptors (sm_100 version bit 46)
-__device__ __forceinline__ uint64_t tc_desc_k(uint32_t saddr) {          // K-major, 128B swizzle, 8-row groups 1024 B apart
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t tc_desc_k(uint32_t saddr) {          // K-major rows of 16 floats: 64B swizzle, 8-row groups 512 B apart
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 __device__ __forceinline__ uint64_t tc_desc_mn(uint32_t saddr) {         // MN-major fp32: 128B swizzle with 32B atoms
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_SLAB >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
@@ -157,7 +161,11 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
   extern __shared__ __align__(1024) uint8_t tc_raw[];
   __shared__ __align__(8) uint64_t full[TC_STAGES], ready[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], aux_bar;
   __shared__ uint32_t tmem_base_s;
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)tc_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ long long ts[4][8][3];            // SACX_TC_DBG & 128: per-role timestamps of CTA 0's first 8 tiles
+  const long long t_start = clock64();
+  uint8_t* smem = tc_raw;
+  if ((tc_smem(tc_raw) & 1023u) != 0u) __trap();        // swizzled tiles need 1024-byte alignment (declared on tc_raw)
+  __shared__ __align__(16) float bias_sm[TC_NMAX];     // FWD: bias row of the epilogue's current tile
   uint8_t* stg = smem + TC_STAGES * TC_STAGE_BYTES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -185,9 +193,12 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         const TcOp& o = P.ops[t.op];
         const CUtensorMap* ma = &maps.a[t.op];
         const CUtensorMap* mb = &maps.b[t.op];
+        const int tn_ = (tile - blockIdx.x) / gridDim.x;
+        if (tn_ < 8) ts[0][tn_][0] = clock64() - t_start;
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           tc_mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+          if (tn_ < 8 && kb == 0) ts[0][tn_][1] = clock64() - t_start;
           tc_mbar_expect_tx(&full[s], (uint32_t)(o.a_bytes + o.b_bytes));
           uint8_t* st = smem + s * TC_STAGE_BYTES;
           const int k = t.k0 + kb * TC_BK;
@@ -197,6 +208,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           if (!o.b_mn) tc_tma_load(st + TC_A_BYTES, mb, &full[s], k, 0, t.agent);
           else
             for (int j = 0; j < o.b_rows; ++j) tc_tma_load(st + TC_A_BYTES + j * TC_SLAB, mb, &full[s], 32 * j, k, t.agent);
+          if (tn_ < 8) ts[0][tn_][2] = clock64() - t_start;
         }
       }
     }
@@ -210,11 +222,13 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         const uint32_t buf = tc & 1;
         tc_mbar_wait(&acc_empty[buf], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
+        if (tc < 8) ts[2][tc][0] = clock64() - t_start;
         const uint32_t tacc = tmem_base + buf * TC_NMAX;
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           tc_mbar_wait(&ready[s], (it / TC_STAGES) & 1);
           tc_fence_after();
+          if (tc < 8 && kb == 0) ts[2][tc][1] = clock64() - t_start;
           const uint32_t hi = tc_smem(smem + s * TC_STAGE_BYTES), lo = hi + TC_HALF;
 #pragma unroll
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
@@ -224,12 +238,15 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
             const uint64_t bh = o.b_mn ? tc_desc_mn(hi + boff) : tc_desc_k(hi + boff);
             const uint64_t bl = o.b_mn ? tc_desc_mn(lo + boff) : tc_desc_k(lo + boff);
             tc_mma(tacc, al, bh, o.idesc, (kb | k8) != 0);
-            tc_mma(tacc, ah, bl, o.idesc, 1u);
-            tc_mma(tacc, ah, bh, o.idesc, 1u);
+            if (!(P.dbg & 2)) {
+              tc_mma(tacc, ah, bl, o.idesc, 1u);
+              tc_mma(tacc, ah, bh, o.idesc, 1u);
+            }
           }
           tc_commit(&empty[s]);
         }
         tc_commit(&acc_full[buf]);
+        if (tc < 8) ts[2][tc][2] = clock64() - t_start;
       }
     }
   } else if (warp >= 6) {
@@ -240,56 +257,82 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       const TcTile t = tc_decode(P, tile);
       const TcOp& o = P.ops[t.op];
       const bool want_bias = (o.kind == EPI_DW) && (o.bias_part >= 0);
-      float bs[4][4];
+      float bs[2][4];       // dy tile = 4 slabs of 128 float4; this thread meets slabs (st >> 7) and (st >> 7) + 2
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) bs[j][e] = 0.f;
       const int n4 = (TC_A_BYTES + o.b_bytes) >> 4;
       for (int kb = 0; kb < t.nkb; ++kb, ++it) {
         const int s = it % TC_STAGES;
         tc_mbar_wait(&full[s], (it / TC_STAGES) & 1);
+        { const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 8 && kb == 0) ts[1][tn_][0] = clock64() - t_start; }
         float4* hi = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_HALF);
-#pragma unroll 4
-        for (int i = st; i < n4; i += TC_SPLIT_THREADS) {
-          const float4 x = hi[i];
-          float4 h, l;
-          h.x = __uint_as_float((__float_as_uint(x.x) + 0x1000u) & 0xffffe000u); l.x = x.x - h.x;
-          h.y = __uint_as_float((__float_as_uint(x.y) + 0x1000u) & 0xffffe000u); l.y = x.y - h.y;
-          h.z = __uint_as_float((__float_as_uint(x.z) + 0x1000u) & 0xffffe000u); l.z = x.z - h.z;
-          h.w = __uint_as_float((__float_as_uint(x.w) + 0x1000u) & 0xffffe000u); l.w = x.w - h.w;
-          hi[i] = h;
-          lo[i] = l;
-          if (want_bias && i < (TC_A_BYTES >> 4)) {      // slab j = i / 256 of the dy tile: column sums = bias gradient
-            const int j = i >> 8;
+        // six float4 per thread cover a full-width stage (1536 float4): all loads first, then the arithmetic and stores
+        constexpr int U = 6;
+        for (int base = st; base < ((P.dbg & 1) ? 0 : n4); base += TC_SPLIT_THREADS * U) {
+          float4 x[U];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              if (jj == j) { bs[jj][0] += x.x; bs[jj][1] += x.y; bs[jj][2] += x.z; bs[jj][3] += x.w; }
+          for (int u = 0; u < U; ++u) {
+            const int i = base + u * TC_SPLIT_THREADS;
+            x[u] = (i < n4) ? hi[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = base + u * TC_SPLIT_THREADS;
+            if (i < n4) {
+              float4 h, l;
+              if (P.dbg & 256) {     // experiment: leave the raw value as "hi" (the tensor core drops the low 13 bits itself)
+                l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xffffe000u);
+                l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xffffe000u);
+                l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xffffe000u);
+                l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xffffe000u);
+                lo[i] = l;
+                continue;
+              }
+              h.x = __uint_as_float((__float_as_uint(x[u].x) + 0x1000u) & 0xffffe000u); l.x = x[u].x - h.x;
+              h.y = __uint_as_float((__float_as_uint(x[u].y) + 0x1000u) & 0xffffe000u); l.y = x[u].y - h.y;
+              h.z = __uint_as_float((__float_as_uint(x[u].z) + 0x1000u) & 0xffffe000u); l.z = x[u].z - h.z;
+              h.w = __uint_as_float((__float_as_uint(x[u].w) + 0x1000u) & 0xffffe000u); l.w = x[u].w - h.w;
+              hi[i] = h;
+              lo[i] = l;
+            }
+          }
+          if (want_bias && base == st) {         // column sums of the dy tile (float4 0..511 = u 0, 1) = bias gradient
+            bs[0][0] += x[0].x; bs[0][1] += x[0].y; bs[0][2] += x[0].z; bs[0][3] += x[0].w;
+            bs[1][0] += x[1].x; bs[1][1] += x[1].y; bs[1][2] += x[1].z; bs[1][3] += x[1].w;
           }
         }
         tc_fence_async();
         __syncwarp();
         if (lane == 0) tc_mbar_arrive(&ready[s]);
+        { const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 8) ts[1][tn_][kb == 0 ? 1 : 2] = clock64() - t_start; }
       }
       if (want_bias) {
-        // thread (k-row r = st / 8, 16-byte chunk q = st % 8) of slab j holds out-features j*32 + ((q>>1) ^ (r&3))*8 + (q&1)*4 + e
-        // a warp covers 4 k-rows: sum them (lanes that hold the same logical chunk), then the 8 warps through shared memory
+        // thread (k-row r = (st % 128) / 8, 16-byte chunk q = st % 8) holds out-features slab*32 + ((q>>1) ^ (r&3))*8 + (q&1)*4 + e
+        // of its two slabs; a warp covers 4 k-rows of one slab pair: sum them (lanes holding the same logical chunk)
         const int rr = lane >> 3, q = lane & 7, c = (q >> 1) ^ rr, hbit = q & 1;
 #pragma unroll
         for (int d = 1; d <= 2; d <<= 1) {
           const int r2 = rr ^ d, src = r2 * 8 + (((c ^ r2) << 1) | hbit);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) bs[j][e] += __shfl_sync(0xffffffffu, bs[j][e], src);
         }
-        // per-warp shares go straight to the scratch ([row block][warp][128]); tc_dw_reduce_kernel sums them in a fixed order
+        // per-warp shares go straight to the scratch ([row block][warp][128], zeros for the slabs a warp does not meet);
+        // tc_dw_reduce_kernel sums them in a fixed order
         if (rr == 0) {
           float* dst = P.scratch + t.agent * P.scratch_stride + o.bias_part + ((i64)(t.split * o.m_tiles + t.mt) * TC_SPLIT_WARPS + sw) * TC_BM;
+          const int sl0 = sw >> 2;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(dst + j * 32 + c * 8 + hbit * 4) = make_float4(bs[j][0], bs[j][1], bs[j][2], bs[j][3]);
+          for (int j = 0; j < 4; ++j) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j == sl0) v = make_float4(bs[0][0], bs[0][1], bs[0][2], bs[0][3]);
+            if (j == sl0 + 2) v = make_float4(bs[1][0], bs[1][1], bs[1][2], bs[1][3]);
+            *reinterpret_cast<float4*>(dst + j * 32 + c * 8 + hbit * 4) = v;
+          }
         }
       }
     }
@@ -302,15 +345,17 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       const uint32_t buf = tc & 1;
       tc_mbar_wait(&acc_full[buf], (tc >> 1) & 1);
       tc_fence_after();
+      if (tid == 0 && tc < 8) ts[3][tc][0] = clock64() - t_start;
       const int row = tid;                                  // row of the tile == TMEM lane
       const int crow = (o.kind == EPI_DW) ? (t.split * o.m_tiles + t.mt) * TC_BM : t.m0;
       const int ncols = (o.N + 31) & ~31;
+      const int act = o.act;
+      if (o.kind == EPI_FWD) {                 // the tile's bias row -> shared memory (the previous tile's readers are past their last chunk: barrier below)
+        tc_bar(1, TC_EPI_WARPS * 32);
+        for (int n = tid; n < ncols; n += TC_EPI_WARPS * 32) bias_sm[n] = (n < o.N) ? __ldg(P.arena + t.agent * P.agent_stride + o.bias + n) : 0.f;
+      }
       for (int c0 = 0; c0 < ncols; c0 += 32, ++chunk) {
         uint8_t* sb = stg + (chunk & 1) * TC_STG_BYTES;
-        // bias of this 32-column chunk: one coalesced load per warp, in flight across the barriers and the TMEM load,
-        // handed out by shuffles (every thread needs all 32 values: it owns a row)
-        float bl = 0.f;
-        if (o.kind == EPI_FWD && c0 + lane < o.N) bl = __ldg(P.arena + t.agent * P.agent_stride + o.bias + c0 + lane);
         if (tid == 0) tc_bulk_wait_read<1>();               // the store that last read this buffer has drained it
         tc_bar(1, TC_EPI_WARPS * 32);
         if (o.has_aux) {
@@ -322,29 +367,52 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           ++auxn;
         }
         uint32_t v[32];
-        tc_ld32(tmem_base + buf * TC_NMAX + c0 + ((uint32_t)(warp * 32) << 16), v);
+        if (!(P.dbg & 32)) tc_ld32(tmem_base + buf * TC_NMAX + c0 + ((uint32_t)(warp * 32) << 16), v);
+        else { for (int z = 0; z < 32; ++z) v[z] = 0u; }
         float4* srow = reinterpret_cast<float4*>(sb + row * 128);
-        const int act = o.act;
+        const int sx = row & 7;
+        if (o.kind == EPI_FWD) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c0);       // broadcast reads
+          if (act == SACX_ACT_RELU) {
 #pragma unroll
-        for (int qd = 0; qd < 8; ++qd) {
-          float4 a = make_float4(__uint_as_float(v[4 * qd]), __uint_as_float(v[4 * qd + 1]), __uint_as_float(v[4 * qd + 2]),
-                                 __uint_as_float(v[4 * qd + 3]));
-          float4* slot = srow + (qd ^ (row & 7));
-          if (o.kind == EPI_FWD) {
-            a.x += __shfl_sync(0xffffffffu, bl, 4 * qd); a.y += __shfl_sync(0xffffffffu, bl, 4 * qd + 1);
-            a.z += __shfl_sync(0xffffffffu, bl, 4 * qd + 2); a.w += __shfl_sync(0xffffffffu, bl, 4 * qd + 3);
-            if (act == SACX_ACT_RELU) a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
-            else a = make_float4(act_fwd(act, a.x), act_fwd(act, a.y), act_fwd(act, a.z), act_fwd(act, a.w));
-          } else if (o.kind == EPI_DACT) {
-            const float4 h = *slot;
-            if (act == SACX_ACT_RELU) a = make_float4(h.x > 0.f ? a.x : 0.f, h.y > 0.f ? a.y : 0.f, h.z > 0.f ? a.z : 0.f, h.w > 0.f ? a.w : 0.f);
-            else a = make_float4(a.x * act_dz(act, h.x), a.y * act_dz(act, h.y), a.z * act_dz(act, h.z), a.w * act_dz(act, h.w));
+            for (int qd = 0; qd < 8; ++qd) {
+              const float4 b = b4[qd];
+              srow[qd ^ sx] = make_float4(fmaxf(__uint_as_float(v[4 * qd]) + b.x, 0.f), fmaxf(__uint_as_float(v[4 * qd + 1]) + b.y, 0.f),
+                                          fmaxf(__uint_as_float(v[4 * qd + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[4 * qd + 3]) + b.w, 0.f));
+            }
+          } else {
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd) {
+              const float4 b = b4[qd];
+              srow[qd ^ sx] = make_float4(act_fwd(act, __uint_as_float(v[4 * qd]) + b.x), act_fwd(act, __uint_as_float(v[4 * qd + 1]) + b.y),
+                                          act_fwd(act, __uint_as_float(v[4 * qd + 2]) + b.z), act_fwd(act, __uint_as_float(v[4 * qd + 3]) + b.w));
+            }
           }
-          *slot = a;
+        } else if (o.kind == EPI_DACT) {
+          if (act == SACX_ACT_RELU) {
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd) {
+              const float4 h = srow[qd ^ sx];
+              srow[qd ^ sx] = make_float4(h.x > 0.f ? __uint_as_float(v[4 * qd]) : 0.f, h.y > 0.f ? __uint_as_float(v[4 * qd + 1]) : 0.f,
+                                          h.z > 0.f ? __uint_as_float(v[4 * qd + 2]) : 0.f, h.w > 0.f ? __uint_as_float(v[4 * qd + 3]) : 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd) {
+              const float4 h = srow[qd ^ sx];
+              srow[qd ^ sx] = make_float4(__uint_as_float(v[4 * qd]) * act_dz(act, h.x), __uint_as_float(v[4 * qd + 1]) * act_dz(act, h.y),
+                                          __uint_as_float(v[4 * qd + 2]) * act_dz(act, h.z), __uint_as_float(v[4 * qd + 3]) * act_dz(act, h.w));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int qd = 0; qd < 8; ++qd)
+            srow[qd ^ sx] = make_float4(__uint_as_float(v[4 * qd]), __uint_as_float(v[4 * qd + 1]), __uint_as_float(v[4 * qd + 2]),
+                                        __uint_as_float(v[4 * qd + 3]));
         }
-        tc_fence_async();
-        tc_bar(1, TC_EPI_WARPS * 32);
-        if (tid == 0) {
+        if (!(P.dbg & 8)) tc_fence_async();
+        if (!(P.dbg & 64)) tc_bar(1, TC_EPI_WARPS * 32);
+        if (tid == 0 && !(P.dbg & 4)) {
           tc_tma_store(&maps.c[t.op], sb, c0, crow, t.agent);
           tc_bulk_commit();
         }
@@ -352,11 +420,20 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
+      if (tid == 0 && tc < 8) ts[3][tc][1] = clock64() - t_start;
     }
     if (tid == 0) tc_bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
+  if ((P.dbg & 128) && blockIdx.x == 0 && tid == 0) {
+    const int nt = min(8, (P.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
+    printf("tc kernel: %d ops, %d tiles, K0 %d; end %lld cycles\n", P.n_ops, P.total_tiles, P.ops[0].K, clock64() - t_start);
+    for (int i = 0; i < nt; ++i)
+      printf("  tile %d: tma start %lld first-empty %lld issued %lld | split first-full %lld first-done %lld last-done %lld | mma acc-empty %lld "
+             "first-ready %lld committed %lld | epi acc-full %lld done %lld\n", i, ts[0][i][0], ts[0][i][1], ts[0][i][2], ts[1][i][0], ts[1][i][1],
+             ts[1][i][2], ts[2][i][0], ts[2][i][1], ts[2][i][2], ts[3][i][0], ts[3][i][1]);
+  }
   if (warp == 5) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -384,20 +461,34 @@ __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant
   float* base = R.arena + (i64)blockIdx.z * R.agent_stride;
   const float* scratch = R.scratch + (i64)blockIdx.z * R.scratch_stride;
   const AgentScalars* scal = reinterpret_cast<const AgentScalars*>(base + R.scal_off);
-  const int n4 = op.N >> 2;
-  const i64 total = (i64)op.M * n4 + op.M;           // weight float4s, then one bias element per output row
+  const bool vec = ((op.N & 3) == 0) && (((op.p | op.pm | op.pv | op.pg) & 3) == 0) && (op.pt < 0 || (op.pt & 3) == 0);
+  const int n4 = (op.N + 3) >> 2;
+  const i64 total = (i64)op.M * n4 + op.M;           // weight float4 groups, then one bias element per output row
   const float ss = (op.flags & DW_ADAM) ? __ldcg(&scal->adam_step_size[op.opt]) : 0.f;
   const float bc = (op.flags & DW_ADAM) ? __ldcg(&scal->adam_bc2_sqrt[op.opt]) : 1.f;
   for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
     if (e < (i64)op.M * n4) {
       const int m = (int)(e / n4), n = (int)(e % n4) * 4;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* p = scratch + r.part + (i64)m * r.n_ld + n;
+      const float* p = scratch + r.part + (i64)m * r.n_ld + n;           // n_ld is a multiple of 4: the group is in range
       for (int s = 0; s < r.splits; ++s) {
         const float4 x = __ldcs(reinterpret_cast<const float4*>(p + (i64)s * r.m_pad * r.n_ld));
         g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
       }
       const i64 w = (i64)m * op.N + n;
+      if (!vec) {                                    // narrow or unaligned weight rows (first layer of a 5-wide input, ...)
+        const float gg[4] = {g.x, g.y, g.z, g.w};
+        for (int j = 0; j < 4 && n + j < op.N; ++j) {
+          if (op.flags & DW_STORE_GRAD) base[op.pg + w + j] = gg[j];
+          if (op.flags & DW_ADAM) {
+            float pp = base[op.p + w + j], mm = base[op.pm + w + j], vv = base[op.pv + w + j];
+            adam_update(gg[j], pp, mm, vv, ss, bc);
+            base[op.p + w + j] = pp; base[op.pm + w + j] = mm; base[op.pv + w + j] = vv;
+            if (op.flags & DW_POLYAK) base[op.pt + w + j] = polyak_mix(R.hp.tau, R.hp.one_minus_tau, pp, base[op.pt + w + j]);
+          }
+        }
+        continue;
+      }
       if (op.flags & DW_STORE_GRAD) *reinterpret_cast<float4*>(base + op.pg + w) = g;
       if (op.flags & DW_ADAM) {
         const float4 p4 = *reinterpret_cast<const float4*>(base + op.p + w), m4 = *reinterpret_cast<const float4*>(base + op.pm + w),
