@@ -395,15 +395,28 @@ def main():
                 traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_update")
         except Exception:
             traffic = None
+    tc_on, tc_why, tc_launches = eng.tensor_core()
+    path = eng.path()[0]
+    if tc_on:
+        kernel = ("sacx_tc_kernel (tcgen05 3xTF32 tiles, TMEM accumulators, TMA operands) + sacx_rows_kernel + tc_dw_reduce_kernel; "
+                  "achieved = algorithmic FLOP of the whole update / measured time per update (profiles/: per-kernel launch list)")
+        note = ("tensor-core path: every product is three TF32 MMAs (hi/lo split, fp32-level accuracy: parity contract rel 1e-4), so the "
+                "ceiling of this path is one third of the TF32 rate, i.e. about one sixth of the bf16 peak the fraction is quoted against")
+    elif path == "rowpar":
+        kernel = "sacx_rp_kernel (persistent row-parallel fused update: 3xTF32 mma.sync tiles, 4 grid barriers per update)"
+        note = ("single agent at batch 256 is latency-bound: 4 grid + 7 group barriers and ~21 dependent 16-row GEMM jobs per update; "
+                "see profiles/ (phase trace)")
+    else:
+        kernel = "sacx_run_kernel (persistent tile-parallel fused update, FP32 FFMA tiles)"
+        note = "FP32 FFMA path; one grid barrier per dependent layer"
     roofline = {"bound": "tensor", "achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": traffic,
-                "kernel": "sacx_run_kernel (persistent fused update)", "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long loop)",
+                "kernel": kernel, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long loop)",
                 "flop_per_update": fl, "fp32_ffma_nominal_tflops": 148 * 128 * 2 * 1.965e-3,
                 "frac_of_fp32_ffma_nominal": ach_tf / (148 * 128 * 2 * 1.965e-3),
                 "hbm_view": {"bytes_per_update": by, "achieved_gbs": by * per_gpu_rate / 1e9, "peak_gbs": pk["hbm_gbs"],
                              "frac": by * per_gpu_rate / 1e9 / pk["hbm_gbs"]},
-                "note": "FP32 FFMA path (parity contract rel 1e-4 rules out TF32/BF16 inputs); single agent at batch 256 is "
-                        "latency-bound: ~17 dependent phases per update separated by grid barriers"}
+                "note": note}
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_reference(w if w["n_agents"] == 1 else dict(w, fill=w["fill"]), 400, 10, budget_s=40.0)
@@ -411,7 +424,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": w["label"], "agents_per_gpu": n_agents_local, "updates_per_launch": args.chunk,
                                             "l2": "inputs larger than L2 (216 MB ring; each update gathers fresh random rows)",
-                                            "grid": [gx, gy], "smem_bytes": smem, "multi_gpu": ("data parallel: 2 NCCL all-reduces per update" if dp is not None else
+                                            "grid": [gx, gy], "smem_bytes": smem, "path": ("tensor-core" if tc_on else path),
+                                            "tc_kernel_launches": int(tc_launches), "multi_gpu": ("data parallel: 2 NCCL all-reduces per update" if dp is not None else
                                                           "population sharded over ranks, no collective" if w["n_agents"] > 1 else
                                                           "replicas only (independent agents per rank, no collective)")},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

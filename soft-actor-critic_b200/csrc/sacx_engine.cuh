@@ -713,6 +713,9 @@ struct Engine {
     if (cfg.n_agents != 1) { why = "population mode"; return false; }
     if (cfg.dp_world > 1) { why = "data-parallel mode"; return false; }
     { std::string w; if (tc_wanted(w)) { why = "large batch runs the tensor-core path"; return false; } }
+    // measured (Donkey latent shape, batch 1024): 4 row blocks per group cost more than the 64x64 FFMA tiles save in
+    // barriers -- 1932 vs 2358 updates/s; SACX_ROWPAR=1 still forces this kernel
+    if (cfg.batch_size > 512 && !(env && atoi(env) == 1)) { why = "batch above 512: the tile-parallel kernel is faster"; return false; }
     if (pi.L() < 2 || q1.L() < 2) { why = "fewer than two hidden layers"; return false; }
     if (act_needs_z(pi.act_h) || act_needs_z(q1.act_h)) { why = "hidden activation needs saved pre-activations"; return false; }
     if (cfg.act_dim > RP_MAXA) { why = "action dimension above 8"; return false; }
