@@ -13,6 +13,7 @@ logical deque positions (0 = oldest survivor) to ring slots on the device.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import random
 from collections import namedtuple
 from typing import List, Optional, Sequence
@@ -33,6 +34,44 @@ class _Occupancy:
 
     def __len__(self) -> int:
         return len(self._owner)
+
+
+def sample_range(n: int, k: int):
+    """``random.sample(range(n), k)`` of CPython 3.12, bit for bit, in a few bulk draws instead of k Python-level loops.
+
+    The stdlib's set-based branch (n larger than its small-population threshold) is a filter over the Mersenne Twister's
+    32-bit outputs: ``_randbelow(n)`` keeps the top ``n.bit_length()`` bits of a word and rejects values >= n, and a
+    value already selected is rejected too. ``getrandbits(32 * w)`` returns the same w words (least significant first),
+    so drawing exactly as many words as selections are still missing never consumes a word the stdlib loop would not
+    have consumed: the global generator ends in the same state. Other cases fall back to ``random.sample``."""
+    bits = int(n).bit_length()
+    setsize = 21
+    if k > 5:
+        setsize += 4 ** math.ceil(math.log(k * 3, 4))
+    if not (0 < k <= n) or n <= setsize or bits > 32 or type(random.getrandbits.__self__) is not random.Random:
+        return random.sample(range(n), k)
+    shift = 32 - bits
+    getrandbits = random.getrandbits
+    # one bulk draw of k words (the stdlib loop consumes at least k), filtered in numpy ...
+    words = np.frombuffer(getrandbits(32 * k).to_bytes(4 * k, "little"), dtype="<u4")
+    cand = words >> shift
+    out = cand[cand < n].tolist()
+    selected = set(out)
+    if len(selected) != len(out):                 # a repeated value inside the bulk (rare): keep first occurrences, in order
+        selected, kept = set(), []
+        for j in out:
+            if j not in selected:
+                selected.add(j)
+                kept.append(j)
+        out = kept
+    # ... and the few selections lost to rejections finish with the stdlib's own loop
+    while len(out) < k:
+        j = getrandbits(bits)
+        while j >= n or j in selected:
+            j = getrandbits(bits)
+        selected.add(j)
+        out.append(j)
+    return out
 
 
 class ReplayBuffer:
@@ -134,10 +173,11 @@ class ReplayBuffer:
             raise ValueError(
                 f"Not enough samples in the replay buffer to sample {batch_size} transitions. Current size: {n}")
 
-    def draw_indices(self, batch_size: int, agent: int = 0) -> List[int]:
-        """The reference's index stream: k distinct logical positions from the global ``random``."""
+    def draw_indices(self, batch_size: int, agent: int = 0):
+        """The reference's index stream: k distinct logical positions from the global ``random``
+        (``random.sample(self.memory, k)``, replay_buffer.py:39) -- same values, same generator state afterwards."""
         self._require(batch_size, agent)
-        return random.sample(range(self.size(agent)), batch_size)
+        return sample_range(self.size(agent), batch_size)
 
     def sample(self, batch_size: int) -> List[Transition]:
         """Legacy list-of-Transition result (reference: replay_buffer.py:32-39)."""

@@ -137,3 +137,33 @@ def test_models_match_reference_init_and_state_dict_layout(golden_dir):
         build_mlp(3, [], 1)
     with pytest.raises(KeyError):
         build_mlp(3, [4], 1, "swish")
+
+
+def test_bulk_index_stream_is_the_stdlib_stream():
+    """sac.replay_buffer.sample_range (the host-RNG path's index draw) == random.sample(range(n), k) of the reference's
+    replay_buffer.py:39, value for value, and it leaves the global generator in the same state -- checked against the
+    stdlib and against the index streams recorded from the real reference (tests/golden/sampling.json)."""
+    import json
+    import random
+
+    from sac.replay_buffer import sample_range
+    cases = [(0, 1_000_000, 256), (1, 20000, 256), (2, 1500, 100), (3, 1025, 1024), (4, 5000, 1), (5, 300, 256),
+             (6, 2 ** 20, 4096), (7, 2 ** 32 - 5, 64), (8, 2 ** 33, 16), (9, 4200, 1024), (10, 7, 7)]
+    for seed, n, k in cases:
+        random.seed(seed)
+        want = [random.sample(range(n), k) for _ in range(3)]
+        state = random.getstate()
+        random.seed(seed)
+        got = [list(sample_range(n, k)) for _ in range(3)]
+        assert got == want, (seed, n, k)
+        assert random.getstate() == state, (seed, n, k)
+    with pytest.raises(ValueError):
+        sample_range(5, 6)
+    with open(os.path.join(os.path.dirname(__file__), "golden", "sampling.json")) as f:
+        g = json.load(f)
+    for c in g["cases"]:
+        random.seed(c["seed"])
+        n = min(c["pushes"], c["capacity"])
+        oldest = max(c["pushes"] - c["capacity"], 0)
+        for ids in c["push_ids"]:
+            assert [oldest + j for j in sample_range(n, c["k"])] == ids
