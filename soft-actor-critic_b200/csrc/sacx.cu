@@ -226,6 +226,7 @@ static int engine_launch_rp(Engine* e, int n_steps, const RunArgs& proto) {
     a.ring_s = r->off_s; a.ring_a = r->off_a; a.ring_r = r->off_r; a.ring_s2 = r->off_s2; a.ring_d = r->off_d;
   }
   a.rp_part = e->d_rp_part;
+  a.rp_maps = e->d_rp_maps;
   SACX_CUDA(cudaMemsetAsync(e->d_barrier, 0, sizeof(unsigned) * 64 * (1 + RP_MAX_GROUPS), e->stream));
   const Plan* dplan = e->d_plans + PLAN_RP;
   const RpProgram* dprog = e->d_prog;
@@ -408,6 +409,37 @@ static int engine_setup_tc(Engine* e) {
       SACX_CUDA(cudaMemset(e->d_tc_scratch, 0, e->tc_scratch_floats * sizeof(float)));
     }
   }
+  return SACX_OK;
+}
+
+// tensor maps of the row-parallel kernel's TMA-staged weight slices (needs the arena address)
+static int engine_setup_rp_tma(Engine* e) {
+  if (!e->rp) return SACX_OK;
+  RpProgram& P = e->h_prog;
+  bool any = false;
+  for (int j = 0; j < P.n_jobs; ++j) any = any || P.jobs[j].tma;
+  if (!any) return SACX_OK;
+  auto clear = [&]() { for (int j = 0; j < P.n_jobs; ++j) P.jobs[j].tma = 0; cudaGetLastError(); };
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  std::vector<CUtensorMap> maps(P.n_jobs);
+  memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
+  bool ok = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn;
+  for (int j = 0; ok && j < P.n_jobs; ++j) {
+    const RpJob& jb = P.jobs[j];
+    if (!jb.tma) continue;
+    cuuint64_t dims[2], strides[1] = {(cuuint64_t)jb.w_ld * 4};
+    cuuint32_t box[2], estr[2] = {1, 1};
+    box[0] = 32; box[1] = 32;                                   // 32 x 32 tiles (4 KB), one per warp
+    if (!jb.bkm) { dims[0] = jb.K; dims[1] = jb.N; }            // W [N][K]: 32 rows n x 32 k
+    else { dims[0] = jb.N; dims[1] = jb.K; }                    // W [K][N]: 32 rows k x 32 columns n
+    ok = ((TcEncodeFn)fn)(&maps[j], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e->arena + jb.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  if (ok && cudaMalloc(&e->d_rp_maps, sizeof(CUtensorMap) * maps.size()) != cudaSuccess) ok = false;
+  if (ok && cudaMemcpy(e->d_rp_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+  if (!ok) { clear(); if (e->d_rp_maps) { cudaFree(e->d_rp_maps); e->d_rp_maps = nullptr; } }
+  SACX_CUDA(cudaMemcpy(e->d_prog, &e->h_prog, sizeof(RpProgram), cudaMemcpyHostToDevice));
   return SACX_OK;
 }
 
@@ -658,6 +690,7 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   if (e.cfg.dp_world <= 0) { e.cfg.dp_world = 1; e.cfg.dp_rank = 0; }
   { const char* mb = getenv("SACX_TC_MIN_BATCH"); if (mb && atoi(mb) > 0) e.tc_min_batch = atoi(mb); }
   e.tc_min_m = e.cfg.n_agents > 1 ? 128 : e.tc_min_batch;
+  { const char* rt = getenv("SACX_RP_TMA"); if (rt && atoi(rt) == 0) e.rp_tma = false; }
   int dev = 0;
   SACX_CUDA(cudaGetDevice(&dev));
   SACX_CUDA(cudaDeviceGetAttribute(&e.n_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -705,6 +738,7 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
     e.own_arena = true;
   }
   if ((rc = engine_setup_tc(&e))) { delete h; return rc; }
+  if ((rc = engine_setup_rp_tma(&e))) { delete h; return rc; }
   SACX_CUDA(cudaMalloc((void**)&e.d_plans, sizeof(Plan) * N_PLANS));
   SACX_CUDA(cudaMemcpy(e.d_plans, e.h_plans.data(), sizeof(Plan) * N_PLANS, cudaMemcpyHostToDevice));
   SACX_CUDA(cudaMalloc((void**)&e.d_barrier, sizeof(unsigned) * 64 * 4096));
@@ -724,6 +758,7 @@ int sacx_agent_destroy(sacx_agent_t h) {
   if (e.d_plans) cudaFree(e.d_plans);
   if (e.d_prog) cudaFree(e.d_prog);
   if (e.d_rp_part) cudaFree(e.d_rp_part);
+  if (e.d_rp_maps) cudaFree(e.d_rp_maps);
   if (e.d_tc_scratch) cudaFree(e.d_tc_scratch);
   if (e.d_barrier) cudaFree(e.d_barrier);
   if (e.pinned_metrics) cudaFreeHost(e.pinned_metrics);

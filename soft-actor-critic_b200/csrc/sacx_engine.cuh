@@ -89,6 +89,8 @@ struct Engine {
   RpProgram* d_prog = nullptr;
   float* d_rp_part = nullptr;
   int rp_grid = 0, rp_smem_bytes = 0;
+  bool rp_tma = true;              // weight slices by TMA where the layout allows (SACX_RP_TMA=0: cp.async everywhere)
+  void* d_rp_maps = nullptr;       // device array of CUtensorMap, one per job
   std::string rp_why;
   // tensor-core path (sacx_tc.cuh): single agent at large batch; per plan phase the TC-eligible GEMM ops in groups of <= 4
   struct TcGroup { TcParams p; TcMaps maps; int grid = 0; bool has_red = false; TcRedParams red; int red_blocks = 0; };
@@ -741,9 +743,15 @@ struct Engine {
     auto cur = [&]() -> RpStep& { return P.steps[P.n_steps_a + P.n_steps_c]; };
     auto add_job = [&](const RpJob& j) {
       if (P.n_jobs >= RP_MAX_JOBS) { overflow = true; return; }
-      P.jobs[P.n_jobs++] = j; cur().njobs++;
       const int NS = j.N / RP_CS;
-      wmax = std::max(wmax, j.bkm ? j.K * NS : NS * (j.Kp + 4));
+      RpJob jj = j;
+      // TMA-staged slice (sacx_rowpar.cuh): 32 columns per CTA, rows the tensor map can address; map index = job index
+      jj.tma = (rp_tma && NS == 32 && (j.w_ld % 4) == 0 && (j.w % 4) == 0 && j.K <= 256) ? 1 : 0;
+      jj.map = P.n_jobs;
+      P.jobs[P.n_jobs++] = jj; cur().njobs++;
+      const int cp_floats = j.bkm ? j.K * NS : NS * (j.Kp + 4);
+      const int tma_floats = j.bkm ? j.K * 32 : ((j.K + 31) / 32) * 1024;
+      wmax = std::max(wmax, jj.tma ? tma_floats : cp_floats);
     };
     auto add_load = [&](i64 off, int ld, int K, int abuf) {
       if (P.n_loads >= RP_MAX_LOADS) { overflow = true; return; }
@@ -871,11 +879,11 @@ struct Engine {
     P.lda = hmax + 4; P.abuf_floats = RP_RB * P.lda;
     P.ldx = ((O + A + 7) & ~7) + 4;
     P.gldx = ldx;
-    P.wslot_floats = ((wmax + 3) & ~3) + 1024;      // + epilogue operand [16][32] + projection weights [16][32]
+    P.wslot_floats = ((wmax + 255) & ~255) + 1024;   // (1 KB granules: swizzled TMA tiles) + epilogue operand [16][32] + projection weights [16][32]
     int off = 0;
     P.sm_abuf = off; off += RP_NABUF * P.abuf_floats;
     P.sm_xbuf = off; off += 3 * RP_RB * P.ldx;
-    off = (off + 3) & ~3;
+    off = (off + 255) & ~255;
     P.sm_wslot = off; off += RP_NWSLOT * P.wslot_floats;
     P.sm_red = off; off += RP_RED;
     P.sm_otile = off; P.sm_pw = off;

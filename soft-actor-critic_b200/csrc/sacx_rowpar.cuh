@@ -48,6 +48,7 @@ struct RpJob {
   int w_ld;                // leading dimension of W in global memory
   int out_ld, aux_ld;
   int proj_J, proj_slot, proj_sj, proj_sn;      // projection of the output slice onto J weight vectors (0: none)
+  int tma, map;            // tma = 1: the weight slice arrives by TMA (tensor map `map`, 128B-swizzled tiles) instead of cp.async
   i64 w, bias, out, aux, proj_w;                // arena offsets (-1: unused)
 };
 struct RpLoad { i64 off; int ld, K, abuf, pad; };
@@ -94,9 +95,10 @@ struct RpCtx {
   unsigned* gbar;         // this group's barrier counter (flag at +32)
   int rank, step, row0;
   RpTrace* tr;
+  uint64_t* wbar;         // one mbarrier per weight slot (TMA-staged slices)
 };
 
-#define RP_SMEM extern __shared__ __align__(16) float smem_raw[]
+#define RP_SMEM extern __shared__ __align__(1024) float rp_dyn_smem[]; float* const smem_raw = rp_dyn_smem
 
 // ---- shared-memory accessors (explicit state space: the helpers receive offsets, not generic pointers) ---------------
 __device__ __forceinline__ uint32_t rp_saddr(const float* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,6 +110,30 @@ __device__ __forceinline__ float rp_lds(uint32_t a) {
 
 __device__ __forceinline__ void rp_cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rp_saddr(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// ---- TMA-staged weight slices (hidden width 256: NS = 32 columns per CTA) -------------------------------------------------
+// One thread issues the whole slice (8 tile loads for a 32 x 256 forward slice, one for a 256 x 32 backward slice) and the
+// copy runs behind the current job's math; the cp.async version blocks every thread for the ~2.4K cycles the L2 needs to
+// deliver 32 KB to each of the 128 CTAs at once. Tiles are 128B-swizzled (32 floats per row): conflict-free fragment loads
+// for the forward orientation, two-way conflicts for the backward one.
+__device__ __forceinline__ void rp_mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(count));
+}
+__device__ __forceinline__ void rp_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rp_mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"((uint32_t)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void rp_tma_load(float* dst, const void* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(reinterpret_cast<uint64_t>(map)),
+                 "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
 // ---- 3xTF32 tensor-core arithmetic ------------------------------------------------------------------------------
@@ -158,7 +184,7 @@ __device__ __forceinline__ void rp_group_barrier(unsigned* counter, unsigned& ep
 // slot = [weight slice | epilogue operand (bias[NS] or aux[16][NS]) | projection weights [J][NS]], all by cp.async (one
 // commit group per job, committed by the caller). (1-D bulk copies were tried: ~90 cycles of issue per row copy on the
 // single TMA queue -- 3.5K cycles for a 32-row slice -- against ~1.4K for 8 cp.async per thread.)
-__device__ __forceinline__ void rp_issue_job(const RpJob& jb, float* __restrict__ slot, const RpCtx& c) {
+__device__ __forceinline__ void rp_issue_job(const RpJob& jb, float* __restrict__ slot, const RpCtx& c, int slot_idx) {
   const RpProgram& P = *c.P;
   const float* __restrict__ base = c.base;
   const int NS = 1 << jb.ns_log2, n0g = c.rank << jb.ns_log2, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -167,7 +193,30 @@ __device__ __forceinline__ void rp_issue_job(const RpJob& jb, float* __restrict_
   float* pws = slot + P.wslot_floats - 512;
   const int J = jb.proj_J, cl = jb.ns_log2 - 2;            // chunks per NS-wide row = NS / 4 = 1 << cl
   const int B = c.args->hp.B;
-  if (!jb.bkm) {
+  if (jb.tma) {
+    if (lane == 0) {
+      // one 32 x 32 tile (4 KB) per warp: the issue cost (~100 cycles per tile on the TMA queue) is spread over the warps.
+      // The slot was last read with ordinary loads (the caller's barrier ordered them): fence towards the async proxy.
+      uint64_t* bar = c.wbar + slot_idx;
+      const int slabs = (jb.K + 31) >> 5;                  // K <= 256: at most 8
+      if (warp < slabs) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const char* map = reinterpret_cast<const char*>(c.args->rp_maps) + (size_t)jb.map * 128;
+        rp_mbar_expect_tx(bar, 4096u);
+        if (!jb.bkm) rp_tma_load(slot + warp * 1024, map, bar, 32 * warp, n0g);
+        else rp_tma_load(slot + warp * 1024, map, bar, n0g, 32 * warp);
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+      }
+    }
+    if (!jb.bkm) {
+      if (tid < (1 << cl)) cp_async16(eps + (tid << 2), base + jb.bias + n0g + (tid << 2), 16);
+    } else if (tid < (RP_RB << cl)) {
+      const int m = tid >> cl, cc = (tid & ((1 << cl) - 1)) << 2;
+      const bool ok = c.row0 + m < B;
+      cp_async16(eps + m * NS + cc, ok ? base + jb.aux + (i64)(c.row0 + m) * jb.aux_ld + n0g + cc : base, ok ? 16 : 0);
+    }
+  } else if (!jb.bkm) {
     const int ldw = jb.Kp + 4;
     const bool vec = ((jb.K & 3) == 0) && ((jb.w & 3) == 0) && ((jb.w_ld & 3) == 0);
     if (vec) {
@@ -248,6 +297,53 @@ __device__ __forceinline__ void rp_job_math(const RpJob& jb, uint32_t As, int ld
   }
   uint32_t ao = 32u * (uint32_t)ks0, bo = bstep * (uint32_t)ks0;
   int ks = ks0;
+  if (jb.tma) {
+    // 128B-swizzled tiles (NS = 32). forward: slab (ks >> 2) of [32 rows n][32 floats k], element (n, kk) in 16-byte chunk
+    // (kk >> 2) ^ (n & 7); backward: [K rows][32 floats n], element (k, n) in chunk (n >> 2) ^ (k & 7)
+    const uint32_t nrow = (uint32_t)(n0 + g);
+    if (!jb.bkm) {
+      const uint32_t rowb = nrow * 128u + 4u * (uint32_t)t;
+      while (ks < ks1) {
+        const uint32_t sl = Bs + (uint32_t)(ks >> 2) * 4096u + rowb;
+        if ((ks & 3) == 0 && ks + 4 <= ks1) {          // a whole slab: four k-steps at fixed offsets
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a[4] = {rp_lds(a0p + ao + 32u * q), rp_lds(a1p + ao + 32u * q), rp_lds(a0p + ao + 32u * q + 16u), rp_lds(a1p + ao + 32u * q + 16u)};
+            const float b[2] = {rp_lds(sl + (((uint32_t)(2 * q) ^ (uint32_t)g) << 4)), rp_lds(sl + (((uint32_t)(2 * q + 1) ^ (uint32_t)g) << 4))};
+            if (q & 1) rp_mma3(d0, d1, d2, a, b);
+            else rp_mma3(c0, c1, c2, a, b);
+          }
+          ao += 128u; ks += 4;
+        } else {
+          const uint32_t ch = (uint32_t)(ks & 3) * 2u;
+          const float a[4] = {rp_lds(a0p + ao), rp_lds(a1p + ao), rp_lds(a0p + ao + 16u), rp_lds(a1p + ao + 16u)};
+          const float b[2] = {rp_lds(sl + ((ch ^ (uint32_t)g) << 4)), rp_lds(sl + (((ch + 1u) ^ (uint32_t)g) << 4))};
+          if (ks & 1) rp_mma3(d0, d1, d2, a, b);
+          else rp_mma3(c0, c1, c2, a, b);
+          ao += 32u; ++ks;
+        }
+      }
+    } else {
+      const uint32_t nc = nrow >> 2, w = 4u * (nrow & 3u);
+      const uint32_t off0 = (uint32_t)t * 128u + ((nc ^ (uint32_t)t) << 4) + w, off1 = (uint32_t)(t + 4) * 128u + ((nc ^ (uint32_t)(t + 4)) << 4) + w;
+      uint32_t kb = Bs + (uint32_t)ks * 1024u;
+      for (; ks + 1 < ks1; ks += 2) {
+        const float a[4] = {rp_lds(a0p + ao), rp_lds(a1p + ao), rp_lds(a0p + ao + 16u), rp_lds(a1p + ao + 16u)};
+        const float b[2] = {rp_lds(kb + off0), rp_lds(kb + off1)};
+        const float a2[4] = {rp_lds(a0p + ao + 32u), rp_lds(a1p + ao + 32u), rp_lds(a0p + ao + 48u), rp_lds(a1p + ao + 48u)};
+        const float b2[2] = {rp_lds(kb + 1024u + off0), rp_lds(kb + 1024u + off1)};
+        rp_mma3(c0, c1, c2, a, b);
+        rp_mma3(d0, d1, d2, a2, b2);
+        ao += 64u; kb += 2048u;
+      }
+      if (ks < ks1) {
+        const float a[4] = {rp_lds(a0p + ao), rp_lds(a1p + ao), rp_lds(a0p + ao + 16u), rp_lds(a1p + ao + 16u)};
+        const float b[2] = {rp_lds(kb + off0), rp_lds(kb + off1)};
+        rp_mma3(c0, c1, c2, a, b);
+        ++ks;
+      }
+    }
+  }
   for (; ks + 1 < ks1; ks += 2) {
     const float a[4] = {rp_lds(a0p + ao), rp_lds(a1p + ao), rp_lds(a0p + ao + 16u), rp_lds(a1p + ao + 16u)};
     const float b[2] = {rp_lds(bp + bo), rp_lds(bp + bo + b4)};
@@ -730,6 +826,7 @@ __device__ __noinline__ void rp_pi_bwd(const RpCtx& c) {
 // ---- the step interpreter ---------------------------------------------------------------------------------------------
 struct RpSync {            // barrier state that lives across phases and updates
   unsigned gepoch;         // group barrier epoch
+  unsigned wphase;         // parity bit per weight slot (TMA mbarriers)
 };
 
 __device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, RpSync& sy) {
@@ -739,7 +836,7 @@ __device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, RpS
   float* wring = smem_raw + P.sm_wslot;
   const int B = c.args->hp.B;
   for (int j = jbeg; j < jbeg + 2; ++j) {
-    if (j < jend) rp_issue_job(P.jobs[j], wring + (j % RP_NWSLOT) * P.wslot_floats, c);
+    if (j < jend) rp_issue_job(P.jobs[j], wring + (j % RP_NWSLOT) * P.wslot_floats, c, j % RP_NWSLOT);
     cp_async_commit();
   }
   for (int s = s0; s < s1; ++s) {
@@ -766,10 +863,14 @@ __device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, RpS
     for (int j = st.job0; j < st.job0 + st.njobs; ++j) {
       const int sl = j % RP_NWSLOT;
       cp_async_wait<1>();                      // this thread's share of job j has landed (job j + 1 may still be in flight)
+      if (P.jobs[j].tma) {                     // ... and the TMA-staged weight slice
+        rp_mbar_wait(c.wbar + sl, (sy.wphase >> sl) & 1u);
+        sy.wphase ^= 1u << sl;
+      }
       __syncthreads();                         // ... everyone's has; and everyone is done with job j - 1
       RP_TRACE(3500);
       // slot of job j + 2 == slot of job j - 1: free now
-      if (j + 2 < jend) rp_issue_job(P.jobs[j + 2], wring + ((j + 2) % RP_NWSLOT) * P.wslot_floats, c);
+      if (j + 2 < jend) rp_issue_job(P.jobs[j + 2], wring + ((j + 2) % RP_NWSLOT) * P.wslot_floats, c, (j + 2) % RP_NWSLOT);
       cp_async_commit();
       RP_TRACE(4000 + j);
       const RpJob jb = P.jobs[j];
@@ -792,7 +893,13 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   __shared__ Op sops[RP_MAX_DW_OPS];
   __shared__ Phase sphase[2];
   __shared__ RpTrace trace;
+  __shared__ __align__(8) uint64_t wbar[RP_NWSLOT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < RP_NWSLOT; ++i) rp_mbar_init(&wbar[i], 8);      // one arrival per warp and job
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (args.rp_maps && (((uint32_t)__cvta_generic_to_shared(smem_raw)) & 1023u)) __trap();   // swizzled tiles need 1024 B alignment
+  }
   {
     const int* src = reinterpret_cast<const int*>(gprog);
     int* dst = reinterpret_cast<int*>(&sprog);
@@ -809,14 +916,14 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   float* base = args.arena;
   AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
   const int B = args.hp.B, nrb = (B + RP_RB - 1) / RP_RB;
-  RpCtx c{base, scal, &args, &sprog, &rows, args.rp_part + (i64)gid * sprog.part_stride, args.barrier + 64 * (1 + gid), rank, 0, 0, &trace};
+  RpCtx c{base, scal, &args, &sprog, &rows, args.rp_part + (i64)gid * sprog.part_stride, args.barrier + 64 * (1 + gid), rank, 0, 0, &trace, wbar};
   // dW phases reuse the tile code of the tile-parallel kernel; their shared memory aliases the row-parallel buffers
   float* wsm = smem_raw;
   float* gsm = smem_raw + WSM_FLOATS;
   RowCtx rc{base, scal, &args, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};
   EpiCtx ec{base, scal, &args.hp, nullptr, gsm + CfgSmall::SMEM_FLOATS};
   unsigned epoch = 0;
-  RpSync sy{0u};
+  RpSync sy{0u, 0u};
   unsigned* counter = args.barrier;
   const int sa = sprog.n_steps_a, sc = sprog.n_steps_c;
   for (int step = 0; step < args.n_steps; ++step) {

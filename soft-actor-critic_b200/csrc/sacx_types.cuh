@@ -114,6 +114,7 @@ struct RunArgs {
   int barrier_mode;
   int tc_skip;               // 1: GEMM ops marked for the tensor-core path (op.cfg & 2) are run by sacx_tc_kernel, skip them here
   float* rp_part;            // row-parallel kernel: partial-sum scratch [groups][part_stride]
+  const void* rp_maps;       // row-parallel kernel: device array of CUtensorMap (128 B each) for the TMA-staged weight slices, or null
   Hyper hp;
 };
 
