@@ -196,11 +196,11 @@ __device__ __forceinline__ void rp_issue_job(const RpJob& jb, float* __restrict_
   if (jb.tma) {
     if (lane == 0) {
       // one 32 x 32 tile (4 KB) per warp: the issue cost (~100 cycles per tile on the TMA queue) is spread over the warps.
-      // The slot was last read with ordinary loads (the caller's barrier ordered them): fence towards the async proxy.
+      // The slot was last READ with ordinary loads, all complete before the caller's barrier -- the usual consumer-release /
+      // producer-acquire pattern of TMA pipelines, no proxy fence (it would also wait for the cp.async copies in flight).
       uint64_t* bar = c.wbar + slot_idx;
       const int slabs = (jb.K + 31) >> 5;                  // K <= 256: at most 8
       if (warp < slabs) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const char* map = reinterpret_cast<const char*>(c.args->rp_maps) + (size_t)jb.map * 128;
         rp_mbar_expect_tx(bar, 4096u);
         if (!jb.bkm) rp_tma_load(slot + warp * 1024, map, bar, 32 * warp, n0g);
@@ -408,6 +408,12 @@ __device__ __forceinline__ void rp_job(const RpJob& jb, const RpCtx& c, int wslo
       // share of CTA `rank` goes to [rank][m][j] of the group's scratch, summed in rank order by every reader
       const int lpr = NS >> 1, r = (tid & 31) & (lpr - 1);
       float* dst = c.part + P.part_off[jb.proj_slot] + (c.rank * RP_RB + m) * J;
+      if (J == 1) {                    // critic heads: one weight vector, one butterfly
+        const float2 w = *reinterpret_cast<const float2*>(pws + n);
+        float p1 = fmaf(v.x, w.x, v.y * w.y);
+        for (int o = lpr >> 1; o > 0; o >>= 1) p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+        if (r == 0) dst[0] = p1;
+      } else
       for (int j0 = 0; j0 < J; j0 += 8) {
         float p[8];
 #pragma unroll
