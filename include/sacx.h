@@ -121,6 +121,9 @@ int sacx_ring_flush(sacx_ring_t r);
 /* replaces ReplayBuffer.__len__ (replay_buffer.py:41-42) */
 int64_t sacx_ring_len(sacx_ring_t r, int32_t agent);
 int64_t sacx_ring_pushes(sacx_ring_t r, int32_t agent);
+/* exact resume (no reference counterpart: the reference cannot resume a run): after a saved ring image has
+ * been copied back into the ring's device block, re-read the per-agent push counters from the ring headers */
+int sacx_ring_resync(sacx_ring_t r);
 /* replaces ReplayBuffer.sample + SAC.sample_batch (replay_buffer.py:32-39, agent.py:166-193) for a
  * caller-supplied LOGICAL index stream (== random.sample(range(len), B)).  Outputs nullable.
  * SACX_ERR_UNDERFILLED when len < B; SACX_ERR_INVALID when an index is out of range (host variant). */
@@ -159,6 +162,8 @@ int sacx_agent_path(sacx_agent_t h, char* reason, int32_t capacity);
  * default 4096: 3xTF32 tiles with TMEM accumulators, TMA-staged operands; sacx_tc.cuh), 0 otherwise (reason, may be NULL,
  * says why). tc_launches (may be NULL) receives the number of tensor-core kernel launches so far. */
 int sacx_agent_tc(sacx_agent_t h, char* reason, int32_t capacity, int64_t* tc_launches);
+/* counter of the rollout-noise stream (sacx_act with eps == NULL); set_to >= 0 overwrites it (exact-resume snapshot) */
+int64_t sacx_agent_act_counter(sacx_agent_t h, int64_t set_to);
 
 /* replaces SAC.training_step (agent.py:302-327), n_steps consecutive updates in ONE launch of the
  * persistent fused kernel: gather -> target -> critic Adam x2 -> actor Adam -> alpha -> Polyak.
@@ -208,6 +213,11 @@ int sacx_apply_grads(sacx_agent_t h, int32_t which, int32_t polyak);
 /* SAC.select_action (agent.py:149-156) / PolicyNetwork.deterministic_action (models.py:89-92) */
 int sacx_act(sacx_agent_t h, int32_t agent, const float* s_dev, int32_t n, const float* eps_dev /* nullable */,
              int32_t deterministic, float* a_dev);
+/* vectorised rollouts of a population: the action of every agent's policy on its own n_per_agent states in
+ * ONE launch. s_dev [n_agents, n_per_agent, obs], eps_dev [n_agents, n_per_agent, act] or NULL (device Philox),
+ * a_out_dev [n_agents, n_per_agent, act]; same arithmetic as sacx_act (agent.py:149-156 per agent). */
+int sacx_act_population(sacx_agent_t h, const float* s_dev, int32_t n_per_agent, const float* eps_dev /* nullable */,
+                        int32_t deterministic, float* a_out_dev);
 int sacx_act_host(sacx_agent_t h, int32_t agent, const float* s_host, int32_t n, const float* eps_host /* nullable */,
                   int32_t deterministic, float* a_host);
 /* the two critic forwards of SAC._log_q_values (agent.py:493-500) */

@@ -599,6 +599,30 @@ int sacx_ring_flush(sacx_ring_t h) { return h ? h->r.flush() : fail(SACX_ERR_INV
 int64_t sacx_ring_len(sacx_ring_t h, int32_t agent) { return (h && agent >= 0 && agent < h->r.n_agents) ? h->r.len(agent) : -1; }
 int64_t sacx_ring_pushes(sacx_ring_t h, int32_t agent) { return (h && agent >= 0 && agent < h->r.n_agents) ? h->r.pushes[agent] : -1; }
 
+// exact resume: after the caller has copied a saved ring image back into the device block, re-derive the
+// host-side push counters from the ring headers (RingMeta.pushes of every agent)
+int sacx_ring_resync(sacx_ring_t h) {
+  if (!h) return fail(SACX_ERR_INVALID, "null ring");
+  Ring& r = h->r;
+  int rc = r.flush();
+  if (rc) return rc;
+  SACX_CUDA(cudaStreamSynchronize(r.stream));
+  for (int ag = 0; ag < r.n_agents; ++ag) {
+    RingMeta m;
+    SACX_CUDA(cudaMemcpy(&m, r.dev + (i64)ag * r.stride, sizeof m, cudaMemcpyDeviceToHost));
+    if (m.pushes < 0) return fail(SACX_ERR_INVALID, "ring_resync: corrupt ring header");
+    r.pushes[ag] = m.pushes;
+  }
+  return SACX_OK;
+}
+
+// rollout-noise counter of the engine (device Philox stream of sacx_act): part of an exact-resume snapshot
+int64_t sacx_agent_act_counter(sacx_agent_t h, int64_t set_to) {
+  if (!h) return -1;
+  if (set_to >= 0) h->e.act_calls = (unsigned long long)set_to;
+  return (int64_t)h->e.act_calls;
+}
+
 int sacx_ring_gather(sacx_ring_t h, int32_t agent, const int64_t* idx_dev, int32_t B, float* s, float* a, float* rr, float* s2, float* d) {
   if (!h || !idx_dev || B <= 0) return fail(SACX_ERR_INVALID, "ring_gather: bad arguments");
   Ring& r = h->r;
@@ -1097,9 +1121,22 @@ int sacx_act(sacx_agent_t h, int32_t agent, const float* s, int32_t n, const flo
   Engine& e = h->e;
   if (agent < 0 || agent >= e.cfg.n_agents) return fail(SACX_ERR_INVALID, "act: agent out of range");
   const int mw = max_width(e.pi);
-  act_kernel<<<n, 256, (size_t)2 * mw * 4, e.stream>>>(e.arena + (i64)agent * e.stride, make_ref(e.pi, 0), mw, s, eps, deterministic,
+  act_kernel<<<n, 256, (size_t)2 * mw * 4, e.stream>>>(e.arena, make_ref(e.pi, 0), mw, s, eps, deterministic,
                                                       a_out, e.cfg.act_dim, e.hp.log_std_min, e.hp.log_std_max, e.hp.action_scale,
-                                                      e.hp.seed, e.act_calls++, agent);
+                                                      e.hp.seed, e.act_calls++, agent, e.stride);
+  ++e.launches;
+  SACX_CUDA(cudaGetLastError());
+  return SACX_OK;
+}
+
+int sacx_act_population(sacx_agent_t h, const float* s, int32_t n_per_agent, const float* eps, int32_t deterministic, float* a_out) {
+  if (!h || !s || !a_out || n_per_agent <= 0) return fail(SACX_ERR_INVALID, "act_population: bad arguments");
+  Engine& e = h->e;
+  if (e.cfg.n_agents > 65535) return fail(SACX_ERR_INVALID, "act_population: more than 65535 agents");
+  const int mw = max_width(e.pi);
+  act_kernel<<<dim3(n_per_agent, e.cfg.n_agents), 256, (size_t)2 * mw * 4, e.stream>>>(
+      e.arena, make_ref(e.pi, 0), mw, s, eps, deterministic, a_out, e.cfg.act_dim, e.hp.log_std_min, e.hp.log_std_max, e.hp.action_scale,
+      e.hp.seed, e.act_calls++, 0, e.stride);
   ++e.launches;
   SACX_CUDA(cudaGetLastError());
   return SACX_OK;

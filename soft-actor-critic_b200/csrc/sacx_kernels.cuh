@@ -334,11 +334,14 @@ __device__ __forceinline__ const float* mlp_row(const float* __restrict__ base, 
 __global__ void act_kernel(const float* __restrict__ base, NetRef net, int maxw, const float* __restrict__ s,
                            const float* __restrict__ eps, int deterministic, float* __restrict__ a_out, int A,
                            float lo, float hi, float scale, unsigned long long seed, unsigned long long counter,
-                           int agent) {
+                           int agent0, i64 agent_stride) {
+  // grid (rows per agent, agents): blockIdx.y walks a population (vectorised rollouts: one launch for every agent's action)
   extern __shared__ float sm[];
   float* b0 = sm;
   float* b1 = sm + maxw;
-  const int row = blockIdx.x;
+  const int agent = agent0 + blockIdx.y;
+  base += (i64)agent * agent_stride;
+  const int row = blockIdx.y * gridDim.x + blockIdx.x;
   for (int k = threadIdx.x; k < net.in_dim; k += blockDim.x) b0[k] = s[(i64)row * net.in_dim + k];
   __syncthreads();
   const float* head = mlp_row(base, net, b0, b1);
@@ -350,7 +353,7 @@ __global__ void act_kernel(const float* __restrict__ base, NetRef net, int maxw,
     } else {
       const float ls = fminf(fmaxf(head[A + j], lo), hi);
       const float e = eps ? eps[(i64)row * A + j]
-                          : philox_normal(seed, counter, 3, (uint32_t)row, (uint32_t)j, (uint32_t)agent);
+                          : philox_normal(seed, counter, 3, (uint32_t)blockIdx.x, (uint32_t)j, (uint32_t)agent);
       v = tanhf(mu + e * expf(ls)) * scale;                      // models.py:79-84
     }
     a_out[(i64)row * A + j] = v;

@@ -82,6 +82,7 @@ SYMBOLS = {
     "sacx_ring_pushes": (_I64, [_P, _I32]),
     "sacx_ring_gather": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "sacx_ring_gather_host": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _P]),
+    "sacx_ring_resync": (C.c_int, [_P]),
     "sacx_ring_sample_indices": (C.c_int, [_P, _I32, _U64, _U64, _I32, _P]),
     "sacx_agent_arena_floats": (C.c_int, [C.POINTER(SacxConfig), C.POINTER(_I64)]),
     "sacx_agent_create": (C.c_int, [C.POINTER(SacxConfig), _P, C.POINTER(_P)]),
@@ -95,6 +96,7 @@ SYMBOLS = {
     "sacx_agent_refresh_alpha": (C.c_int, [_P]),
     "sacx_agent_grid": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32)]),
     "sacx_agent_path": (C.c_int, [_P, C.c_char_p, _I32]),
+    "sacx_agent_act_counter": (_I64, [_P, _I64]),
     "sacx_agent_tc": (C.c_int, [_P, C.c_char_p, _I32, C.POINTER(_I64)]),
     "sacx_update": (C.c_int, [_P, _P, _P, _P, _I32]),
     "sacx_update_host": (C.c_int, [_P, _P, _P, _P, _I32, C.POINTER(SacxMetrics)]),
@@ -112,6 +114,7 @@ SYMBOLS = {
     "sacx_actor_grads": (C.c_int, [_P, _P, _P]),
     "sacx_apply_grads": (C.c_int, [_P, _I32, _I32]),
     "sacx_act": (C.c_int, [_P, _I32, _P, _I32, _P, _I32, _P]),
+    "sacx_act_population": (C.c_int, [_P, _P, _I32, _P, _I32, _P]),
     "sacx_act_host": (C.c_int, [_P, _I32, _P, _I32, _P, _I32, _P]),
     "sacx_q_values": (C.c_int, [_P, _I32, _P, _P, _I32, _P, _P]),
     "sacx_q_values_host": (C.c_int, [_P, _I32, _P, _P, _I32, _P, _P]),

@@ -424,6 +424,54 @@ class SAC:
             ck["alpha_optimizer_state_dict"] = snap_opt(self.alpha_optimizer)
         torch.save(ck, filepath)
 
+    # ------------------------------------------------------------------ exact resume (the reference cannot)
+    def save_snapshot(self, filepath: str) -> None:
+        """Everything a bit-exact continuation needs: the engine's scalar / parameter / optimiser / target blocks as one
+        arena slice, the replay ring image, the rollout-noise counter and the host generators the host-RNG path consumes
+        (Python ``random``, torch CPU, numpy). ``save_agent`` stays the reference-compatible checkpoint."""
+        import random
+        self.engine.sync()
+        eng = self.engine
+        end = eng.layout["block.targets"][0] + eng.layout["block.targets"][2]       # scalars | params | m | v | g | targets
+        snap = {
+            "format": "sacx-snapshot-1",
+            "arena_head": eng.arena[:end].detach().cpu(),
+            "act_counter": int(eng.lib.sacx_agent_act_counter(eng.h, -1)),
+            "seed": int(self.config["train"]["seed"]),          # keys the device index / normal streams
+            "ring": self.replay_buffer.image() if self.replay_buffer.handle is not None else None,
+            "ring_dims": (self.replay_buffer.capacity, self.replay_buffer.obs_dim, self.replay_buffer.act_dim),
+            "python_random": random.getstate(),
+            "torch_rng": torch.get_rng_state(),
+            "numpy_rng": np.random.get_state(),
+        }
+        torch.save(snap, filepath)
+
+    def load_snapshot(self, filepath: str) -> None:
+        import random
+        snap = torch.load(filepath, map_location="cpu", weights_only=False)
+        if snap.get("format") != "sacx-snapshot-1":
+            raise ValueError("not a sacx snapshot")
+        if int(snap["seed"]) != int(self.config["train"]["seed"]):
+            raise ValueError("snapshot was taken with train.seed=%d: build the agent from the same config to resume" % snap["seed"])
+        eng = self.engine
+        eng.sync()
+        head = snap["arena_head"]
+        end = eng.layout["block.targets"][0] + eng.layout["block.targets"][2]
+        if head.numel() != end:
+            raise ValueError("snapshot was taken with different network shapes")
+        eng.arena[:end].copy_(head.to(eng.arena.device))
+        eng.lib.sacx_agent_act_counter(eng.h, int(snap["act_counter"]))
+        if snap["ring"] is not None:
+            cap, od, ad = snap["ring_dims"]
+            if self.replay_buffer.handle is None:
+                self.replay_buffer._allocate(int(od), int(ad))
+                self.engine.attach_ring(self.replay_buffer)
+            self.replay_buffer.load_image(snap["ring"])
+        random.setstate(snap["python_random"])
+        torch.set_rng_state(snap["torch_rng"])
+        np.random.set_state(snap["numpy_rng"])
+        eng.sync()
+
     def load_agent(self, filepath: str) -> None:
         ck = torch.load(filepath, map_location=self.device)
         self.engine.sync()

@@ -197,6 +197,16 @@ class UpdateEngine:
         E.check(self.lib.sacx_act(self.h, agent, s.data_ptr(), s.shape[0], E.ptr(eps), 1 if deterministic else 0, out.data_ptr()))
         return out
 
+    def act_population(self, states: torch.Tensor, eps: Optional[torch.Tensor] = None, deterministic: bool = False) -> torch.Tensor:
+        """states [n_agents, n, obs] (device) -> actions [n_agents, n, act]: every agent's policy on its own states, one launch."""
+        self._sync_stream()
+        s = states.to(device=self.device, dtype=torch.float32).contiguous().view(self.n_agents, -1, self.obs_dim)
+        n = s.shape[1]
+        out = torch.empty(self.n_agents, n, self.act_dim, device=self.device, dtype=torch.float32)
+        e = None if eps is None else eps.to(device=self.device, dtype=torch.float32).contiguous()
+        E.check(self.lib.sacx_act_population(self.h, E.ptr(s), n, E.ptr(e), 1 if deterministic else 0, E.ptr(out)))
+        return out
+
     def act_host(self, state: np.ndarray, eps: Optional[np.ndarray] = None, deterministic: bool = False, agent: int = 0) -> np.ndarray:
         self._sync_stream()
         s = np.ascontiguousarray(state, dtype=np.float32).reshape(-1, self.obs_dim)

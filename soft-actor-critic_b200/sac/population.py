@@ -110,6 +110,13 @@ class SACPopulation:
         """n_steps updates of every local agent: one kernel launch, no collective."""
         self.engine.update(None, None, None, n_steps)
 
+    def act_all(self, states, deterministic: bool = False, eps=None) -> torch.Tensor:
+        """One action per local agent from its own observation (vectorised envs): states [n_local, obs] (numpy or tensor) ->
+        device tensor [n_local, act]; one kernel launch for the whole population (reference: select_action per agent,
+        agent.py:149-156)."""
+        s = torch.as_tensor(np.asarray(states, np.float32) if not torch.is_tensor(states) else states)
+        return self.engine.act_population(s.view(self.n_local, 1, self.obs_dim), eps, deterministic)[:, 0, :]
+
     def act(self, agent: int, state, deterministic: bool = False) -> np.ndarray:
         return self.engine.act_host(np.asarray(state, np.float32), None, deterministic, agent=agent)[0]
 

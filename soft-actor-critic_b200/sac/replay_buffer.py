@@ -185,6 +185,21 @@ class ReplayBuffer:
         s, a, r, s2, d = self.gather_host(idx)
         return [Transition(s[i], a[i], float(r[i]), s2[i], bool(d[i] != 0.0)) for i in range(batch_size)]
 
+    # ------------------------------------------------------------------ exact-resume image
+    def image(self) -> torch.Tensor:
+        """The whole ring (headers with the push counters + SoA fields) as one CPU tensor."""
+        E.check(self._lib.sacx_ring_flush(self._h))
+        torch.cuda.synchronize(self.device)
+        return self._store.detach().cpu()
+
+    def load_image(self, img: torch.Tensor) -> None:
+        if self._h is None or img.numel() != self._store.numel():
+            raise ValueError("ring image does not match this buffer (capacity / obs_dim / act_dim / n_agents)")
+        E.check(self._lib.sacx_ring_flush(self._h))
+        self._store.copy_(img.to(self.device))
+        torch.cuda.synchronize(self.device)
+        E.check(self._lib.sacx_ring_resync(self._h))
+
     # ------------------------------------------------------------------ fast paths
     def gather_host(self, logical_idx: Sequence[int], agent: int = 0):
         idx = np.ascontiguousarray(logical_idx, dtype=np.int64)

@@ -229,3 +229,65 @@ def test_gradient_steps_burst_and_push_device():
     l0 = agent.engine.launch_count()
     agent.training_steps(5)
     assert agent.last_metrics()["updates"] == 5 and agent.engine.launch_count() - l0 == 1
+
+
+def test_snapshot_resumes_bit_exactly(tmp_path):
+    """save_snapshot / load_snapshot (arena head + ring image + RNG states) -- a fresh agent that loads the
+    snapshot continues exactly like the original: same parameters after M more updates, in both RNG modes, and the same
+    rollout actions."""
+    import random
+    from gpu_helpers import FakeEnv, base_config
+    from helpers import synth_transitions
+    from sac.agent import SAC
+    obs, act = 6, 2
+    for mode in ("device", "host"):
+        cfg = base_config(hidden=(64, 64), batch=64, capacity=500, rng=mode)
+        a = SAC(FakeEnv(obs, act), cfg)
+        s, ac, r, s2, d = synth_transitions(700, obs, act, 4)          # wraps the 500-slot ring
+        for i in range(700):
+            a.store_transition(s[i], ac[i], float(r[i]), s2[i], bool(d[i]))
+        random.seed(3); torch.manual_seed(3)
+        for _ in range(5):
+            a.training_step()
+        a.select_action(s[0])                                            # advances the rollout-noise counter
+        path = str(tmp_path / f"snap_{mode}.pt")
+        a.save_snapshot(path)
+        for _ in range(4):
+            a.training_step()
+        act_a = a.select_action(s[1])
+        with pytest.raises(ValueError):
+            SAC(FakeEnv(obs, act), base_config(hidden=(64, 64), batch=64, capacity=500, rng=mode, seed=9)).load_snapshot(path)
+        b = SAC(FakeEnv(obs, act), cfg)
+        b.engine.view("block.params").mul_(1.7)                          # a state that is nothing like the snapshot's
+        for i in range(80):
+            b.store_transition(s[i] * 3, ac[i], 1.0, s2[i], False)
+        b.training_step()
+        b.load_snapshot(path)
+        assert len(b.replay_buffer) == 500
+        for _ in range(4):
+            b.training_step()
+        act_b = b.select_action(s[1])
+        for n in ("block.params", "block.targets", "block.m", "block.v"):
+            assert torch.equal(a.engine.view(n), b.engine.view(n)), (mode, n)
+        assert float(a.engine.view("scal.log_alpha")) == float(b.engine.view("scal.log_alpha"))
+        assert int(a.engine.view("scal.updates")) == int(b.engine.view("scal.updates")) == 9
+        assert np.array_equal(act_a, act_b)
+
+
+def test_population_act_all_matches_per_agent_act():
+    """one launch returns every agent's action on its own observation; equal to per-agent sacx_act."""
+    from gpu_helpers import base_config
+    from sac.population import SACPopulation
+    obs, act, n = 5, 3, 7
+    pop = SACPopulation(obs, act, base_config(hidden=(32, 48), batch=16, capacity=100), n, reference_init=True)
+    rng = np.random.default_rng(0)
+    states = rng.standard_normal((n, obs)).astype(np.float32)
+    det = pop.act_all(states, deterministic=True).cpu().numpy()
+    for ag in range(n):
+        assert np.array_equal(det[ag], pop.act(ag, states[ag], deterministic=True))
+    eps = torch.as_tensor(rng.standard_normal((n, 1, act)).astype(np.float32)).cuda()
+    sto = pop.act_all(states, deterministic=False, eps=eps).cpu().numpy()
+    for ag in range(n):
+        one = pop.engine.act(torch.as_tensor(states[ag:ag + 1]).cuda(), eps[ag], deterministic=False, agent=ag).cpu().numpy()[0]
+        assert np.array_equal(sto[ag], one)
+    assert np.all(np.abs(sto) <= 1.0) and not np.array_equal(det, sto)
