@@ -175,6 +175,7 @@ struct Engine {
       sub("scal.alpha", offsetof(AgentScalars, alpha), 1, 1);
       sub("scal.step", offsetof(AgentScalars, step), N_OPT, 2);
       sub("scal.updates", offsetof(AgentScalars, updates), 1, 2);
+      sub("scal.alpha_lr", offsetof(AgentScalars, alpha_lr), 1, 1);
       sub("scal.alpha_f32", offsetof(AgentScalars, alpha_f32), 1, 0);
       sub("scal.metrics", offsetof(AgentScalars, metrics), 12, 0);
       sub("scal.nonfinite", offsetof(AgentScalars, nonfinite), 1, 0);
@@ -977,6 +978,7 @@ struct Engine {
     if (cfg.n_agents > 1) {      // population: every agent contributes >= one 128-row tile; enough agents to fill the chip
       const char* pe = getenv("SACX_TC_POP");
       if (pe && atoi(pe) == 0) { why = "disabled by SACX_TC_POP=0"; return false; }
+      if (cfg.n_agents > 65535) { why = "more than 65535 agents (grid.z of the dW reduce kernel)"; return false; }
       if (cfg.batch_size < 128 || (long long)cfg.n_agents * cfg.batch_size < 4LL * tc_min_batch) {
         why = "population too small for the tensor-core path"; return false;
       }

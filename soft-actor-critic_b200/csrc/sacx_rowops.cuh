@@ -614,7 +614,8 @@ __device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int
       s->alpha_v = s->alpha_v * 0.999 + (1.0 - 0.999) * g * g;
       const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
       const double denom = sqrt(s->alpha_v) / sqrt(bc2) + 1e-8;
-      s->log_alpha = s->log_alpha - (hp.alpha_lr / bc1) * (s->alpha_m / denom);
+      const double alr = s->alpha_lr > 0.0 ? s->alpha_lr : hp.alpha_lr;      // per-agent override (Optuna trials as a population)
+      s->log_alpha = s->log_alpha - (alr / bc1) * (s->alpha_m / denom);
       s->alpha = exp(s->log_alpha);
       s->alpha_f32 = (float)s->alpha;
       s->metrics[3] = -mean_lt;

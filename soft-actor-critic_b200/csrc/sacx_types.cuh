@@ -65,7 +65,7 @@ struct AgentScalars {
   double log_alpha, alpha_m, alpha_v, alpha;         // F6: float64 temperature state
   i64 step[N_OPT];                                   // Adam step counters (pi, q1, q2, alpha)
   i64 updates;                                       // completed updates (device RNG counter)
-  i64 reserved;
+  double alpha_lr;                                   // per-agent temperature learning rate (population of trials); 0: Hyper.alpha_lr
   float alpha_f32;                                   // alpha as used by target/actor (F5)
   float adam_step_size[3];                           // lr / (1 - beta1^t)      per optimiser
   float adam_bc2_sqrt[3];                            // sqrt(1 - beta2^t)

@@ -110,6 +110,32 @@ class SACPopulation:
         """n_steps updates of every local agent: one kernel launch, no collective."""
         self.engine.update(None, None, None, n_steps)
 
+    # ------------------------------------------------------------------ trials (SURVEY 8f-2)
+    def set_trial(self, agent: int, alpha: Optional[float] = None, alpha_lr: Optional[float] = None) -> None:
+        """Per-agent values of the two hyper-parameters the reference's Optuna study searches
+        (hparam_search/configs/search_space.yaml: ``sac.alpha``, ``sac.alpha_lr``): the initial temperature and the
+        temperature optimiser's learning rate of local agent `agent`. Call before the first update."""
+        import math
+        eng = self.engine
+        eng.sync()
+        if alpha is not None:
+            if not alpha > 0:
+                raise ValueError("alpha must be positive")
+            la = math.log(alpha)          # agent.py:49-50: log_alpha = log(alpha) in float64, alpha = exp(log_alpha)
+            eng.view("scal.log_alpha", agent).fill_(la)
+            eng.view("scal.alpha", agent).fill_(math.exp(la) if self.config["sac"]["auto_entropy_tuning"] else float(np.float32(alpha)))
+        if alpha_lr is not None:
+            eng.view("scal.alpha_lr", agent).fill_(float(alpha_lr))
+        eng.refresh_alpha()
+
+    def set_trials(self, trials: Sequence[Dict[str, float]]) -> None:
+        """trials[g] = {"alpha": ..., "alpha_lr": ...} for GLOBAL agent g (one Optuna trial per agent); this rank applies its
+        own block. The sequential `subprocess.run` loop of hparam_search/scripts/run_search.py:58-65 becomes one population."""
+        if len(trials) != self.n_agents_global:
+            raise ValueError("one trial per agent expected")
+        for a, g in enumerate(self.agent_ids):
+            self.set_trial(a, trials[g].get("alpha"), trials[g].get("alpha_lr"))
+
     def act_all(self, states, deterministic: bool = False, eps=None) -> torch.Tensor:
         """One action per local agent from its own observation (vectorised envs): states [n_local, obs] (numpy or tensor) ->
         device tensor [n_local, act]; one kernel launch for the whole population (reference: select_action per agent,

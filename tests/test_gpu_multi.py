@@ -161,3 +161,48 @@ def test_population_class_shards_and_matches_reference_init():
     assert set(sd) == {"policy_net_state_dict", "q_net1_state_dict", "q_net2_state_dict", "q_net1_target_state_dict", "q_net2_target_state_dict"}
     a = pops[0].act(0, S[0])
     assert a.shape == (g.act,) and np.all(np.abs(a) <= 1.0)
+
+
+def test_population_trials_match_single_agents_with_those_hyperparameters():
+    """the reference's Optuna study varies sac.alpha and sac.alpha_lr per trial
+    (hparam_search/configs/search_space.yaml). A population whose agents carry per-agent (alpha, alpha_lr) must follow, agent
+    by agent, a single-agent engine built from a config with those values (same weights, ring, indices and normals)."""
+    from sac.engine import UpdateEngine
+    from sac.population import SACPopulation
+    from sac.replay_buffer import ReplayBuffer
+    from test_gpu_parity import _random_nets
+    obs, act, B, K = 5, 2, 64, 3
+    trials = [{"alpha": 0.2, "alpha_lr": 3e-4}, {"alpha": 0.004, "alpha_lr": 2e-2}, {"alpha": 0.05, "alpha_lr": 1e-5}]
+    cfg = base_config(hidden=(64, 64), batch=B, capacity=600, alpha=0.2)
+    pop = SACPopulation(obs, act, cfg, len(trials), reference_init=False)
+    nets = _random_nets(obs, act, (64, 64), (64, 64), scale=0.2)
+    s, a, r, s2, d = synth_transitions(500, obs, act, 1)
+    for ag in range(len(trials)):
+        load_nets(pop.engine, nets, agent=ag)
+    pop.engine.reset_state()
+    pop.set_trials(trials)
+    for ag in range(len(trials)):
+        pop.ring.push_batch(s, a, r, s2, d.astype(np.float32), agent=ag)
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, 500, (K, len(trials), B)).astype(np.int64)
+    e1 = rng.standard_normal((K, len(trials), B, act)).astype(np.float32)
+    e2 = rng.standard_normal((K, len(trials), B, act)).astype(np.float32)
+    pop.engine.update(dev(idx), dev(e1), dev(e2), K)
+    pop.engine.sync()
+    la = []
+    for ag, t in enumerate(trials):
+        c1 = base_config(hidden=(64, 64), batch=B, capacity=600, alpha=t["alpha"])
+        c1["sac"]["alpha_lr"] = t["alpha_lr"]
+        one = UpdateEngine(obs, act, c1)
+        load_nets(one, nets)
+        one.reset_state()
+        rb = ReplayBuffer(600, obs, act)
+        rb.push_batch(s, a, r, s2, d.astype(np.float32))
+        one.attach_ring(rb)
+        one.update(dev(idx[:, ag]), dev(e1[:, ag]), dev(e2[:, ag]), K)
+        one.sync()
+        assert_close(f"agent {ag} params", pop.engine.view("block.params", ag).cpu().numpy(), one.view("block.params").cpu().numpy(), 3e-5)
+        got, want = float(pop.engine.view("scal.log_alpha", ag)), float(one.view("scal.log_alpha"))
+        assert abs(got - want) < 1e-6 * max(1.0, abs(want)), (ag, got, want)
+        la.append(got)
+    assert len({round(x, 6) for x in la}) == len(trials)              # the trials really differ
