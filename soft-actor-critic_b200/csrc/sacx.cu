@@ -305,7 +305,8 @@ static int engine_setup_tc(Engine* e) {
   {  // light row kernel: staging area for the widest head (falls back to global reads beyond 48 KB)
     const int A = e->cfg.act_dim, Kp = e->pi.dims[e->pi.L()], Kq = e->q1.dims[e->q1.L()], H0 = e->q1.dims[1];
     int need = std::max(std::max(2 * A * Kp + 2 * A, 4 * Kq), 2 * A * H0 + 2 * A * Kp);
-    e->rows_tsm_floats = std::min(rup(need, 4), 12288);
+    need = std::max(need, 64 * SMALLK_MAX);          // input tile of the small-K forward layers
+    e->rows_tsm_floats = std::max(std::min(rup(need, 4), 12288), 64 * SMALLK_MAX);
     e->rows_smem_bytes = (WSM_FLOATS + e->rows_tsm_floats) * 4;
     if (cudaFuncSetAttribute(sacx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->rows_smem_bytes) != cudaSuccess)
       return off("cannot size the row kernel's shared memory");

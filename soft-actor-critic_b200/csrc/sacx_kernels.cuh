@@ -125,25 +125,41 @@ __device__ __forceinline__ bool small_fwd_ok(const Op& o) {
   return o.type == OP_GEMM && o.epi == EPI_FWD && o.K <= SMALLK_MAX && o.zout < 0 && o.mode == 0 && o.i[4] == 0 && o.a_sk == 1 && o.b_sk == 1 &&
          o.cfg >= 1;
 }
-__device__ __forceinline__ void small_fwd_tile(const Op& op, float* __restrict__ base, int tile) {
+// K <= KB: the reduction is unrolled over KB register-resident weights; the tile's 64 input rows are staged (zero-padded to
+// KB) in shared memory first, so the inner loop has no global load and no predicate. (Profile history: one 32-wide bucket
+// ran 32 predicated steps per output for a K = 5 layer -- instruction-bound; per-row global loads -- latency-bound.)
+// Called by all 256 threads of the CTA (two barriers inside); xs: 64 * KB floats of shared memory.
+template <int KB>
+__device__ __forceinline__ void small_fwd_tile_k(const Op& op, float* __restrict__ base, int tile, float* __restrict__ xs) {
   const int tm = tile / op.tiles_n, tn = tile % op.tiles_n;
-  const int n = tn * 64 + (threadIdx.x & 63), m0 = tm * 64 + (threadIdx.x >> 6) * 16;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * KB; i += 256) {
+    const int r = i / KB, k = i % KB, m = tm * 64 + r;
+    xs[i] = (m < op.M && k < op.K) ? __ldcg(base + op.a + (i64)m * op.a_sm + k) : 0.f;
+  }
+  __syncthreads();
+  const int n = tn * 64 + (threadIdx.x & 63), r0 = (threadIdx.x >> 6) * 16;
   if (n >= op.N) return;
-  float w[SMALLK_MAX];
+  float w[KB];
 #pragma unroll
-  for (int k = 0; k < SMALLK_MAX; ++k) w[k] = (k < op.K) ? __ldg(base + op.b + (i64)n * op.b_sn + k) : 0.f;
+  for (int k = 0; k < KB; ++k) w[k] = (k < op.K) ? __ldg(base + op.b + (i64)n * op.b_sn + k) : 0.f;
   const float bias = __ldg(base + op.bias + n);
+  const int act = op.act;
 #pragma unroll 4
   for (int r = 0; r < 16; ++r) {
-    const int m = m0 + r;
+    const int m = tm * 64 + r0 + r;
     if (m >= op.M) break;
-    const float* x = base + op.a + (i64)m * op.a_sm;
+    const float* x = xs + (r0 + r) * KB;               // same address in every lane of the warp: broadcast
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < SMALLK_MAX; ++k)
-      if (k < op.K) s = fmaf(__ldcg(x + k), w[k], s);
-    base[op.c + (i64)m * op.ldc + n] = act_fwd(op.act, s + bias);
+    for (int k = 0; k < KB; ++k) s = fmaf(x[k], w[k], s);
+    base[op.c + (i64)m * op.ldc + n] = act == SACX_ACT_RELU ? fmaxf(s + bias, 0.f) : act_fwd(act, s + bias);
   }
+}
+__device__ __forceinline__ void small_fwd_tile(const Op& op, float* __restrict__ base, int tile, float* __restrict__ xs) {
+  if (op.K <= 8) small_fwd_tile_k<8>(op, base, tile, xs);
+  else if (op.K <= 16) small_fwd_tile_k<16>(op, base, tile, xs);
+  else small_fwd_tile_k<SMALLK_MAX>(op, base, tile, xs);
 }
 
 constexpr int ROWS_SMEM_OPS = 8;
@@ -178,7 +194,7 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
       rc.fresh = (oi != last_oi);          // head weights are staged once per (agent, op) run of tiles, not once per 8 rows
       last_oi = oi;
       switch (op.type) {
-        case OP_GEMM: if (!(op.cfg & 2) && small_fwd_ok(op)) small_fwd_tile(op, base, lt); break;
+        case OP_GEMM: if (!(op.cfg & 2) && small_fwd_ok(op)) { small_fwd_tile(op, base, lt, tsm); __syncthreads(); } break;
         case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
         case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); __syncthreads(); break;
         case OP_Q_ROW: tile_q_row<1>(op, rc, lt); __syncthreads(); break;
