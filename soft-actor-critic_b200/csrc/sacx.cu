@@ -305,8 +305,9 @@ static int engine_setup_tc(Engine* e) {
   {  // light row kernel: staging area for the widest head (falls back to global reads beyond 48 KB)
     const int A = e->cfg.act_dim, Kp = e->pi.dims[e->pi.L()], Kq = e->q1.dims[e->q1.L()], H0 = e->q1.dims[1];
     int need = std::max(std::max(2 * A * Kp + 2 * A, 4 * Kq), 2 * A * H0 + 2 * A * Kp);
-    need = std::max(need, 64 * SMALLK_MAX);          // input tile of the small-K forward layers
-    e->rows_tsm_floats = std::max(std::min(rup(need, 4), 12288), 64 * SMALLK_MAX);
+    const int small_floats = std::max(64 * SMALLK_MAX, 4 * 64 * (SMALLM_MAX + 1));      // small-K forward input tile / narrow dW reduction
+    need = std::max(need, small_floats);
+    e->rows_tsm_floats = std::max(std::min(rup(need, 4), 12288), small_floats);
     e->rows_smem_bytes = (WSM_FLOATS + e->rows_tsm_floats) * 4;
     if (cudaFuncSetAttribute(sacx_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->rows_smem_bytes) != cudaSuccess)
       return off("cannot size the row kernel's shared memory");
@@ -335,7 +336,12 @@ static int engine_setup_tc(Engine* e) {
             const Op& oo = pl.ops[i];
             const bool small_fwd = ty == OP_GEMM && oo.epi == EPI_FWD && oo.K <= SMALLK_MAX && oo.zout < 0 && oo.mode == 0 && oo.i[4] == 0 &&
                                    oo.a_sk == 1 && oo.b_sk == 1 && oo.cfg >= 1;      // the light kernel's small_fwd_tile (64x64 tile grid)
-            if ((ty == OP_GEMM && !small_fwd) || ty == OP_DW_HEAD || ty == OP_LOAD_EXT || ty == OP_NONE) tp.light = false;
+            const bool small_dw = ty == OP_GEMM && oo.epi == EPI_DW && oo.M <= SMALLM_MAX && oo.K <= SMALLDW_MAXK && oo.a_sm == 1 && oo.b_sn == 1 &&
+                                  oo.cfg >= 1 && !(oo.flags & DW_ATOMIC) && oo.i[0] <= 1;         // the light kernel's small_dw_tile
+            if ((ty == OP_GEMM && !small_fwd && !small_dw) || ty == OP_DW_HEAD || ty == OP_LOAD_EXT || ty == OP_NONE) tp.light = false;
+            if (pass == 1 && id == PLAN_FUSED && ty == OP_GEMM && !small_fwd && !small_dw && getenv("SACX_TC_VERBOSE"))
+              fprintf(stderr, "sacx: FFMA leftover in the fused plan: phase %d epi %d M %d N %d K %d a_sm %d a_sk %d b_sk %d b_sn %d\n", ph, oo.epi,
+                      oo.M, oo.N, oo.K, oo.a_sm, oo.a_sk, oo.b_sk, oo.b_sn);
           }
         }
         size_t so = 0;                       // scratch offset inside this phase (floats)

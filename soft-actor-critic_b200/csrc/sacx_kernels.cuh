@@ -162,6 +162,77 @@ __device__ __forceinline__ void small_fwd_tile(const Op& op, float* __restrict__
   else small_fwd_tile_k<SMALLK_MAX>(op, base, tile, xs);
 }
 
+// weight gradient of a narrow output layer whose delta rows TMA cannot address (policy head with 2A not a multiple of 4:
+// row stride 8 or 24 bytes): dW[m][n] = sum_b dy[b][m] x[b][n] (+ db[m] = sum_b dy[b][m]), M <= 8 rows, 64-column tile of the
+// op's tile grid, batch range split over 4 thread groups and reduced through shared memory, optimiser epilogue as in
+// sacx_gemm.cuh. Called by all 256 threads; xs: >= 4 * 64 * 9 floats.
+constexpr int SMALLM_MAX = 8, SMALLDW_MAXK = 4096;
+__device__ __forceinline__ bool small_dw_ok(const Op& o) {
+  return o.type == OP_GEMM && o.epi == EPI_DW && o.M <= SMALLM_MAX && o.K <= SMALLDW_MAXK && o.a_sm == 1 && o.b_sn == 1 && o.cfg >= 1 &&
+         !(o.flags & DW_ATOMIC) && o.i[0] <= 1;
+}
+__device__ __forceinline__ void small_dw_tile(const Op& op, float* __restrict__ base, const AgentScalars* scal, const Hyper& hp, int tile,
+                                              float* __restrict__ xs) {
+  const int tn = tile % op.tiles_n, c = threadIdx.x & 63, kg = threadIdx.x >> 6, n = tn * 64 + c;
+  const int kper = (op.K + 3) >> 2, b0 = kg * kper, b1 = min(op.K, b0 + kper);
+  float acc[SMALLM_MAX + 1];
+#pragma unroll
+  for (int m = 0; m <= SMALLM_MAX; ++m) acc[m] = 0.f;
+  if (n < op.N) {
+    int b = b0;
+    for (; b + 3 < b1; b += 4) {              // four batch rows per step: their loads are in flight together
+      float x[4], d[4][SMALLM_MAX];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        x[u] = __ldcg(base + op.b + (i64)(b + u) * op.b_sk + n);
+        const float* dy = base + op.a + (i64)(b + u) * op.a_sk;
+#pragma unroll
+        for (int m = 0; m < SMALLM_MAX; ++m) d[u][m] = (m < op.M) ? __ldcg(dy + m) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int m = 0; m < SMALLM_MAX; ++m) acc[m] = fmaf(d[u][m], x[u], acc[m]);
+    }
+    for (; b < b1; ++b) {
+      const float x = __ldcg(base + op.b + (i64)b * op.b_sk + n);
+      const float* dy = base + op.a + (i64)b * op.a_sk;
+#pragma unroll
+      for (int m = 0; m < SMALLM_MAX; ++m)
+        if (m < op.M) acc[m] = fmaf(__ldcg(dy + m), x, acc[m]);
+    }
+  }
+  if (tn == 0 && c < op.M)                      // bias gradient: column c of dy
+    for (int b = b0; b < b1; ++b) acc[SMALLM_MAX] += __ldcg(base + op.a + (i64)b * op.a_sk + c);
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m <= SMALLM_MAX; ++m) xs[(kg * 64 + c) * (SMALLM_MAX + 1) + m] = acc[m];
+  __syncthreads();
+  if (kg == 0) {
+    const float ss = (op.flags & DW_ADAM) ? __ldcg(&scal->adam_step_size[op.opt]) : 0.f;
+    const float bc = (op.flags & DW_ADAM) ? __ldcg(&scal->adam_bc2_sqrt[op.opt]) : 1.f;
+    auto apply = [&](float g, i64 p, i64 pm, i64 pv, i64 pt, i64 pg) {
+      if (op.flags & DW_STORE_GRAD) base[pg] = g;
+      if (op.flags & DW_ADAM) {
+        float w = base[p], mm = base[pm], vv = base[pv];
+        adam_update(g, w, mm, vv, ss, bc);
+        base[p] = w; base[pm] = mm; base[pv] = vv;
+        if ((op.flags & DW_POLYAK) && pt >= 0) base[pt] = polyak_mix(hp.tau, hp.one_minus_tau, w, base[pt]);
+      }
+    };
+    for (int m = 0; m <= SMALLM_MAX; ++m) {
+      float g = 0.f;
+      for (int q = 0; q < 4; ++q) g += xs[(q * 64 + c) * (SMALLM_MAX + 1) + m];
+      if (m < op.M && n < op.N) {
+        const i64 e = (i64)m * op.N + n;
+        apply(g, op.p + e, op.pm + e, op.pv + e, op.pt >= 0 ? op.pt + e : -1, op.pg + e);
+      } else if (m == SMALLM_MAX && tn == 0 && c < op.M && op.pb >= 0) {
+        apply(g, op.pb + c, op.pbm + c, op.pbv + c, op.pbt >= 0 ? op.pbt + c : -1, op.pbg + c);
+      }
+    }
+  }
+}
+
 constexpr int ROWS_SMEM_OPS = 8;
 __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restrict__ gplan, const RunArgs args, int tsm_floats) {
   extern __shared__ __align__(16) float rows_raw[];
@@ -194,7 +265,11 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
       rc.fresh = (oi != last_oi);          // head weights are staged once per (agent, op) run of tiles, not once per 8 rows
       last_oi = oi;
       switch (op.type) {
-        case OP_GEMM: if (!(op.cfg & 2) && small_fwd_ok(op)) { small_fwd_tile(op, base, lt, tsm); __syncthreads(); } break;
+        case OP_GEMM:
+          if (op.cfg & 2) break;                      // tensor-core kernel
+          if (small_fwd_ok(op)) { small_fwd_tile(op, base, lt, tsm); __syncthreads(); }
+          else if (small_dw_ok(op)) { small_dw_tile(op, base, scal, args.hp, lt, tsm); __syncthreads(); }
+          break;
         case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
         case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); __syncthreads(); break;
         case OP_Q_ROW: tile_q_row<1>(op, rc, lt); __syncthreads(); break;
