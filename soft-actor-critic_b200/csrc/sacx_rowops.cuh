@@ -569,6 +569,26 @@ __device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int
   constexpr int NT = CTA ? 256 : 32;
   auto mean_of = [&](const float* p) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (CTA && (B & 3) == 0 && ((((uintptr_t)p) & 15) == 0)) {
+      // large batch: 16-byte loads, four per thread in flight (a 65536-term mean was 60 us of dependent round trips)
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      const int n4 = B >> 2;
+      float4 a4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int i = lane;
+      for (; i + 3 * NT < n4; i += 4 * NT) {
+        const float4 v0 = __ldcg(p4 + i), v1 = __ldcg(p4 + i + NT), v2 = __ldcg(p4 + i + 2 * NT), v3 = __ldcg(p4 + i + 3 * NT);
+        a4[0].x += v0.x; a4[0].y += v0.y; a4[0].z += v0.z; a4[0].w += v0.w;
+        a4[1].x += v1.x; a4[1].y += v1.y; a4[1].z += v1.z; a4[1].w += v1.w;
+        a4[2].x += v2.x; a4[2].y += v2.y; a4[2].z += v2.z; a4[2].w += v2.w;
+        a4[3].x += v3.x; a4[3].y += v3.y; a4[3].z += v3.z; a4[3].w += v3.w;
+      }
+      for (; i < n4; i += NT) { const float4 v = __ldcg(p4 + i); a4[0].x += v.x; a4[0].y += v.y; a4[0].z += v.z; a4[0].w += v.w; }
+      const float s = ((a4[0].x + a4[0].y) + (a4[0].z + a4[0].w)) + ((a4[1].x + a4[1].y) + (a4[1].z + a4[1].w)) +
+                      ((a4[2].x + a4[2].y) + (a4[2].z + a4[2].w)) + ((a4[3].x + a4[3].y) + (a4[3].z + a4[3].w));
+      return final_sum<CTA>(s, red) * invB;
+    }
     int b = lane;
     for (; b + 3 * NT < B; b += 4 * NT) {        // four independent loads in flight per thread
       acc[0] += __ldcg(p + b); acc[1] += __ldcg(p + b + NT); acc[2] += __ldcg(p + b + 2 * NT); acc[3] += __ldcg(p + b + 3 * NT);
@@ -592,6 +612,15 @@ __device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int
     const float* lp = c.args->lp_ext ? c.args->lp_ext : base + op.o[3];
     float acc = 0.f, accl = 0.f;
     const float la32 = (float)s->log_alpha;
+    if (CTA && (B & 3) == 0 && ((((uintptr_t)lp) & 15) == 0)) {
+      const float4* p4 = reinterpret_cast<const float4*>(lp);
+      for (int i = lane; i < (B >> 2); i += NT) {
+        const float4 v = __ldcg(p4 + i);
+        const float t0 = v.x + hp.target_entropy, t1 = v.y + hp.target_entropy, t2 = v.z + hp.target_entropy, t3 = v.w + hp.target_entropy;
+        acc += (t0 + t1) + (t2 + t3);
+        accl += (la32 * t0 + la32 * t1) + (la32 * t2 + la32 * t3);
+      }
+    } else
     for (int b = lane; b < B; b += NT) {
       const float t = __ldcg(lp + b) + hp.target_entropy;
       acc += t;
