@@ -471,8 +471,17 @@ __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant
       const int m = (int)(e / n4), n = (int)(e % n4) * 4;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* p = scratch + r.part + (i64)m * r.n_ld + n;           // n_ld is a multiple of 4: the group is in range
-      for (int s = 0; s < r.splits; ++s) {
-        const float4 x = __ldcs(reinterpret_cast<const float4*>(p + (i64)s * r.m_pad * r.n_ld));
+      const i64 sstep = (i64)r.m_pad * r.n_ld;
+      int s = 0;
+      for (; s + 7 < r.splits; s += 8) {            // eight partial tiles in flight (the loop is latency-bound); summed in split order
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = __ldcs(reinterpret_cast<const float4*>(p + (s + u) * sstep));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { g.x += x[u].x; g.y += x[u].y; g.z += x[u].z; g.w += x[u].w; }
+      }
+      for (; s < r.splits; ++s) {
+        const float4 x = __ldcs(reinterpret_cast<const float4*>(p + s * sstep));
         g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
       }
       const i64 w = (i64)m * op.N + n;
