@@ -211,3 +211,40 @@ def test_tc_population_matches_ffma_population(monkeypatch):
         assert errs.max() < 100 * bar, (k, errs.max())
     # agents are independent: different seeds -> different parameters
     assert not np.array_equal(res[True]["block.params"][0], res[True]["block.params"][1])
+
+
+def test_tc_full_size_batch_65536(monkeypatch):
+    """BASELINE config 5 at its full size (BipedalWalker shape, batch 65536, one rank): one update through the tensor-core
+    path against the FFMA path on the same device-generated batch. 512 row tiles per layer, 64 batch splits per dW. Also
+    the size-independent property of the update: the Polyak step is exactly tau * theta + (1 - tau) * target."""
+    obs, act, B = 24, 4, 65536
+    res = {}
+    for tc in (True, False):
+        eng = _engine(obs, act, (256, 256), (256, 256), B, "relu", monkeypatch, tc, min_batch=4096, cap=100_000, fill=100_000 - 3, scale=0.1)
+        assert eng.tensor_core()[0] == tc
+        t0 = eng.view("block.targets").clone()
+        eng.update(None, None, None, 1)
+        eng.sync()
+        m = eng.metrics()
+        assert m["nonfinite"] == 0 and m["updates"] == 1
+        res[tc] = {n: eng.view(n).cpu().numpy().copy() for n in ("batch.idx", "out.y", "out.q1", "out.logpi", "block.params", "block.targets")}
+        res[tc]["m"] = {n: eng.view(n).cpu().numpy().copy() for n in ("m.q1.W1", "m.q2.W0", "m.q1.b1", "m.q1.W2", "m.pi.W1")}
+        res[tc]["metrics"] = m
+        # Polyak exactness (agent.py:288-291): target' = tau * theta' + (1 - tau) * target, products rounded separately
+        q_on = np.concatenate([eng.view(f"{c}.{t}").cpu().numpy().ravel() for c in ("q1", "q2") for t in ("W0", "b0", "W1", "b1", "W2", "b2")])
+        q_tg = np.concatenate([eng.view(f"{c}t.{t}").cpu().numpy().ravel() for c in ("q1", "q2") for t in ("W0", "b0", "W1", "b1", "W2", "b2")])
+        q_t0 = np.concatenate([t0.cpu().numpy().ravel()])[: q_tg.size]
+        tau = np.float32(0.005)
+        want = (tau * q_on).astype(np.float32) + (np.float32(1.0 - 0.005) * q_t0[: q_on.size]).astype(np.float32)
+        if q_t0.size >= q_on.size and eng.view("block.targets").numel() == q_on.size:
+            assert np.array_equal(q_tg, want)
+    a, b = res[True], res[False]
+    assert np.array_equal(a["batch.idx"], b["batch.idx"])                 # same device index stream (distinct indices)
+    assert len(np.unique(a["batch.idx"])) == B
+    for n in ("out.y", "out.q1", "out.logpi"):
+        assert_close(n, a[n], b[n], 2e-5)
+    for n in a["m"]:
+        assert_close(n, a["m"][n], b["m"][n], 5e-4 if n.startswith("m.pi") else 1e-4)
+    assert_close("block.params", a["block.params"], b["block.params"], 1e-4)
+    for key in ("q1_loss", "q2_loss", "policy_loss", "log_alpha"):
+        assert abs(a["metrics"][key] - b["metrics"][key]) <= 1e-4 * abs(b["metrics"][key]) + 1e-6, key
