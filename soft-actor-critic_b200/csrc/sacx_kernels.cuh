@@ -262,19 +262,23 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
       while (oi + 1 < ph.op0 + ph.nops && t >= ops[oi + 1].tile0) ++oi;
       const Op& op = ops[oi];
       const int lt = t - op.tile0;
-      rc.fresh = (oi != last_oi);          // head weights are staged once per (agent, op) run of tiles, not once per 8 rows
+      // head weights are staged once per (agent, op) run of tiles, not once per 8 rows; between two tiles of the same op the
+      // warps are NOT synchronised (each owns its row and its scratch), so a warp whose row is done moves on to the next
+      // tile's loads -- the CTA-wide barrier sits only where the staging area changes hands
+      rc.fresh = (oi != last_oi);
+      if (rc.fresh && last_oi != -1) __syncthreads();
       last_oi = oi;
       switch (op.type) {
         case OP_GEMM:
           if (op.cfg & 2) break;                      // tensor-core kernel
-          if (small_fwd_ok(op)) { small_fwd_tile(op, base, lt, tsm); __syncthreads(); }
-          else if (small_dw_ok(op)) { small_dw_tile(op, base, scal, args.hp, lt, tsm); __syncthreads(); }
+          if (small_fwd_ok(op)) { small_fwd_tile(op, base, lt, tsm); last_oi = -2; }       // (these tiles use the staging area themselves)
+          else if (small_dw_ok(op)) { small_dw_tile(op, base, scal, args.hp, lt, tsm); last_oi = -2; }
           break;
         case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
-        case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); __syncthreads(); break;
-        case OP_Q_ROW: tile_q_row<1>(op, rc, lt); __syncthreads(); break;
-        case OP_ACTOR_Q: tile_actor_q<1>(op, rc, lt); __syncthreads(); break;
-        case OP_ACTOR_BWD: tile_actor_bwd<1>(op, rc, lt); __syncthreads(); break;
+        case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); break;
+        case OP_Q_ROW: tile_q_row<1>(op, rc, lt); break;
+        case OP_ACTOR_Q: tile_actor_q<1>(op, rc, lt); break;
+        case OP_ACTOR_BWD: tile_actor_bwd<1>(op, rc, lt); break;
         case OP_PROLOGUE: if (tid == 0) op_prologue(op, rc); break;
         case OP_FINAL: op_final_impl<true>(op, rc, tid, fred); break;      // all 256 threads: B terms per mean
         case OP_POLYAK: op_polyak(op, rc, lt); break;
