@@ -59,7 +59,7 @@ struct Engine {
   // batch / scratch
   int ldx = 0;
   i64 x_sa, x_s2, x_pi, b_r, b_d, b_idx, b_eps1, b_eps2, b_lp2, b_lp, b_y, b_tq[2], b_q[2], b_qa[2], b_dout[2], b_loss[2],
-      b_ploss, b_tz, b_se, b_mask, b_headz, b_dhead, b_part_q[2], b_part_qt[2], b_part_da[2];
+      b_ploss, b_tz, b_se, b_mask, b_headz, b_headz_t, b_dhead, b_part_q[2], b_part_qt[2], b_part_da[2];
   int ntn_q = 0, ntn_q0 = 0;
   bool fuse_rows = false;
   ActSet a_pit, a_pia, a_q[2], a_qt[2];
@@ -244,6 +244,7 @@ struct Engine {
     b_se = alloc("scr.se", B, A);
     b_mask = alloc("scr.mask", B, A);
     b_headz = alloc("scr.headz", B, 2 * A);
+    b_headz_t = alloc("scr.headz_t", B, 2 * A);      // head pre-activations of pi(s') (tensor-core plans)
     b_dhead = alloc("scr.dhead", B, 2 * A);
     alloc_actset(a_pit, "act.pit", pi, false);
     alloc_actset(a_pia, "act.pia", pi, true);
@@ -328,6 +329,36 @@ struct Engine {
     Op o = blank(OP_GATHER);
     o.o[0] = x_sa; o.o[1] = x_s2; o.o[2] = x_pi; o.o[3] = b_r; o.o[4] = b_d; o.o[5] = b_idx;
     o.i[0] = ldx; o.ntiles = row_tiles();
+    return o;
+  }
+  // large batch: the policy head as [tensor-core GEMM -> one-thread-per-row tail] instead of the one-warp-per-row head op
+  bool tc_heads() const {
+    std::string w;
+    return tc_wanted(w) && cfg.n_agents == 1 && (2 * cfg.act_dim) % 4 == 0 && pi.dims[pi.L()] % 4 == 0 && !getenv_off("SACX_TC_HEADS");
+  }
+  static bool getenv_off(const char* name) { const char* v = getenv(name); return v && atoi(v) == 0; }
+  Op gemm_pi_head(bool actor) const {
+    const ActSet& as = actor ? a_pia : a_pit;
+    const int L = pi.L();
+    Op o = blank(OP_GEMM);
+    o.epi = EPI_FWD; o.act = SACX_ACT_IDENTITY;            // pre-activations: the tail applies the output activation
+    o.M = cfg.batch_size; o.N = 2 * cfg.act_dim; o.K = pi.dims[L];
+    o.a = as.h[L - 1]; o.a_sm = as.ld[L - 1]; o.a_sk = 1;
+    o.b = pi.W[L]; o.b_sk = 1; o.b_sn = o.K;
+    o.bias = pi.b[L];
+    o.c = actor ? b_headz : b_headz_t; o.ldc = 2 * cfg.act_dim; o.zout = -1;
+    finish_gemm(o);
+    return o;
+  }
+  Op op_pi_tail(bool actor) const {
+    Op o = blank(OP_PI_TAIL);
+    o.mode = actor ? 2 : 1; o.act_out = pi.act_o;
+    o.o[0] = actor ? b_headz : b_headz_t;
+    o.o[3] = actor ? x_pi : x_s2; o.i[2] = ldx;
+    o.o[4] = actor ? b_lp : b_lp2;
+    o.o[5] = actor ? b_eps2 : b_eps1;
+    if (actor) { o.o[6] = b_tz; o.o[7] = b_se; o.o[8] = b_mask; }
+    o.ntiles = (cfg.batch_size + TAIL_ROWS - 1) / TAIL_ROWS;
     return o;
   }
   Op op_pi_head(bool actor) const {
@@ -465,9 +496,14 @@ struct Engine {
       pb.add(gemm_dw(n, 0, opt, flags, L >= 1 ? dl(0) : dout, L >= 1 ? ldd(0) : ld_dout, x, ld_x, is_critic));
   }
 
+  // the head of pi(s') / pi(s): one phase (row op) or two (GEMM, then tail)
+  void emit_pi_head(PB& pb, bool actor) const {
+    if (tc_heads()) { pb.phase(); pb.add(gemm_pi_head(actor)); pb.phase(); pb.add(op_pi_tail(actor)); }
+    else { pb.phase(); pb.add(op_pi_head(actor)); }
+  }
   void emit_target(PB& pb) const {
     for (int l = 0; l < pi.L(); ++l) { pb.phase(); pb.add(gemm_fwd(pi, l, 0, l ? a_pit.h[l - 1] : x_s2, l ? a_pit.ld[l - 1] : ldx, a_pit)); }
-    pb.phase(); pb.add(op_pi_head(false));
+    emit_pi_head(pb, false);
     for (int l = 0; l < q1.L(); ++l) {
       pb.phase();
       for (int c = 0; c < 2; ++c)
@@ -495,7 +531,7 @@ struct Engine {
       if (l == 0 && (flags & DW_ADAM)) pb.add(op_prologue(1 << OPT_PI));
       pb.add(gemm_fwd(pi, l, 0, l ? a_pia.h[l - 1] : x_pi, l ? a_pia.ld[l - 1] : ldx, a_pia));
     }
-    pb.phase(); pb.add(op_pi_head(true));
+    emit_pi_head(pb, true);
     emit_actor_tail(pb, flags, (flags & DW_ADAM) ? 2 : (2 | 16));
   }
   // critics on (s, a~pi) -> routed dQ -> dQ/da -> head backward -> policy backward (+Adam)
@@ -534,8 +570,10 @@ struct Engine {
     // that ran Q1 layer 0 (two short GEMM tiles) and not behind a head tile
     pb.phase();
     pb.add(gemm_fwd(q1, 0, 0, x_sa, ldx, a_q[0]));
-    pb.add(op_pi_head(false)); pb.add(op_pi_head(true));
+    if (tc_heads()) { pb.add(gemm_pi_head(false)); pb.add(gemm_pi_head(true)); }
+    else { pb.add(op_pi_head(false)); pb.add(op_pi_head(true)); }
     pb.add(gemm_fwd(q2, 0, 0, x_sa, ldx, a_q[1]));
+    if (tc_heads()) { pb.phase(); pb.add(op_pi_tail(false)); pb.add(op_pi_tail(true)); }
     for (int l = 0; l < q1.L(); ++l) {
       pb.phase();
       for (int c = 0; c < 2; ++c)
@@ -959,7 +997,9 @@ struct Engine {
     if (o.type != OP_GEMM || o.mode != 0 || o.i[4] != 0 || o.zout >= 0) return false;
     auto al = [](i64 x) { return x >= 0 && (x & 3) == 0; };
     if (o.N > TC_NMAX) return false;
-    if (o.epi != EPI_DW && (o.N < 16 || (o.N & 3))) return false;      // dW: any width (B operand rows are 16B-aligned batch rows)
+    if (o.epi == EPI_DACT && (o.N < 16 || (o.N & 3))) return false;
+    if (o.epi == EPI_FWD && (o.N < 4 || (o.N & 3))) return false;        // narrow heads: UMMA N = 16, weight rows beyond N read as zero
+    // dW: any width (B operand rows are 16B-aligned batch rows)
     if (o.epi == EPI_FWD)
       return o.M >= tc_min_m && o.a_sk == 1 && o.b_sk == 1 && !(o.a_sm & 3) && !(o.b_sn & 3) && !(o.ldc & 3) && al(o.a) && al(o.b) &&
              al(o.c) && al(o.bias) && o.K >= 4;

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
             case OP_GEMM: if (!(args.tc_skip && (op.cfg & 2))) gemm_tile<C>(op, ec, lt, gsm); break;
             case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
             case OP_PI_HEAD: tile_pi_head<0>(op, rc, lt); __syncthreads(); break;
+            case OP_PI_TAIL: tile_pi_tail(op, rc, lt); break;
             case OP_Q_ROW: tile_q_row<0>(op, rc, lt); __syncthreads(); break;
             case OP_ACTOR_Q: tile_actor_q<0>(op, rc, lt); __syncthreads(); break;
             case OP_ACTOR_BWD: tile_actor_bwd<0>(op, rc, lt); __syncthreads(); break;
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
           break;
         case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
         case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); break;
+        case OP_PI_TAIL: tile_pi_tail(op, rc, lt); break;
         case OP_Q_ROW: tile_q_row<1>(op, rc, lt); break;
         case OP_ACTOR_Q: tile_actor_q<1>(op, rc, lt); break;
         case OP_ACTOR_BWD: tile_actor_bwd<1>(op, rc, lt); break;

@@ -210,6 +210,48 @@ __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int til
   SACX_RSTAMP(4);
 }
 
+// ---------------------------------------------------------------- OP_PI_TAIL (large batch, tensor-core path)
+// The policy's output layer is a skinny GEMM (N = 2A) that the tensor-core kernel runs like any other layer; what is left of
+// OP_PI_HEAD is per-row scalar work, so ONE THREAD owns a row (256 rows per tile) instead of one warp: ~30x fewer warp
+// instructions per row than the shuffle-reduced head. Same arithmetic as tile_pi_head (models.py:79-87).
+// o[0]=z (head pre-activations [B][2A]) o[3]=X(dest) o[4]=lp o[5]=eps buf o[6]=tz o[7]=se o[8]=mask (-1: not saved)  i[2]=ldx  mode 1/2
+constexpr int TAIL_ROWS = 256;
+__device__ __forceinline__ void tile_pi_tail(const Op& op, const RowCtx& c, int tile) {
+  const RunArgs& a = *c.args;
+  const Hyper& hp = a.hp;
+  float* base = c.base;
+  const int row = tile * TAIL_ROWS + threadIdx.x, A = hp.act;
+  if (row >= hp.B) return;
+  const float* z = base + op.o[0] + (i64)row * 2 * A;
+  const float* eps_ext = (op.mode == 1) ? a.eps1_ext : a.eps2_ext;
+  const unsigned long long upd = eps_ext ? 0ull : (unsigned long long)__ldcg(&c.scal->updates);
+  float lp = 0.f;
+  bool bad = false;
+  for (int j = 0; j < A; ++j) {
+    const float mu = act_fwd(op.act_out, __ldcg(z + j)), ls_raw = act_fwd(op.act_out, __ldcg(z + A + j));
+    const float ls = fminf(fmaxf(ls_raw, hp.log_std_min), hp.log_std_max);
+    const float sd = expf(ls);
+    const float e = eps_ext ? eps_ext[(((i64)c.step * a.n_agents + c.agent) * hp.B + row) * A + j]
+                            : philox_normal(hp.seed, upd, op.mode, (uint32_t)(hp.row0_global + row), (uint32_t)j, (uint32_t)c.agent);
+    base[op.o[5] + (i64)row * A + j] = e;
+    const float zz = mu + e * sd;                      // Normal.rsample: loc + eps * scale
+    const float tz = tanhf(zz);
+    base[op.o[3] + (i64)row * op.i[2] + hp.obs + j] = tz * hp.action_scale;
+    const float dzm = zz - mu;
+    float l = -(dzm * dzm) / (2.f * (sd * sd)) - logf(sd) - 0.91893853320467274178f;
+    l -= 2.f * (0.69314718055994530942f - zz - softplus20(-2.f * zz));
+    lp += l;
+    bad |= !(isfinite(mu) && isfinite(sd));
+    if (op.o[6] >= 0) {
+      base[op.o[6] + (i64)row * A + j] = tz;
+      base[op.o[7] + (i64)row * A + j] = sd * e;
+      base[op.o[8] + (i64)row * A + j] = (ls_raw >= hp.log_std_min && ls_raw <= hp.log_std_max) ? 1.f : 0.f;
+    }
+  }
+  base[op.o[4] + row] = lp;
+  if (bad) atomicOr(&c.scal->nonfinite, 1);
+}
+
 // ---------------------------------------------------------------- OP_Q_ROW: target y (mode & 1) and / or critic delta (mode & 2)
 // target: o[0..1]=hqt(last hidden) o[2..3]=Wt_L o[4..5]=bt_L o[6]=r o[7]=d o[8]=lp2 o[9]=y o[10..11]=tq
 // critic: o[12..13]=hq(last hidden) o[14..15]=aux(z or h) o[16..17]=W_L o[18..19]=b_L o[20..21]=q out o[22..23]=dout

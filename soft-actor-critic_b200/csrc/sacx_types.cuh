@@ -21,6 +21,7 @@ enum OpType : int {
   OP_ADAM_FLAT,   // Adam over a packed gradient block (data-parallel apply)
   OP_LOAD_EXT,    // copy external y / logpi into arena buffers
   OP_DW_HEAD,     // fused plan: gradient + Adam of the critics' output layer from the head shares
+  OP_PI_TAIL,     // large batch: rsample / tanh squash / log_prob from head pre-activations a tensor-core GEMM produced (one thread per row)
 };
 
 enum Epi : int { EPI_FWD = 1, EPI_DACT = 2, EPI_DW = 3 };
