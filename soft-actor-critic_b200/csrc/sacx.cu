@@ -639,8 +639,20 @@ int sacx_ring_gather(sacx_ring_t h, int32_t agent, const int64_t* idx_dev, int32
                                           " transitions. Current size: " + std::to_string(r.len(agent)));
   int rc = r.flush();
   if (rc) return rc;
-  ring_gather_kernel<<<(B + 7) / 8, 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2, r.off_d, r.O, r.A,
-                                                        (const i64*)idx_dev, B, s, a, rr, s2, d);
+  auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
+  const bool vec = (r.O % 4 == 0) && (r.A % 4 == 0) && (r.off_s % 4 == 0) && (r.off_s2 % 4 == 0) && (r.off_a % 4 == 0) && al16(r.block(agent)) &&
+                   al16(s) && al16(s2) && al16(a) && 2 * (r.O / 4) + r.A / 4 + 2 <= 256;
+  if (vec) {
+    const int pieces = 2 * (r.O / 4) + r.A / 4 + 2;
+    int tl = 0;
+    while ((1 << tl) < pieces) ++tl;
+    const i64 threads = (i64)B << tl;
+    ring_gather_vec_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2,
+                                                                                    r.off_d, r.O, r.A, (const i64*)idx_dev, B, s, a, rr, s2, d, tl);
+  } else {
+    ring_gather_kernel<<<(B + 7) / 8, 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2, r.off_d, r.O, r.A,
+                                                          (const i64*)idx_dev, B, s, a, rr, s2, d);
+  }
   ++r.launches;
   SACX_CUDA(cudaGetLastError());
   return SACX_OK;

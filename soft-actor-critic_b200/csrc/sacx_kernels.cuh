@@ -366,6 +366,35 @@ __global__ void ring_gather_kernel(const float* __restrict__ rb, i64 cap, i64 of
   }
 }
 
+// The same gather with one THREAD per 16-byte piece of a row instead of one warp per row (obs and act dimensions multiples
+// of 4, 16-byte aligned fields): a BipedalWalker row is 6 + 6 + 1 pieces + r + d = 15 -> 16 threads, two rows per warp, every
+// load of a row in flight at once. The warp-per-row kernel above issued five load instructions with 24 / 24 / 4 / 1 / 1
+// active lanes and reached 0.35 TB/s (read + write) on 1M rows (tools/gather_bench.py, profiles/).
+__global__ void ring_gather_vec_kernel(const float* __restrict__ rb, i64 cap, i64 off_s, i64 off_a, i64 off_r, i64 off_s2,
+                                       i64 off_d, int O, int A, const i64* __restrict__ idx, int B, float* __restrict__ s,
+                                       float* __restrict__ a, float* __restrict__ r, float* __restrict__ s2,
+                                       float* __restrict__ d, int tpr_log2) {
+  const i64 gt = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = (int)(gt >> tpr_log2), piece = (int)(gt & ((1 << tpr_log2) - 1));
+  if (row >= B) return;
+  const int cs = O >> 2, ca = A >> 2;
+  if (piece >= 2 * cs + ca + 2) return;
+  const i64 pushes = reinterpret_cast<const RingMeta*>(rb)->pushes;
+  const i64 oldest = pushes > cap ? pushes - cap : 0;
+  const i64 slot = (oldest + __ldg(idx + row)) % cap;
+  if (piece < cs) {
+    if (s) reinterpret_cast<float4*>(s + (i64)row * O)[piece] = __ldcs(reinterpret_cast<const float4*>(rb + off_s + slot * O) + piece);
+  } else if (piece < 2 * cs) {
+    if (s2) reinterpret_cast<float4*>(s2 + (i64)row * O)[piece - cs] = __ldcs(reinterpret_cast<const float4*>(rb + off_s2 + slot * O) + piece - cs);
+  } else if (piece < 2 * cs + ca) {
+    if (a) reinterpret_cast<float4*>(a + (i64)row * A)[piece - 2 * cs] = __ldcs(reinterpret_cast<const float4*>(rb + off_a + slot * A) + piece - 2 * cs);
+  } else if (piece == 2 * cs + ca) {
+    if (r) r[row] = __ldcs(rb + off_r + slot);
+  } else {
+    if (d) d[row] = __ldcs(rb + off_d + slot);
+  }
+}
+
 __global__ void ring_indices_kernel(const float* __restrict__ rb, i64 cap, unsigned long long seed,
                                     unsigned long long counter, int agent, int B, i64* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
