@@ -61,6 +61,9 @@ CASES = [
     (32, 2, (256, 256), (256, 256), 1024, "relu"),       # Donkey latent shape, batch 1024
     (17, 6, (64, 128), (128, 64), 1100, "tanh"),         # ragged batch (8 full row tiles + 76 rows), mixed widths < 256
     (11, 3, (128, 48, 256), (80, 256, 128), 1536, "leaky_relu"),   # three hidden layers; widths that are not multiples of 32
+    (8, 1, (512, 256), (256, 512), 1280, "relu"),        # layers wider than 256 stay on FFMA tiles next to tensor-core layers; 2A = 2
+    (3, 2, (256,), (128,), 1024, "tanh"),                # a single hidden layer; K = 3 / 5 first layers (small-K tiles)
+    (24, 4, (64, 64, 64, 64), (256, 256, 256, 256), 1024, "relu"),   # four hidden layers
 ]
 
 
