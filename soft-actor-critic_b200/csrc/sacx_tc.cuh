@@ -262,7 +262,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) bs[j][e] = 0.f;
-      const int n4 = (TC_A_BYTES + o.b_bytes) >> 4;
+      const int n4 = (P.dbg & 512) ? (TC_A_BYTES >> 4) : ((TC_A_BYTES + o.b_bytes) >> 4);      // 512: timing experiment, B operand not split
       for (int kb = 0; kb < t.nkb; ++kb, ++it) {
         const int s = it % TC_STAGES;
         tc_mbar_wait(&full[s], (it / TC_STAGES) & 1);
