@@ -369,7 +369,8 @@ static int engine_setup_tc(Engine* e) {
             const float* Bm = e->arena + o.b;
             if (o.epi == EPI_FWD || o.epi == EPI_DACT) {
               ok = ok && tc_encode(enc, &g.maps.a[j], A, o.K, o.M, o.a_sm, TC_BK, TC_BM, 2, NA, AS);
-              ok = ok && tc_encode(enc, &g.maps.c[j], e->arena + o.c, o.N, o.M, o.ldc, 32, TC_BM, 0, NA, AS);
+              // (a width that is not a multiple of 4 floats: store the zero columns of the 16-byte padded rows as well)
+              ok = ok && tc_encode(enc, &g.maps.c[j], e->arena + o.c, (o.N & 3) ? std::min(rup(o.N, 4), o.ldc) : o.N, o.M, o.ldc, 32, TC_BM, 0, NA, AS);
               if (o.epi == EPI_FWD) {
                 t.b_rows = t.n_mma; t.b_bytes = t.n_mma * TC_BK * 4;
                 ok = ok && tc_encode(enc, &g.maps.b[j], Bm, o.K, o.N, o.b_sn, TC_BK, t.n_mma, 2, NA, AS);

@@ -59,7 +59,7 @@ struct Engine {
   // batch / scratch
   int ldx = 0;
   i64 x_sa, x_s2, x_pi, b_r, b_d, b_idx, b_eps1, b_eps2, b_lp2, b_lp, b_y, b_tq[2], b_q[2], b_qa[2], b_dout[2], b_loss[2],
-      b_ploss, b_tz, b_se, b_mask, b_headz, b_headz_t, b_dhead, b_part_q[2], b_part_qt[2], b_part_da[2];
+      b_ploss, b_tz, b_se, b_mask, b_headz, b_headz_t, b_headz_a, b_dhead, b_part_q[2], b_part_qt[2], b_part_da[2];
   int ntn_q = 0, ntn_q0 = 0;
   bool fuse_rows = false;
   ActSet a_pit, a_pia, a_q[2], a_qt[2];
@@ -244,7 +244,8 @@ struct Engine {
     b_se = alloc("scr.se", B, A);
     b_mask = alloc("scr.mask", B, A);
     b_headz = alloc("scr.headz", B, 2 * A);
-    b_headz_t = alloc("scr.headz_t", B, 2 * A);      // head pre-activations of pi(s') (tensor-core plans)
+    b_headz_t = alloc("scr.headz_t", B, 2 * A, rup4(2 * A));      // head pre-activations of pi(s') / pi(s) as the tensor-core head GEMM
+    b_headz_a = alloc("scr.headz_a", B, 2 * A, rup4(2 * A));      // writes them: rows padded to 16 bytes (TMA store)
     b_dhead = alloc("scr.dhead", B, 2 * A);
     alloc_actset(a_pit, "act.pit", pi, false);
     alloc_actset(a_pia, "act.pia", pi, true);
@@ -334,7 +335,7 @@ struct Engine {
   // large batch: the policy head as [tensor-core GEMM -> one-thread-per-row tail] instead of the one-warp-per-row head op
   bool tc_heads() const {
     std::string w;
-    return tc_wanted(w) && cfg.n_agents == 1 && (2 * cfg.act_dim) % 4 == 0 && pi.dims[pi.L()] % 4 == 0 && !getenv_off("SACX_TC_HEADS");
+    return tc_wanted(w) && pi.dims[pi.L()] % 4 == 0 && !getenv_off("SACX_TC_HEADS");
   }
   static bool getenv_off(const char* name) { const char* v = getenv(name); return v && atoi(v) == 0; }
   Op gemm_pi_head(bool actor) const {
@@ -346,18 +347,18 @@ struct Engine {
     o.a = as.h[L - 1]; o.a_sm = as.ld[L - 1]; o.a_sk = 1;
     o.b = pi.W[L]; o.b_sk = 1; o.b_sn = o.K;
     o.bias = pi.b[L];
-    o.c = actor ? b_headz : b_headz_t; o.ldc = 2 * cfg.act_dim; o.zout = -1;
+    o.c = actor ? b_headz_a : b_headz_t; o.ldc = rup4(2 * cfg.act_dim); o.zout = -1;
     finish_gemm(o);
     return o;
   }
   Op op_pi_tail(bool actor) const {
     Op o = blank(OP_PI_TAIL);
     o.mode = actor ? 2 : 1; o.act_out = pi.act_o;
-    o.o[0] = actor ? b_headz : b_headz_t;
+    o.o[0] = actor ? b_headz_a : b_headz_t; o.i[3] = rup4(2 * cfg.act_dim);
     o.o[3] = actor ? x_pi : x_s2; o.i[2] = ldx;
     o.o[4] = actor ? b_lp : b_lp2;
     o.o[5] = actor ? b_eps2 : b_eps1;
-    if (actor) { o.o[6] = b_tz; o.o[7] = b_se; o.o[8] = b_mask; }
+    if (actor) { o.o[6] = b_tz; o.o[7] = b_se; o.o[8] = b_mask; o.o[9] = b_headz; }      // o[9]: compact copy for the head backward
     o.ntiles = (cfg.batch_size + TAIL_ROWS - 1) / TAIL_ROWS;
     return o;
   }
@@ -998,7 +999,7 @@ struct Engine {
     auto al = [](i64 x) { return x >= 0 && (x & 3) == 0; };
     if (o.N > TC_NMAX) return false;
     if (o.epi == EPI_DACT && (o.N < 16 || (o.N & 3))) return false;
-    if (o.epi == EPI_FWD && (o.N < 4 || (o.N & 3))) return false;        // narrow heads: UMMA N = 16, weight rows beyond N read as zero
+    if (o.epi == EPI_FWD && o.N < 1) return false;                        // narrow heads: UMMA N = 16, weight rows beyond N read as zero
     // dW: any width (B operand rows are 16B-aligned batch rows)
     if (o.epi == EPI_FWD)
       return o.M >= tc_min_m && o.a_sk == 1 && o.b_sk == 1 && !(o.a_sm & 3) && !(o.b_sn & 3) && !(o.ldc & 3) && al(o.a) && al(o.b) &&

@@ -214,7 +214,8 @@ __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int til
 // The policy's output layer is a skinny GEMM (N = 2A) that the tensor-core kernel runs like any other layer; what is left of
 // OP_PI_HEAD is per-row scalar work, so ONE THREAD owns a row (256 rows per tile) instead of one warp: ~30x fewer warp
 // instructions per row than the shuffle-reduced head. Same arithmetic as tile_pi_head (models.py:79-87).
-// o[0]=z (head pre-activations [B][2A]) o[3]=X(dest) o[4]=lp o[5]=eps buf o[6]=tz o[7]=se o[8]=mask (-1: not saved)  i[2]=ldx  mode 1/2
+// o[0]=z (head pre-activations [B][i[3]]) o[3]=X(dest) o[4]=lp o[5]=eps buf o[6]=tz o[7]=se o[8]=mask o[9]=compact z copy (-1: not saved)
+// i[2]=ldx i[3]=row stride of z   mode 1/2
 constexpr int TAIL_ROWS = 256;
 __device__ __forceinline__ void tile_pi_tail(const Op& op, const RowCtx& c, int tile) {
   const RunArgs& a = *c.args;
@@ -222,13 +223,15 @@ __device__ __forceinline__ void tile_pi_tail(const Op& op, const RowCtx& c, int 
   float* base = c.base;
   const int row = tile * TAIL_ROWS + threadIdx.x, A = hp.act;
   if (row >= hp.B) return;
-  const float* z = base + op.o[0] + (i64)row * 2 * A;
+  const float* z = base + op.o[0] + (i64)row * op.i[3];
   const float* eps_ext = (op.mode == 1) ? a.eps1_ext : a.eps2_ext;
   const unsigned long long upd = eps_ext ? 0ull : (unsigned long long)__ldcg(&c.scal->updates);
   float lp = 0.f;
   bool bad = false;
   for (int j = 0; j < A; ++j) {
-    const float mu = act_fwd(op.act_out, __ldcg(z + j)), ls_raw = act_fwd(op.act_out, __ldcg(z + A + j));
+    const float zm = __ldcg(z + j), zl = __ldcg(z + A + j);
+    if (op.o[9] >= 0) { base[op.o[9] + (i64)row * 2 * A + j] = zm; base[op.o[9] + (i64)row * 2 * A + A + j] = zl; }
+    const float mu = act_fwd(op.act_out, zm), ls_raw = act_fwd(op.act_out, zl);
     const float ls = fminf(fmaxf(ls_raw, hp.log_std_min), hp.log_std_max);
     const float sd = expf(ls);
     const float e = eps_ext ? eps_ext[(((i64)c.step * a.n_agents + c.agent) * hp.B + row) * A + j]
