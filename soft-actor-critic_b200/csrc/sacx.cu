@@ -365,6 +365,7 @@ static int engine_setup_tc(Engine* e) {
             t.m_tiles = (o.M + TC_BM - 1) / TC_BM;
             t.splits = 1; t.k_per_split = rup(o.K, TC_BK);
             t.bias = o.bias; t.bias_part = -1;
+            t.proj_w = o.o[28]; t.proj_out = o.o[29]; t.proj_b = o.o[30];      // critic head riding on this layer (blank(): -1)
             const float* A = e->arena + o.a;
             const float* Bm = e->arena + o.b;
             if (o.epi == EPI_FWD || o.epi == EPI_DACT) {
@@ -781,7 +782,16 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
     SACX_CUDA(cudaMemset(e.arena, 0, total));
     e.own_arena = true;
   }
-  if ((rc = engine_setup_tc(&e))) { delete h; return rc; }
+  {
+    std::string w;
+    const bool planned = e.tc_wanted(w);
+    if ((rc = engine_setup_tc(&e))) { delete h; return rc; }
+    if (planned && !e.tc) {            // the plans were built for the tensor-core path (head GEMMs, tails, projections): rebuild without
+      e.tc_forbid = true;
+      if ((rc = e.build_plans())) { delete h; return rc; }
+      if ((rc = engine_setup_rp(&e))) { delete h; return rc; }
+    }
+  }
   if ((rc = engine_setup_rp_tma(&e))) { delete h; return rc; }
   SACX_CUDA(cudaMalloc((void**)&e.d_plans, sizeof(Plan) * N_PLANS));
   SACX_CUDA(cudaMemcpy(e.d_plans, e.h_plans.data(), sizeof(Plan) * N_PLANS, cudaMemcpyHostToDevice));

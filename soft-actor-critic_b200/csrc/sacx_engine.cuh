@@ -58,7 +58,7 @@ struct Engine {
   i64 n_online = 0, n_critic = 0;
   // batch / scratch
   int ldx = 0;
-  i64 x_sa, x_s2, x_pi, b_r, b_d, b_idx, b_eps1, b_eps2, b_lp2, b_lp, b_y, b_tq[2], b_q[2], b_qa[2], b_dout[2], b_loss[2],
+  i64 x_sa, x_s2, x_pi, b_r, b_d, b_idx, b_eps1, b_eps2, b_lp2, b_lp, b_y, b_tq[2], b_q[2], b_qa[2], b_dout[2], b_loss[2], b_coef[2],
       b_ploss, b_tz, b_se, b_mask, b_headz, b_headz_t, b_headz_a, b_dhead, b_part_q[2], b_part_qt[2], b_part_da[2];
   int ntn_q = 0, ntn_q0 = 0;
   bool fuse_rows = false;
@@ -99,6 +99,7 @@ struct Engine {
   int tc_min_batch = 4096;         // single agent: smallest batch that takes the tensor-core path
   int tc_min_m = 4096;             // smallest GEMM row count per agent (population: 128, one row tile)
   std::string tc_why;
+  bool tc_forbid = false;          // tensor-core setup failed: plans are rebuilt without the features that need it
   std::vector<std::vector<TcPhase>> tc_phases;       // [plan][phase]
   float* d_tc_scratch = nullptr;
   size_t tc_scratch_floats = 0;
@@ -230,6 +231,7 @@ struct Engine {
       b_qa[c] = alloc("out.q" + s + "_pi", 1, B);
       b_dout[c] = alloc("scr.dout" + s, B, 1, 4);        // row stride 4: the dW tile reads it as a 16B-aligned [batch][1] operand
       b_loss[c] = alloc("scr.lossrow" + s, 1, B);
+      b_coef[c] = alloc("scr.coef" + s, B, 1, 4);         // actor phase: routed dQ coefficient per row (tensor-core plans)
     }
     ntn_q = (cfg.hidden_q[cfg.n_hidden_q - 1] + 31) / 32;      // head shares per row: one per 32-wide column tile
     ntn_q0 = (cfg.hidden_q[0] + 31) / 32;
@@ -330,6 +332,48 @@ struct Engine {
     Op o = blank(OP_GATHER);
     o.o[0] = x_sa; o.o[1] = x_s2; o.o[2] = x_pi; o.o[3] = b_r; o.o[4] = b_d; o.o[5] = b_idx;
     o.i[0] = ldx; o.ntiles = row_tiles();
+    return o;
+  }
+  // large batch: critic heads projected in the epilogue of the last hidden layer's tensor-core GEMM, per-row tails, delta stream
+  bool tc_rows() const {
+    std::string w;
+    if (!tc_wanted(w) || getenv_off("SACX_TC_ROWS")) return false;
+    const int L = q1.L();
+    if (q1.dims[L] > TC_NMAX || (q1.dims[L] & 3)) return false;
+    Op t = gemm_fwd(q1, L - 1, 0, L > 1 ? a_q[0].h[L - 2] : x_sa, L > 1 ? a_q[0].ld[L - 2] : ldx, a_q[0]);
+    return tc_op_eligible(t);            // the projection needs that GEMM on the tensor-core kernel
+  }
+  // forward layer l of critic c; the last hidden layer carries the head projection into `head_out` when tc_rows()
+  Op gemm_fwd_q(int c, int l, i64 wshift, i64 x, int ld_x, const ActSet& as, i64 head_out) const {
+    const NetLayout& n = c ? q2 : q1;
+    Op o = gemm_fwd(n, l, wshift, x, ld_x, as);
+    if (l == n.L() - 1 && tc_rows()) { o.o[28] = n.W[n.L()] + wshift; o.o[29] = head_out; o.o[30] = n.b[n.L()] + wshift; }
+    return o;
+  }
+  Op op_q_tail(int mode) const {
+    Op o = blank(OP_Q_TAIL);
+    o.mode = mode; o.act_out = q1.act_o;
+    for (int c = 0; c < 2; ++c) {
+      o.o[c] = b_tq[c]; o.o[2 + c] = b_q[c]; o.o[4 + c] = b_qa[c];
+      o.o[10 + c] = (mode & 4) ? b_coef[c] : b_dout[c]; o.o[12 + c] = b_loss[c];
+    }
+    o.o[6] = b_r; o.o[7] = b_d; o.o[8] = b_lp2; o.o[9] = b_y; o.o[14] = b_lp; o.o[15] = b_ploss;
+    o.ntiles = (cfg.batch_size + TAIL_ROWS - 1) / TAIL_ROWS;
+    return o;
+  }
+  Op op_delta(bool actor) const {
+    Op o = blank(OP_DELTA);
+    const int L = q1.L();
+    o.act = q1.act_h;
+    for (int c = 0; c < 2; ++c) {
+      o.o[c] = actor ? b_coef[c] : b_dout[c];
+      o.o[2 + c] = (c ? q2 : q1).W[L];
+      o.o[4 + c] = a_q[c].aux(L - 1);
+      o.o[6 + c] = d_q[c][L - 1];
+    }
+    o.i[0] = a_q[0].ld[L - 1]; o.i[1] = q1.dims[L];
+    o.i[2] = (cfg.batch_size + DELTA_ROWS - 1) / DELTA_ROWS;
+    o.ntiles = 2 * o.i[2];
     return o;
   }
   // large batch: the policy head as [tensor-core GEMM -> one-thread-per-row tail] instead of the one-warp-per-row head op
@@ -508,17 +552,18 @@ struct Engine {
     for (int l = 0; l < q1.L(); ++l) {
       pb.phase();
       for (int c = 0; c < 2; ++c)
-        pb.add(gemm_fwd(c ? q2 : q1, l, T0 - q1.begin, l ? a_qt[c].h[l - 1] : x_s2, l ? a_qt[c].ld[l - 1] : ldx, a_qt[c]));
+        pb.add(gemm_fwd_q(c, l, T0 - q1.begin, l ? a_qt[c].h[l - 1] : x_s2, l ? a_qt[c].ld[l - 1] : ldx, a_qt[c], b_tq[c]));
     }
-    pb.phase(); pb.add(op_q_row(1));
+    pb.phase(); pb.add(tc_rows() ? op_q_tail(1) : op_q_row(1));
   }
   void emit_critic(PB& pb, int flags) const {
     for (int l = 0; l < q1.L(); ++l) {
       pb.phase();
       if (l == 0 && (flags & DW_ADAM)) pb.add(op_prologue((1 << OPT_Q1) | (1 << OPT_Q2)));
-      for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l, 0, l ? a_q[c].h[l - 1] : x_sa, l ? a_q[c].ld[l - 1] : ldx, a_q[c]));
+      for (int c = 0; c < 2; ++c) pb.add(gemm_fwd_q(c, l, 0, l ? a_q[c].h[l - 1] : x_sa, l ? a_q[c].ld[l - 1] : ldx, a_q[c], b_q[c]));
     }
-    pb.phase(); pb.add(op_q_row(2));
+    if (tc_rows()) { pb.phase(); pb.add(op_q_tail(2)); pb.phase(); pb.add(op_delta(false)); }
+    else { pb.phase(); pb.add(op_q_row(2)); }
     for (int k = 0; k < bwd_stages(q1); ++k) {
       pb.phase();
       for (int c = 0; c < 2; ++c)
@@ -539,9 +584,10 @@ struct Engine {
   void emit_actor_tail(PB& pb, int flags, int final_mode) const {
     for (int l = 0; l < q1.L(); ++l) {
       pb.phase();
-      for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l, 0, l ? a_q[c].h[l - 1] : x_pi, l ? a_q[c].ld[l - 1] : ldx, a_q[c]));
+      for (int c = 0; c < 2; ++c) pb.add(gemm_fwd_q(c, l, 0, l ? a_q[c].h[l - 1] : x_pi, l ? a_q[c].ld[l - 1] : ldx, a_q[c], b_qa[c]));
     }
-    pb.phase(); pb.add(op_actor_q());
+    if (tc_rows()) { pb.phase(); pb.add(op_q_tail(4)); pb.phase(); pb.add(op_delta(true)); }
+    else { pb.phase(); pb.add(op_actor_q()); }
     for (int k = 0; k + 1 < q1.L(); ++k) {
       pb.phase();
       for (int c = 0; c < 2; ++c)
@@ -570,19 +616,20 @@ struct Engine {
     // tile order matters: tiles wrap round the 148 CTAs, so the second-wave tiles (Q2 layer 0) land on the CTAs
     // that ran Q1 layer 0 (two short GEMM tiles) and not behind a head tile
     pb.phase();
-    pb.add(gemm_fwd(q1, 0, 0, x_sa, ldx, a_q[0]));
+    pb.add(gemm_fwd_q(0, 0, 0, x_sa, ldx, a_q[0], b_q[0]));
     if (tc_heads()) { pb.add(gemm_pi_head(false)); pb.add(gemm_pi_head(true)); }
     else { pb.add(op_pi_head(false)); pb.add(op_pi_head(true)); }
-    pb.add(gemm_fwd(q2, 0, 0, x_sa, ldx, a_q[1]));
+    pb.add(gemm_fwd_q(1, 0, 0, x_sa, ldx, a_q[1], b_q[1]));
     if (tc_heads()) { pb.phase(); pb.add(op_pi_tail(false)); pb.add(op_pi_tail(true)); }
     for (int l = 0; l < q1.L(); ++l) {
       pb.phase();
       for (int c = 0; c < 2; ++c)
-        pb.add(gemm_fwd(c ? q2 : q1, l, T0 - q1.begin, l ? a_qt[c].h[l - 1] : x_s2, l ? a_qt[c].ld[l - 1] : ldx, a_qt[c]));
+        pb.add(gemm_fwd_q(c, l, T0 - q1.begin, l ? a_qt[c].h[l - 1] : x_s2, l ? a_qt[c].ld[l - 1] : ldx, a_qt[c], b_tq[c]));
       if (l + 1 < q1.L())
-        for (int c = 0; c < 2; ++c) pb.add(gemm_fwd(c ? q2 : q1, l + 1, 0, a_q[c].h[l], a_q[c].ld[l], a_q[c]));
+        for (int c = 0; c < 2; ++c) pb.add(gemm_fwd_q(c, l + 1, 0, a_q[c].h[l], a_q[c].ld[l], a_q[c], b_q[c]));
     }
-    pb.phase(); pb.add(op_q_row(3));      // target y and critic delta chained on the same row: one phase
+    if (tc_rows()) { pb.phase(); pb.add(op_q_tail(3)); pb.phase(); pb.add(op_delta(false)); }
+    else { pb.phase(); pb.add(op_q_row(3)); }      // target y and critic delta chained on the same row: one phase
     for (int k = 0; k < bwd_stages(q1); ++k) {   // critic Adam with the Polyak update fused behind it (K10)
       pb.phase();
       for (int c = 0; c < 2; ++c)
@@ -1015,6 +1062,7 @@ struct Engine {
   bool tc_wanted(std::string& why) const {
     const char* env = getenv("SACX_TC");
     if (env && atoi(env) == 0) { why = "disabled by SACX_TC=0"; return false; }
+    if (tc_forbid) { why = "tensor-core setup failed"; return false; }
     if (cfg.n_agents == 1 && cfg.batch_size < tc_min_batch) { why = "batch below the tensor-core threshold"; return false; }
     if (cfg.n_agents > 1) {      // population: every agent contributes >= one 128-row tile; enough agents to fill the chip
       const char* pe = getenv("SACX_TC_POP");

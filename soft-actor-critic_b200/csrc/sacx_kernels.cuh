@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
             case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
             case OP_PI_HEAD: tile_pi_head<0>(op, rc, lt); __syncthreads(); break;
             case OP_PI_TAIL: tile_pi_tail(op, rc, lt); break;
+            case OP_Q_TAIL: tile_q_tail(op, rc, lt); break;
+            case OP_DELTA: tile_delta(op, rc, lt); break;
             case OP_Q_ROW: tile_q_row<0>(op, rc, lt); __syncthreads(); break;
             case OP_ACTOR_Q: tile_actor_q<0>(op, rc, lt); __syncthreads(); break;
             case OP_ACTOR_BWD: tile_actor_bwd<0>(op, rc, lt); __syncthreads(); break;
@@ -278,6 +280,8 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
         case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
         case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); break;
         case OP_PI_TAIL: tile_pi_tail(op, rc, lt); break;
+        case OP_Q_TAIL: tile_q_tail(op, rc, lt); break;
+        case OP_DELTA: tile_delta(op, rc, lt); break;
         case OP_Q_ROW: tile_q_row<1>(op, rc, lt); break;
         case OP_ACTOR_Q: tile_actor_q<1>(op, rc, lt); break;
         case OP_ACTOR_BWD: tile_actor_bwd<1>(op, rc, lt); break;

@@ -255,6 +255,68 @@ __device__ __forceinline__ void tile_pi_tail(const Op& op, const RowCtx& c, int 
   if (bad) atomicOr(&c.scal->nonfinite, 1);
 }
 
+// ---------------------------------------------------------------- OP_Q_TAIL / OP_DELTA (large batch, tensor-core path)
+// The critics' output layer (N = 1) rides on the last hidden layer's GEMM: its epilogue thread owns a whole row and projects
+// it onto W_L (sacx_tc.cuh: TcOp.proj_*), leaving z = h . W_L + b in the q buffers. What remains of OP_Q_ROW / OP_ACTOR_Q is
+// scalar work per row (OP_Q_TAIL, one thread per row) and one element-wise pass that needs h again (OP_DELTA).
+// mode bits: 1 target y (agent.py:195-211), 2 critic loss gradient (agent.py:213-236), 4 actor routing (agent.py:238-260).
+// o[0..1]=tq (z in, value out) o[2..3]=q (z in, value out) o[4..5]=qa (z in, value out) o[6]=r o[7]=d o[8]=lp2 o[9]=y
+// o[10..11]=dout/coef (row stride 4) o[12..13]=lossrow o[14]=lp o[15]=plossrow
+__device__ __forceinline__ void tile_q_tail(const Op& op, const RowCtx& c, int tile) {
+  const Hyper& hp = c.args->hp;
+  float* base = c.base;
+  const int row = tile * TAIL_ROWS + threadIdx.x;
+  if (row >= hp.B) return;
+  const float alpha = __ldcg(&c.scal->alpha_f32);
+  float y = 0.f;
+  if (op.mode & 1) {
+    const float t0 = act_fwd(op.act_out, __ldcg(base + op.o[0] + row)), t1 = act_fwd(op.act_out, __ldcg(base + op.o[1] + row));
+    const float r = __ldcg(base + op.o[6] + row), d = __ldcg(base + op.o[7] + row), lp2 = __ldcg(base + op.o[8] + row);
+    y = r + (hp.gamma * (1.f - d)) * (fminf(t0, t1) - alpha * lp2);
+    base[op.o[0] + row] = t0; base[op.o[1] + row] = t1; base[op.o[9] + row] = y;
+  }
+  if (op.mode & 2) {
+    if (!(op.mode & 1)) y = c.args->y_ext ? c.args->y_ext[row] : __ldcg(base + op.o[9] + row);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const float z = __ldcg(base + op.o[2 + cc] + row), q = act_fwd(op.act_out, z), diff = q - y;
+      base[op.o[2 + cc] + row] = q;
+      base[op.o[10 + cc] + (i64)row * 4] = (2.f * diff / (float)hp.B_global) * act_dz2(op.act_out, z, q);
+      base[op.o[12 + cc] + row] = diff * diff;
+    }
+  }
+  if (op.mode & 4) {
+    const float z0 = __ldcg(base + op.o[4] + row), z1 = __ldcg(base + op.o[5] + row);
+    const float q0 = act_fwd(op.act_out, z0), q1 = act_fwd(op.act_out, z1);
+    const float w1 = q0 < q1 ? 1.f : (q0 == q1 ? 0.5f : 0.f);            // torch.min backward, ties split
+    base[op.o[4] + row] = q0; base[op.o[5] + row] = q1;
+    base[op.o[10] + (i64)row * 4] = (-w1 / (float)hp.B_global) * act_dz2(op.act_out, z0, q0);
+    base[op.o[11] + (i64)row * 4] = (-(1.f - w1) / (float)hp.B_global) * act_dz2(op.act_out, z1, q1);
+    base[op.o[15] + row] = alpha * __ldcg(base + op.o[14] + row) - fminf(q0, q1);
+  }
+}
+
+// o[0..1]=coef (row stride 4) o[2..3]=W_L o[4..5]=aux (saved activation, ld i[0]) o[6..7]=delta out (ld i[0])  i[1]=H  i[2]=tiles per critic
+// tile = 16 rows of one critic; thread = one float4 of a row, 256 / (H / 4) rows per pass
+constexpr int DELTA_ROWS = 16;
+__device__ __forceinline__ void tile_delta(const Op& op, const RowCtx& c, int tile) {
+  const Hyper& hp = c.args->hp;
+  float* base = c.base;
+  const int cc = tile / op.i[2], rb = (tile % op.i[2]) * DELTA_ROWS;
+  const int H = op.i[1], ld = op.i[0], cpr = H >> 2;
+  if ((int)threadIdx.x >= (256 / cpr) * cpr) return;
+  const int k = (threadIdx.x % cpr) << 2, r0 = threadIdx.x / cpr, rstep = 256 / cpr;
+  const float4 w = __ldg(reinterpret_cast<const float4*>(base + op.o[2 + cc] + k));
+  for (int r = r0; r < DELTA_ROWS; r += rstep) {
+    const int row = rb + r;
+    if (row >= hp.B) break;
+    const float co = __ldcg(base + op.o[cc] + (i64)row * 4);
+    const float4 h = __ldcs(reinterpret_cast<const float4*>(base + op.o[4 + cc] + (i64)row * ld + k));
+    *reinterpret_cast<float4*>(base + op.o[6 + cc] + (i64)row * ld + k) =
+        make_float4(co * w.x * act_dz(op.act, h.x), co * w.y * act_dz(op.act, h.y), co * w.z * act_dz(op.act, h.z), co * w.w * act_dz(op.act, h.w));
+  }
+}
+
 // ---------------------------------------------------------------- OP_Q_ROW: target y (mode & 1) and / or critic delta (mode & 2)
 // target: o[0..1]=hqt(last hidden) o[2..3]=Wt_L o[4..5]=bt_L o[6]=r o[7]=d o[8]=lp2 o[9]=y o[10..11]=tq
 // critic: o[12..13]=hq(last hidden) o[14..15]=aux(z or h) o[16..17]=W_L o[18..19]=b_L o[20..21]=q out o[22..23]=dout

@@ -56,6 +56,9 @@ struct TcOp {
   int has_aux, pad;
   i64 bias;                  // FWD: arena offset of the bias row
   i64 bias_part;             // DW: scratch offset of the bias partials [split * m_tiles][8 splitter warps][128] (-1: none)
+  // FWD: projection of every output row onto one weight vector (critic head riding on the last hidden layer's GEMM: the epilogue
+  // thread owns the whole 256-wide row): out[m] = sum_n act(...)[m][n] * w[n] + b.  Arena offsets, -1: none
+  i64 proj_w, proj_b, proj_out;
 };
 
 struct TcParams {
@@ -161,11 +164,12 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
   extern __shared__ __align__(1024) uint8_t tc_raw[];
   __shared__ __align__(8) uint64_t full[TC_STAGES], ready[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], aux_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ long long ts[4][8][3];            // SACX_TC_DBG & 128: per-role timestamps of CTA 0's first 8 tiles
+  __shared__ long long ts[4][4][3];            // SACX_TC_DBG & 128: per-role timestamps of CTA 0's first 4 tiles
   const long long t_start = clock64();
   uint8_t* smem = tc_raw;
   if ((tc_smem(tc_raw) & 1023u) != 0u) __trap();        // swizzled tiles need 1024-byte alignment (declared on tc_raw)
   __shared__ __align__(16) float bias_sm[TC_NMAX];     // FWD: bias row of the epilogue's current tile
+  __shared__ __align__(16) float proj_sm[TC_NMAX];     // FWD: projection vector of the current tile (critic head)
   uint8_t* stg = smem + TC_STAGES * TC_STAGE_BYTES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -194,11 +198,11 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         const CUtensorMap* ma = &maps.a[t.op];
         const CUtensorMap* mb = &maps.b[t.op];
         const int tn_ = (tile - blockIdx.x) / gridDim.x;
-        if (tn_ < 8) ts[0][tn_][0] = clock64() - t_start;
+        if (tn_ < 4) ts[0][tn_][0] = clock64() - t_start;
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           tc_mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
-          if (tn_ < 8 && kb == 0) ts[0][tn_][1] = clock64() - t_start;
+          if (tn_ < 4 && kb == 0) ts[0][tn_][1] = clock64() - t_start;
           tc_mbar_expect_tx(&full[s], (uint32_t)(o.a_bytes + o.b_bytes));
           uint8_t* st = smem + s * TC_STAGE_BYTES;
           const int k = t.k0 + kb * TC_BK;
@@ -208,7 +212,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           if (!o.b_mn) tc_tma_load(st + TC_A_BYTES, mb, &full[s], k, 0, t.agent);
           else
             for (int j = 0; j < o.b_rows; ++j) tc_tma_load(st + TC_A_BYTES + j * TC_SLAB, mb, &full[s], 32 * j, k, t.agent);
-          if (tn_ < 8) ts[0][tn_][2] = clock64() - t_start;
+          if (tn_ < 4) ts[0][tn_][2] = clock64() - t_start;
         }
       }
     }
@@ -222,13 +226,13 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         const uint32_t buf = tc & 1;
         tc_mbar_wait(&acc_empty[buf], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (tc < 8) ts[2][tc][0] = clock64() - t_start;
+        if (tc < 4) ts[2][tc][0] = clock64() - t_start;
         const uint32_t tacc = tmem_base + buf * TC_NMAX;
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           tc_mbar_wait(&ready[s], (it / TC_STAGES) & 1);
           tc_fence_after();
-          if (tc < 8 && kb == 0) ts[2][tc][1] = clock64() - t_start;
+          if (tc < 4 && kb == 0) ts[2][tc][1] = clock64() - t_start;
           const uint32_t hi = tc_smem(smem + s * TC_STAGE_BYTES), lo = hi + TC_HALF;
 #pragma unroll
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
@@ -246,7 +250,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           tc_commit(&empty[s]);
         }
         tc_commit(&acc_full[buf]);
-        if (tc < 8) ts[2][tc][2] = clock64() - t_start;
+        if (tc < 4) ts[2][tc][2] = clock64() - t_start;
       }
     }
   } else if (warp >= 6) {
@@ -266,7 +270,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       for (int kb = 0; kb < t.nkb; ++kb, ++it) {
         const int s = it % TC_STAGES;
         tc_mbar_wait(&full[s], (it / TC_STAGES) & 1);
-        { const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 8 && kb == 0) ts[1][tn_][0] = clock64() - t_start; }
+        { const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 4 && kb == 0) ts[1][tn_][0] = clock64() - t_start; }
         float4* hi = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_HALF);
         // six float4 per thread cover a full-width stage (1536 float4): all loads first, then the arithmetic and stores
@@ -307,7 +311,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         tc_fence_async();
         __syncwarp();
         if (lane == 0) tc_mbar_arrive(&ready[s]);
-        { const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 8) ts[1][tn_][kb == 0 ? 1 : 2] = clock64() - t_start; }
+        { const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 4) ts[1][tn_][kb == 0 ? 1 : 2] = clock64() - t_start; }
       }
       if (want_bias) {
         // thread (k-row r = (st % 128) / 8, 16-byte chunk q = st % 8) holds out-features slab*32 + ((q>>1) ^ (r&3))*8 + (q&1)*4 + e
@@ -345,15 +349,20 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       const uint32_t buf = tc & 1;
       tc_mbar_wait(&acc_full[buf], (tc >> 1) & 1);
       tc_fence_after();
-      if (tid == 0 && tc < 8) ts[3][tc][0] = clock64() - t_start;
+      if (tid == 0 && tc < 4) ts[3][tc][0] = clock64() - t_start;
       const int row = tid;                                  // row of the tile == TMEM lane
       const int crow = (o.kind == EPI_DW) ? (t.split * o.m_tiles + t.mt) * TC_BM : t.m0;
       const int ncols = (o.N + 31) & ~31;
       const int act = o.act;
       if (o.kind == EPI_FWD) {                 // the tile's bias row -> shared memory (the previous tile's readers are past their last chunk: barrier below)
         tc_bar(1, TC_EPI_WARPS * 32);
-        for (int n = tid; n < ncols; n += TC_EPI_WARPS * 32) bias_sm[n] = (n < o.N) ? __ldg(P.arena + t.agent * P.agent_stride + o.bias + n) : 0.f;
+        for (int n = tid; n < ncols; n += TC_EPI_WARPS * 32) {
+          bias_sm[n] = (n < o.N) ? __ldg(P.arena + t.agent * P.agent_stride + o.bias + n) : 0.f;
+          if (o.proj_w >= 0) proj_sm[n] = (n < o.N) ? __ldg(P.arena + t.agent * P.agent_stride + o.proj_w + n) : 0.f;
+        }
       }
+      const bool proj = (o.kind == EPI_FWD) && (o.proj_w >= 0);
+      float pacc = 0.f;
       for (int c0 = 0; c0 < ncols; c0 += 32, ++chunk) {
         uint8_t* sb = stg + (chunk & 1) * TC_STG_BYTES;
         if (tid == 0) tc_bulk_wait_read<1>();               // the store that last read this buffer has drained it
@@ -373,19 +382,24 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         const int sx = row & 7;
         if (o.kind == EPI_FWD) {
           const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c0);       // broadcast reads
+          const float4* p4 = reinterpret_cast<const float4*>(proj_sm + c0);
           if (act == SACX_ACT_RELU) {
 #pragma unroll
             for (int qd = 0; qd < 8; ++qd) {
               const float4 b = b4[qd];
-              srow[qd ^ sx] = make_float4(fmaxf(__uint_as_float(v[4 * qd]) + b.x, 0.f), fmaxf(__uint_as_float(v[4 * qd + 1]) + b.y, 0.f),
-                                          fmaxf(__uint_as_float(v[4 * qd + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[4 * qd + 3]) + b.w, 0.f));
+              const float4 hv = make_float4(fmaxf(__uint_as_float(v[4 * qd]) + b.x, 0.f), fmaxf(__uint_as_float(v[4 * qd + 1]) + b.y, 0.f),
+                                            fmaxf(__uint_as_float(v[4 * qd + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[4 * qd + 3]) + b.w, 0.f));
+              srow[qd ^ sx] = hv;
+              if (proj) { const float4 w = p4[qd]; pacc = fmaf(hv.x, w.x, fmaf(hv.y, w.y, fmaf(hv.z, w.z, fmaf(hv.w, w.w, pacc)))); }
             }
           } else {
 #pragma unroll
             for (int qd = 0; qd < 8; ++qd) {
               const float4 b = b4[qd];
-              srow[qd ^ sx] = make_float4(act_fwd(act, __uint_as_float(v[4 * qd]) + b.x), act_fwd(act, __uint_as_float(v[4 * qd + 1]) + b.y),
-                                          act_fwd(act, __uint_as_float(v[4 * qd + 2]) + b.z), act_fwd(act, __uint_as_float(v[4 * qd + 3]) + b.w));
+              const float4 hv = make_float4(act_fwd(act, __uint_as_float(v[4 * qd]) + b.x), act_fwd(act, __uint_as_float(v[4 * qd + 1]) + b.y),
+                                            act_fwd(act, __uint_as_float(v[4 * qd + 2]) + b.z), act_fwd(act, __uint_as_float(v[4 * qd + 3]) + b.w));
+              srow[qd ^ sx] = hv;
+              if (proj) { const float4 w = p4[qd]; pacc = fmaf(hv.x, w.x, fmaf(hv.y, w.y, fmaf(hv.z, w.z, fmaf(hv.w, w.w, pacc)))); }
             }
           }
         } else if (o.kind == EPI_DACT) {
@@ -417,17 +431,19 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           tc_bulk_commit();
         }
       }
+      if (proj && t.m0 + row < o.M)
+        P.arena[t.agent * P.agent_stride + o.proj_out + t.m0 + row] = pacc + __ldg(P.arena + t.agent * P.agent_stride + o.proj_b);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
-      if (tid == 0 && tc < 8) ts[3][tc][1] = clock64() - t_start;
+      if (tid == 0 && tc < 4) ts[3][tc][1] = clock64() - t_start;
     }
     if (tid == 0) tc_bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
   if ((P.dbg & 128) && blockIdx.x == 0 && tid == 0) {
-    const int nt = min(8, (P.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
+    const int nt = min(4, (P.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
     printf("tc kernel: %d ops, %d tiles, K0 %d; end %lld cycles\n", P.n_ops, P.total_tiles, P.ops[0].K, clock64() - t_start);
     for (int i = 0; i < nt; ++i)
       printf("  tile %d: tma start %lld first-empty %lld issued %lld | split first-full %lld first-done %lld last-done %lld | mma acc-empty %lld "

@@ -22,6 +22,8 @@ enum OpType : int {
   OP_LOAD_EXT,    // copy external y / logpi into arena buffers
   OP_DW_HEAD,     // fused plan: gradient + Adam of the critics' output layer from the head shares
   OP_PI_TAIL,     // large batch: rsample / tanh squash / log_prob from head pre-activations a tensor-core GEMM produced (one thread per row)
+  OP_Q_TAIL,      // large batch: Bellman target / critic loss gradient / actor routing from head values the GEMM epilogue projected (one thread per row)
+  OP_DELTA,       // large batch: delta of the critics' last hidden layer, coef[b] * W_L[k] * act'(h[b][k]) (element-wise stream)
 };
 
 enum Epi : int { EPI_FWD = 1, EPI_DACT = 2, EPI_DW = 3 };
