@@ -292,6 +292,7 @@ static int engine_setup_tc(Engine* e) {
   e->tc = e->tc_wanted(e->tc_why);
   if (!e->tc) return SACX_OK;
   auto off = [&](const std::string& why) { e->tc = false; e->tc_why = why; e->tc_phases.clear(); cudaGetLastError(); return SACX_OK; };
+  if (getenv("SACX_TC_FAIL")) return off("forced setup failure (SACX_TC_FAIL, test hook)");
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)

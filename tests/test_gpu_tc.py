@@ -251,3 +251,27 @@ def test_tc_full_size_batch_65536(monkeypatch):
     assert_close("block.params", a["block.params"], b["block.params"], 1e-4)
     for key in ("q1_loss", "q2_loss", "policy_loss", "log_alpha"):
         assert abs(a["metrics"][key] - b["metrics"][key]) <= 1e-4 * abs(b["metrics"][key]) + 1e-6, key
+
+
+def test_tc_setup_failure_falls_back_to_ffma_plans(monkeypatch):
+    """If the tensor-core setup fails after the plans were built for it (head GEMMs, tails, epilogue projections), the engine
+    rebuilds plain FFMA plans: same results, bit for bit, as an engine created with SACX_TC=0."""
+    obs, act, B = 24, 4, 2048
+    rng = np.random.default_rng(3)
+    idx = rng.choice(2 * B - 7, B, replace=False).astype(np.int64)
+    e1 = rng.standard_normal((B, act)).astype(np.float32)
+    e2 = rng.standard_normal((B, act)).astype(np.float32)
+    res = {}
+    for mode in ("fail", "off"):
+        if mode == "fail":
+            monkeypatch.setenv("SACX_TC_FAIL", "1")
+        else:
+            monkeypatch.delenv("SACX_TC_FAIL", raising=False)
+        eng = _engine(obs, act, (256, 256), (256, 256), B, "relu", monkeypatch, mode == "fail")
+        on, why, _ = eng.tensor_core()
+        assert not on and (("forced" in why) if mode == "fail" else ("SACX_TC=0" in why))
+        m = eng.update_host(idx, e1, e2, 1)
+        assert m["nonfinite"] == 0 and eng.tensor_core()[2] == 0
+        res[mode] = {n: eng.view(n).cpu().numpy().copy() for n in ("block.params", "block.targets", "out.y", "out.logpi", "scr.dhead")}
+    for n in res["off"]:
+        assert np.array_equal(res["fail"][n], res["off"][n]), n
