@@ -92,6 +92,7 @@ class TorchPortSAC:
             self.alpha = torch.tensor(sac["alpha"])
         self.memory: deque = deque(maxlen=capacity)
         self.last: Dict[str, torch.Tensor] = {}
+        self.hook_after_critics = None          # tests: observe the state between the critic steps and the actor step
 
     # -- nets --------------------------------------------------------------------
     def _q(self, params, s, a):
@@ -137,14 +138,17 @@ class TorchPortSAC:
             a2, lp2 = self.sample_action(s2, eps1)
             minq = torch.min(self._q(self.q1t, s2, a2), self._q(self.q2t, s2, a2))
             y = r + gamma * (1 - d) * (minq - alpha * lp2)
-        l1 = F.mse_loss(self._q(self.q1, s, a), y)
-        l2 = F.mse_loss(self._q(self.q2, s, a), y)
+        q1v, q2v = self._q(self.q1, s, a), self._q(self.q2, s, a)
+        l1 = F.mse_loss(q1v, y)
+        l2 = F.mse_loss(q2v, y)
         self.opt_q1.zero_grad()
         l1.backward()
         self.opt_q1.step()
         self.opt_q2.zero_grad()
         l2.backward()
         self.opt_q2.step()
+        if self.hook_after_critics is not None:
+            self.hook_after_critics(self)
         an, lp = self.sample_action(s, eps2)
         minq_pi = torch.min(self._q(self.q1, s, an), self._q(self.q2, s, an))
         lpi = (self.alpha.detach() * lp - minq_pi).mean()
@@ -163,13 +167,36 @@ class TorchPortSAC:
             for tgt, src in ((self.q1t, self.q1), (self.q2t, self.q2)):
                 for t, p in zip(tgt, src):
                     t.copy_(tau * p.data + (1.0 - tau) * t)
-        self.last = {"y": y, "q1_loss": l1.detach(), "q2_loss": l2.detach(), "policy_loss": lpi.detach(), "lp": lp.detach()}
+        self.last = {"y": y, "q1_loss": l1.detach(), "q2_loss": l2.detach(), "policy_loss": lpi.detach(), "lp": lp.detach(),
+                     "q1": q1v.detach(), "q2": q2v.detach(), "q1_pi": None, "q2_pi": None}
         return info
 
     def training_step(self):
         """Comparator (A): full step including the deque sample."""
         batch = self.sample_batch(self.cfg["train"]["batch_size"])
         return self.update_from_batch(*batch)
+
+    # -- checkpoint (sac/agent.py:538-554), statement by statement ------------------------
+    def load_checkpoint(self, ck: dict) -> None:
+        """What the reference's ``load_agent`` does with a ``save_agent`` dict. Note the last branch: the reference REBINDS
+        ``self.log_alpha`` to the loaded tensor while ``alpha_optimizer`` keeps the tensor created in ``__init__`` as its
+        parameter, so after a load the temperature optimiser steps a tensor nobody reads and ``alpha`` stays at
+        ``exp(loaded log_alpha)`` (in the loaded tensor's dtype/shape: ``(1,) float32`` in the shipped files). Restated
+        literally so that the port stays bit-exact to runs the reference continued from a checkpoint."""
+        with torch.no_grad():
+            for ps, key in ((self.pi, "policy_net_state_dict"), (self.q1, "q_net1_state_dict"), (self.q2, "q_net2_state_dict"),
+                            (self.q1t, "q_net1_target_state_dict"), (self.q2t, "q_net2_target_state_dict")):
+                sd = ck[key]
+                for l in range(len(ps) // 2):
+                    ps[2 * l].copy_(sd[f"net.{2 * l}.weight"])
+                    ps[2 * l + 1].copy_(sd[f"net.{2 * l}.bias"])
+        self.opt_pi.load_state_dict(ck["policy_optimizer_state_dict"])
+        self.opt_q1.load_state_dict(ck["q1_optimizer_state_dict"])
+        self.opt_q2.load_state_dict(ck["q2_optimizer_state_dict"])
+        if self.auto:
+            self.log_alpha = ck["log_alpha"]
+            self.opt_alpha.load_state_dict(ck["alpha_optimizer_state_dict"])
+            self.alpha = self.log_alpha.exp()
 
     # -- state access for the pin tests ---------------------------------------------
     def flat_state(self) -> Dict[str, np.ndarray]:

@@ -113,11 +113,17 @@ def _adam(opt):
             for i, d in st.items() for k, v in d.items()}
 
 
-def record_run(agent_mod, name, obs, act, cfg, n_fill, K, full_state=True):
+def record_run(agent_mod, name, obs, act, cfg, n_fill, K, full_state=True, start_ckpt=None, big=False, stride=61, store_init=True):
+    """big=True (batch 65536): the index stream and the normals are NOT stored -- the test regenerates them from the
+    seeds exactly as the reference consumed them (random.seed / torch.manual_seed of SAC._set_seed, agent.py:117-124;
+    checksums are stored to prove it) -- and per-row outputs are stored as strided samples + float64 checksums.
+    start_ckpt: a checkpoint loaded through the reference's own load_agent (agent.py:538-554) before the first update."""
     import torch
 
     env = FakeEnv(obs, act)
     agent = agent_mod.SAC(env, copy.deepcopy(cfg))
+    if start_ckpt is not None:
+        agent.load_agent(start_ckpt)
     B = cfg["train"]["batch_size"]
     s, a, r, s2, d = synth_transitions(n_fill, obs, act)
     for i in range(n_fill):
@@ -128,8 +134,18 @@ def record_run(agent_mod, name, obs, act, cfg, n_fill, K, full_state=True):
         for k, v in dct.items():
             out[f"{prefix}/{k}"] = np.asarray(v)
 
-    for tag, net in (("pi", agent.policy_net), ("q1", agent.q_net1), ("q2", agent.q_net2)):
-        put(f"init/{tag}", _sd(net))
+    def chk(v):
+        v64 = np.asarray(v, dtype=np.float64).ravel()
+        return np.array([v64.sum(), (v64 * v64).sum()])
+
+    if start_ckpt is None:       # (a run started from a checkpoint reads its start state from the .pth fixture)
+        for tag, net in (("pi", agent.policy_net), ("q1", agent.q_net1), ("q2", agent.q_net2)):
+            if store_init:
+                put(f"init/{tag}", _sd(net))
+            else:                # large nets: the init recipe (F10) is reproducible from train.seed; keep its checksums + samples
+                for key, v in _sd(net).items():
+                    out[f"init/{tag}/{key}#chk"] = chk(v)
+                    out[f"init/{tag}/{key}#smp"] = v.ravel()[::97].copy()
 
     cap = {}
     orig_target = agent.compute_target_q_values
@@ -179,16 +195,30 @@ def record_run(agent_mod, name, obs, act, cfg, n_fill, K, full_state=True):
         torch.set_rng_state(ts)
         alpha_before = float(agent.alpha)
         agent.training_step()
-        out[f"step{k}/idx"] = np.asarray(idx, dtype=np.int64)
-        out[f"step{k}/eps1"] = e1.numpy()
-        out[f"step{k}/eps2"] = e2.numpy()
+        if big:
+            out[f"step{k}/idx#chk"] = chk(idx)
+            out[f"step{k}/idx#smp"] = np.asarray(idx, dtype=np.int64)[::stride].copy()
+            out[f"step{k}/eps1#chk"] = chk(e1.numpy())
+            out[f"step{k}/eps2#chk"] = chk(e2.numpy())
+        else:
+            out[f"step{k}/idx"] = np.asarray(idx, dtype=np.int64)
+            out[f"step{k}/eps1"] = e1.numpy()
+            out[f"step{k}/eps2"] = e2.numpy()
         out[f"step{k}/alpha_before"] = np.float64(alpha_before)
         for key in ("y", "q1", "q2", "q1_loss", "q2_loss", "lp"):
-            out[f"step{k}/{key}"] = cap[key]
+            if big and np.ndim(cap[key]) == 1:
+                out[f"step{k}/{key}#chk"] = chk(cap[key])
+                out[f"step{k}/{key}#smp"] = cap[key][::stride].copy()
+            else:
+                out[f"step{k}/{key}"] = cap[key]
         if cfg["sac"]["auto_entropy_tuning"]:
             out[f"step{k}/alpha_loss"] = np.float64(cap["alpha_info"]["alpha_loss"])
             out[f"step{k}/alpha"] = np.float64(cap["alpha_info"]["alpha"])
             out[f"step{k}/log_alpha"] = agent.log_alpha.detach().numpy().copy()
+            if k == K - 1:
+                st = agent.alpha_optimizer.state_dict()["state"]
+                if st:      # (empty after load_agent: the reference's optimiser keeps stepping the PRE-load tensor)
+                    out[f"step{k}/adam_alpha"] = np.array([float(st[0]["exp_avg"]), float(st[0]["exp_avg_sq"]), float(st[0]["step"])])
         nets = (("pi", agent.policy_net), ("q1", agent.q_net1), ("q2", agent.q_net2),
                 ("q1t", agent.q_net1_target), ("q2t", agent.q_net2_target))
         if full_state:
@@ -201,6 +231,11 @@ def record_run(agent_mod, name, obs, act, cfg, n_fill, K, full_state=True):
                 put(f"step{k}/adam_pi", _adam(agent.policy_optimizer))
                 put(f"step{k}/adam_q1", _adam(agent.q1_optimizer))
         else:  # large shapes: float64 checksums per tensor (sum, sum of squares) + a strided sample
+            if k == K - 1:
+                for tag, opt in (("adam_pi", agent.policy_optimizer), ("adam_q1", agent.q1_optimizer)):
+                    for key, v in _adam(opt).items():
+                        out[f"step{k}/{tag}/{key}#chk"] = chk(v)
+                        out[f"step{k}/{tag}/{key}#smp"] = np.asarray(v).ravel()[::97].copy()
             for tag, net in nets:
                 for key, v in _sd(net).items():
                     v64 = v.astype(np.float64).ravel()
@@ -220,7 +255,8 @@ def record_run(agent_mod, name, obs, act, cfg, n_fill, K, full_state=True):
     out["act/eps"] = e.numpy()
     out["act/stochastic"] = agent.select_action(st0)
     out["act/deterministic"] = agent.select_action(st0, deterministic=True)
-    meta = {"obs": obs, "act": act, "n_fill": n_fill, "K": K, "config": cfg, "full_state": full_state}
+    meta = {"obs": obs, "act": act, "n_fill": n_fill, "K": K, "config": cfg, "full_state": full_state, "big": big,
+            "stride": stride, "store_init": store_init, "start_ckpt": os.path.basename(start_ckpt) if start_ckpt else None}
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
     print(f"wrote {name}.npz  ({len(out)} arrays)")
@@ -282,6 +318,11 @@ def record_checkpoint_schema(agent, name="checkpoint_schema"):
 
 def main():
     agent_mod, rb_mod = _import_reference()
+    if "--round2-only" in sys.argv:      # keep the round-1 files byte-identical: tiny_auto is re-run into a scratch file
+        a = record_run(agent_mod, "_scratch_tiny_auto", 3, 2, make_config([8, 8], batch=8, auto=True), n_fill=50, K=3)
+        os.remove(os.path.join(HERE, "_scratch_tiny_auto.npz"))
+        record_round2(agent_mod, a)
+        return
     record_sampling(rb_mod)
     a = record_run(agent_mod, "tiny_auto", 3, 2, make_config([8, 8], batch=8, auto=True), n_fill=50, K=3)
     record_checkpoint_schema(a)
@@ -297,6 +338,52 @@ def main():
                n_fill=3000, K=3, full_state=False)
     record_run(agent_mod, "pendulum128", 4, 1, make_config([128, 128], batch=256, auto=True, capacity=2000),
                n_fill=2500, K=2, full_state=False)
+    record_round2(agent_mod, a)
+
+
+SHIPPED_CKPT = REF + "/notebooks/runs/InvertedPendulum-v5/SAC/sac-inverted-pendulum-2025_11_30-11_40_35/sac_agent.pth"
+
+
+def record_round2(agent_mod, tiny_agent):
+    """Round 2: the BASELINE configurations 3, 4, 5 themselves, a K = 10 free run, and runs that start
+    from reference-WRITTEN checkpoints (agent.py:521-536) in both ``log_alpha`` forms (0-dim float64 as written today;
+    (1,) float32 as in the shipped files)."""
+    # cfg 3: InvertedPendulum shape of the Optuna study (hparam_search/configs/inverted_pendulum.yaml): 4/1/2x256, batch 256
+    record_run(agent_mod, "cfg3_pendulum256", 4, 1, make_config([256, 256], batch=256, auto=True, capacity=2000),
+               n_fill=2500, K=3, full_state=False, store_init=False)
+    # cfg 4: Donkey latent 32/2/2x256, batch 1024, 50k ring; its shipped network [256,256,32] elu
+    # (notebooks/configs/donkey_car_new.yaml:15-16,8-11: fixed alpha, tau 0.02, lr 4e-4); real observation width 216 (F11)
+    record_run(agent_mod, "cfg4_donkey", 32, 2, make_config([256, 256], batch=1024, auto=True, capacity=50000),
+               n_fill=3000, K=2, full_state=False, store_init=False)
+    cfg = make_config([256, 256, 32], act="elu", batch=1024, auto=False, alpha=0.1, capacity=50000, seed=23)
+    cfg["sac"].update(tau=0.02, actor_lr=4e-4, critic_lr=4e-4, alpha_lr=4e-4)
+    record_run(agent_mod, "cfg4_donkey_elu", 32, 2, cfg, n_fill=3000, K=2, full_state=False, store_init=False)
+    record_run(agent_mod, "cfg4_donkey_obs216", 216, 2, make_config([256, 256], batch=1024, auto=True, capacity=50000),
+               n_fill=2000, K=1, full_state=False, store_init=False)
+    # cfg 5: BipedalWalker shape at a per-rank slice (2048 rows) and at the full global batch (65536 rows, one update)
+    record_run(agent_mod, "cfg5_b2048", 24, 4, make_config([256, 256], batch=2048, auto=True, capacity=5000),
+               n_fill=5000, K=2, full_state=False, store_init=False)
+    record_run(agent_mod, "cfg5_b65536", 24, 4, make_config([256, 256], batch=65536, auto=True, capacity=100000),
+               n_fill=100000 - 3, K=1, full_state=False, big=True, store_init=False)
+    # SURVEY 8c protocol: K = 10 free-running updates at BipedalWalker shape
+    record_run(agent_mod, "bipedal_k10", 24, 4, make_config([256, 256], batch=256, auto=True, capacity=5000),
+               n_fill=3000, K=10, full_state=False, store_init=False)
+    # reference-written checkpoints and runs continued from them
+    import torch
+    p = os.path.join(HERE, "ref_ckpt_tiny_auto.pth")
+    tiny_agent.save_agent(p)                                    # after the 3 recorded updates of tiny_auto
+    print("wrote", os.path.basename(p))
+    record_run(agent_mod, "ckpt_tiny_auto", 3, 2, make_config([8, 8], batch=8, auto=True), n_fill=50, K=2, start_ckpt=p)
+    cfgp = make_config([128, 128], batch=256, auto=True, capacity=2000)
+    env = FakeEnv(4, 1)
+    ag = agent_mod.SAC(env, copy.deepcopy(cfgp))
+    ag.load_agent(SHIPPED_CKPT)                                  # shipped: Adam step 39886, log_alpha (1,) float32
+    p2 = os.path.join(HERE, "ref_ckpt_pendulum128_auto.pth")
+    ag.save_agent(p2)                                            # re-written by the reference's own save_agent
+    ck = torch.load(p2, map_location="cpu", weights_only=False)
+    assert tuple(ck["log_alpha"].shape) == (1,) and ck["log_alpha"].dtype == torch.float32
+    print("wrote", os.path.basename(p2))
+    record_run(agent_mod, "ckpt_pendulum128", 4, 1, cfgp, n_fill=2500, K=3, full_state=False, start_ckpt=p2)
 
 
 if __name__ == "__main__":

@@ -90,3 +90,34 @@ def assert_close(name, got, ref, tol):
     e = rel_l2(got, ref)
     assert e < tol, f"{name}: rel-L2 {e:.3e} >= {tol:.1e}"
     return e
+
+
+def set_engine_state(eng, st, agent=0):
+    """Put a ReferenceRun.state() snapshot into the engine: parameters, targets, Adam moments and step counters, temperature."""
+    load_nets(eng, {t: st[t] for t in ("pi", "q1", "q2", "q1t", "q2t")}, agent=agent)
+    steps = [0, 0, 0, 0]
+    for oi, tag in enumerate(("pi", "q1", "q2")):
+        for nm, (m, v, step) in st["adam"][tag].items():
+            l = int(nm.split(".")[1]) // 2
+            wb = "W" if nm.endswith("weight") else "b"
+            eng.view(f"m.{tag}.{wb}{l}", agent).reshape(m.shape).copy_(torch.as_tensor(m))
+            eng.view(f"v.{tag}.{wb}{l}", agent).reshape(v.shape).copy_(torch.as_tensor(v))
+            steps[oi] = int(step)
+    if "log_alpha" in st:
+        eng.view("scal.log_alpha", agent).fill_(st["log_alpha"])
+        eng.view("scal.alpha_m", agent).fill_(st["adam_alpha"][0])
+        eng.view("scal.alpha_v", agent).fill_(st["adam_alpha"][1])
+        steps[3] = int(st["adam_alpha"][2])
+    eng.view("scal.step", agent).copy_(torch.as_tensor(steps, dtype=torch.int64))
+    eng.refresh_alpha()
+
+
+def net_errs(eng, tag, ref_sd, prefix="", agent=0):
+    """{tensor name: rel-L2 error} of one network block of the engine against a reference state_dict."""
+    got = read_net(eng, tag, len(ref_sd) // 2, prefix=prefix, agent=agent)
+    return {nm: rel_l2(got[nm], ref_sd[nm]) for nm in ref_sd}
+
+
+def assert_net(eng, tag, ref_sd, tol, what, prefix="", agent=0):
+    for nm, e in net_errs(eng, tag, ref_sd, prefix, agent).items():
+        assert e < tol, f"{what} {prefix}{tag}.{nm}: rel-L2 {e:.3e} >= {tol:.1e}"
