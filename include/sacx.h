@@ -65,6 +65,8 @@ typedef struct sacx_config {
   double  actor_lr, critic_lr, alpha_lr;                      /* sac.*_lr                      */
   uint64_t seed;                                              /* device RNG key (train.seed)   */
   int32_t dp_world, dp_rank;                                  /* large-batch data parallel: batch_size is per rank */
+  int32_t agent_id_base;                                      /* population sharded over ranks: global id of local agent 0 (keys the device RNG streams) */
+  int32_t reserved_i;
 } sacx_config;
 
 typedef struct sacx_ring_s*  sacx_ring_t;    /* replaces sac.replay_buffer.ReplayBuffer        */

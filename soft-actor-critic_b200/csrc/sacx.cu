@@ -260,6 +260,8 @@ static int engine_setup_rp(Engine* e) {
   const int rounds = (nrb + n_groups - 1) / n_groups;
   n_groups = (nrb + rounds - 1) / rounds;
   e->rp_grid = n_groups * RP_CS;
+  if (e->d_rp_part) { cudaFree(e->d_rp_part); e->d_rp_part = nullptr; }       // (second call: plans rebuilt after a failed tensor-core setup)
+  if (e->d_prog) { cudaFree(e->d_prog); e->d_prog = nullptr; }
   SACX_CUDA(cudaMalloc((void**)&e->d_rp_part, sizeof(float) * (size_t)RP_MAX_GROUPS * e->h_prog.part_stride));
   SACX_CUDA(cudaMemset(e->d_rp_part, 0, sizeof(float) * (size_t)RP_MAX_GROUPS * e->h_prog.part_stride));
   SACX_CUDA(cudaMalloc((void**)&e->d_prog, sizeof(RpProgram)));
@@ -292,7 +294,9 @@ static int engine_setup_tc(Engine* e) {
   e->tc = e->tc_wanted(e->tc_why);
   if (!e->tc) return SACX_OK;
   auto off = [&](const std::string& why) { e->tc = false; e->tc_why = why; e->tc_phases.clear(); cudaGetLastError(); return SACX_OK; };
+#ifdef SACX_DEBUG_HOOKS      // failure injection for tests/test_gpu_tc.py (libsacx_debug.so only)
   if (getenv("SACX_TC_FAIL")) return off("forced setup failure (SACX_TC_FAIL, test hook)");
+#endif
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
@@ -352,7 +356,9 @@ static int engine_setup_tc(Engine* e) {
           memset(&g.p, 0, sizeof g.p); memset(&g.maps, 0, sizeof g.maps); memset(&g.red, 0, sizeof g.red);
           g.p.arena = e->arena; g.p.scratch = e->d_tc_scratch;
           g.p.n_agents = (int)NA; g.p.agent_stride = (i64)AS; g.p.scratch_stride = (i64)sstride;
+#ifdef SACX_DEBUG_HOOKS
           { const char* dv = getenv("SACX_TC_DBG"); g.p.dbg = dv ? atoi(dv) : 0; }
+#endif
           g.red.arena = e->arena; g.red.scratch = e->d_tc_scratch; g.red.scal_off = e->scal_off; g.red.hp = e->hp;
           g.red.agent_stride = (i64)AS; g.red.scratch_stride = (i64)sstride;
           int tiles = 0;
@@ -462,8 +468,15 @@ static int engine_init_scalars(Engine* e) {
   s.alpha_f32 = (float)s.alpha;
   s.metrics[4] = (float)s.alpha;
   s.metrics[5] = (float)s.log_alpha;
-  for (int ag = 0; ag < e->cfg.n_agents; ++ag)
-    SACX_CUDA(cudaMemcpyAsync(e->arena + (i64)ag * e->stride + e->scal_off, &s, sizeof s, cudaMemcpyHostToDevice, e->stream));
+  // per-agent hyper-parameters start at the config's values (lr 0 = "use Hyper.lr"); the device RNG streams are keyed by
+  // (train.seed, GLOBAL agent id): agents that share a local index on different ranks draw different streams
+  s.gamma = e->hp.gamma; s.tau = e->hp.tau; s.one_minus_tau = e->hp.one_minus_tau;
+  s.rng_seed = e->hp.seed;
+  std::vector<AgentScalars> all((size_t)e->cfg.n_agents, s);
+  for (int ag = 0; ag < e->cfg.n_agents; ++ag) {
+    all[ag].rng_agent = (unsigned)(e->cfg.agent_id_base + ag);
+    SACX_CUDA(cudaMemcpyAsync(e->arena + (i64)ag * e->stride + e->scal_off, &all[ag], sizeof s, cudaMemcpyHostToDevice, e->stream));
+  }
   SACX_CUDA(cudaStreamSynchronize(e->stream));
   return SACX_OK;
 }
@@ -566,9 +579,19 @@ int sacx_ring_destroy(sacx_ring_t h) {
 
 int sacx_ring_set_stream(sacx_ring_t h, void* stream) {
   if (!h) return fail(SACX_ERR_INVALID, "null ring");
-  int rc = h->r.flush();
+  Ring& r = h->r;
+  int rc = r.flush();
   if (rc) return rc;
-  h->r.stream = (cudaStream_t)stream;
+  if ((cudaStream_t)stream != r.stream) {
+    // work already queued on the old stream (the flush's scatter, earlier pushes) must be ordered before anything the new
+    // stream does with the ring: record on the old stream, make the new one wait
+    cudaEvent_t ev;
+    SACX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SACX_CUDA(cudaEventRecord(ev, r.stream));
+    SACX_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ev, 0));
+    SACX_CUDA(cudaEventDestroy(ev));
+  }
+  r.stream = (cudaStream_t)stream;
   return SACX_OK;
 }
 
@@ -721,6 +744,7 @@ int sacx_agent_arena_floats(const sacx_config* cfg, int64_t* out) {
   return SACX_OK;
 }
 
+// (error paths of create release whatever was allocated so far through the one destroy routine)
 int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* out) {
   int rc = validate(cfg);
   if (rc) return rc;
@@ -756,8 +780,8 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   hp.obs = cfg->obs_dim; hp.act = cfg->act_dim; hp.B = cfg->batch_size;
   hp.B_global = cfg->batch_size * e.cfg.dp_world; hp.row0_global = cfg->batch_size * e.cfg.dp_rank;
   hp.seed = cfg->seed;
-  if ((rc = e.build_plans())) { delete h; return rc; }
-  if ((rc = engine_setup_rp(&e))) { delete h; return rc; }
+  if ((rc = e.build_plans())) { sacx_agent_destroy(h); return rc; }
+  if ((rc = engine_setup_rp(&e))) { sacx_agent_destroy(h); return rc; }
   // launch geometry: one CTA per SM; a single agent spreads over the chip, a population gets one CTA per agent
   const size_t gemm_floats = e.large ? CfgLarge::SMEM_FLOATS : CfgSmall::SMEM_FLOATS;
   e.smem_bytes = (int)(SMEM_OPS * sizeof(Op) + WSM_FLOATS * 4 + gemm_floats * 4 + XSM_FLOATS * 4);
@@ -766,7 +790,7 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   int per_sm = 0;
   if (e.large) SACX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sacx_run_kernel<true>, 256, e.smem_bytes));
   else SACX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sacx_run_kernel<false>, 256, e.smem_bytes));
-  if (per_sm < 1) { delete h; return fail(SACX_ERR_CUDA, "update kernel does not fit on an SM"); }
+  if (per_sm < 1) { sacx_agent_destroy(h); return fail(SACX_ERR_CUDA, "update kernel does not fit on an SM"); }
   e.max_ctas = e.n_sms;                                      // one CTA per SM (persistent)
   if (cfg->n_agents == 1) {
     e.grid_x = cfg->ctas_per_agent > 0 ? cfg->ctas_per_agent : std::min(e.max_ctas, e.max_phase_tiles());
@@ -786,21 +810,21 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   {
     std::string w;
     const bool planned = e.tc_wanted(w);
-    if ((rc = engine_setup_tc(&e))) { delete h; return rc; }
+    if ((rc = engine_setup_tc(&e))) { sacx_agent_destroy(h); return rc; }
     if (planned && !e.tc) {            // the plans were built for the tensor-core path (head GEMMs, tails, projections): rebuild without
       e.tc_forbid = true;
-      if ((rc = e.build_plans())) { delete h; return rc; }
-      if ((rc = engine_setup_rp(&e))) { delete h; return rc; }
+      if ((rc = e.build_plans())) { sacx_agent_destroy(h); return rc; }
+      if ((rc = engine_setup_rp(&e))) { sacx_agent_destroy(h); return rc; }
     }
   }
-  if ((rc = engine_setup_rp_tma(&e))) { delete h; return rc; }
+  if ((rc = engine_setup_rp_tma(&e))) { sacx_agent_destroy(h); return rc; }
   SACX_CUDA(cudaMalloc((void**)&e.d_plans, sizeof(Plan) * N_PLANS));
   SACX_CUDA(cudaMemcpy(e.d_plans, e.h_plans.data(), sizeof(Plan) * N_PLANS, cudaMemcpyHostToDevice));
   SACX_CUDA(cudaMalloc((void**)&e.d_barrier, sizeof(unsigned) * 64 * 4096));
   SACX_CUDA(cudaMemset(e.d_barrier, 0, sizeof(unsigned) * 64 * 4096));
   { const char* bm = getenv("SACX_BARRIER"); e.barrier_mode = bm ? atoi(bm) : 1; }
   SACX_CUDA(cudaMallocHost((void**)&e.pinned_metrics, sizeof(sacx_metrics)));
-  if ((rc = engine_init_scalars(&e))) { delete h; return rc; }
+  if ((rc = engine_init_scalars(&e))) { sacx_agent_destroy(h); return rc; }
   *out = h;
   return SACX_OK;
 }
@@ -826,7 +850,15 @@ int sacx_agent_destroy(sacx_agent_t h) {
 
 int sacx_agent_set_stream(sacx_agent_t h, void* stream) {
   if (!h) return fail(SACX_ERR_INVALID, "null agent");
-  h->e.stream = (cudaStream_t)stream;
+  Engine& e = h->e;
+  if ((cudaStream_t)stream != e.stream) {       // updates queued on the old stream come first
+    cudaEvent_t ev;
+    SACX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SACX_CUDA(cudaEventRecord(ev, e.stream));
+    SACX_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ev, 0));
+    SACX_CUDA(cudaEventDestroy(ev));
+  }
+  e.stream = (cudaStream_t)stream;
   return SACX_OK;
 }
 int sacx_agent_attach_ring(sacx_agent_t h, sacx_ring_t r) {
@@ -1154,7 +1186,7 @@ int sacx_act(sacx_agent_t h, int32_t agent, const float* s, int32_t n, const flo
   const int mw = max_width(e.pi);
   act_kernel<<<n, 256, (size_t)2 * mw * 4, e.stream>>>(e.arena, make_ref(e.pi, 0), mw, s, eps, deterministic,
                                                       a_out, e.cfg.act_dim, e.hp.log_std_min, e.hp.log_std_max, e.hp.action_scale,
-                                                      e.hp.seed, e.act_calls++, agent, e.stride);
+                                                      e.scal_off, e.act_calls++, agent, e.stride);
   ++e.launches;
   SACX_CUDA(cudaGetLastError());
   return SACX_OK;
@@ -1167,7 +1199,7 @@ int sacx_act_population(sacx_agent_t h, const float* s, int32_t n_per_agent, con
   const int mw = max_width(e.pi);
   act_kernel<<<dim3(n_per_agent, e.cfg.n_agents), 256, (size_t)2 * mw * 4, e.stream>>>(
       e.arena, make_ref(e.pi, 0), mw, s, eps, deterministic, a_out, e.cfg.act_dim, e.hp.log_std_min, e.hp.log_std_max, e.hp.action_scale,
-      e.hp.seed, e.act_calls++, 0, e.stride);
+      e.scal_off, e.act_calls++, 0, e.stride);
   ++e.launches;
   SACX_CUDA(cudaGetLastError());
   return SACX_OK;

@@ -181,6 +181,11 @@ struct Engine {
       sub("scal.metrics", offsetof(AgentScalars, metrics), 12, 0);
       sub("scal.nonfinite", offsetof(AgentScalars, nonfinite), 1, 0);
       sub("scal.dp_alpha", offsetof(AgentScalars, dp_mean_t), 2, 0);
+      sub("scal.lr", offsetof(AgentScalars, lr), 3, 1);
+      sub("scal.gamma", offsetof(AgentScalars, gamma), 1, 0);
+      sub("scal.tau", offsetof(AgentScalars, tau), 2, 0);                 // (tau, 1 - tau) as the Polyak update uses them
+      sub("scal.rng_agent", offsetof(AgentScalars, rng_agent), 1, 0);     // uint32 bits in an f32 view
+      sub("scal.rng_seed", offsetof(AgentScalars, rng_seed), 1, 2);
     }
     cur = align4(cur);
     P0 = cur;

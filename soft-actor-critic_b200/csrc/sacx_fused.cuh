@@ -70,7 +70,7 @@ __device__ __forceinline__ CriticRow critic_row_scalars(const Op& op, const Fuse
   r.tq1 = act_fwd(op.act_out, s1 + bt1);
   r.tq2 = act_fwd(op.act_out, s2 + bt2);
   // y = r + gamma (1 - d) (min(Q1t, Q2t) - alpha logpi')      (agent.py:208-210)
-  r.y = rew + (hp.gamma * (1.f - done)) * (fminf(r.tq1, r.tq2) - alpha * lp2);
+  r.y = rew + (__ldcg(&c.scal->gamma) * (1.f - done)) * (fminf(r.tq1, r.tq2) - alpha * lp2);
   const float z = sq + bq;
   r.q = act_fwd(op.act_out, z);
   r.diff = r.q - r.y;
@@ -231,13 +231,14 @@ __device__ __noinline__ void tile_dw_head(const Op& op, const FusedCtx& c, int t
 #pragma unroll
     for (int w = 0; w < 8; ++w) { g += red[w * 33 + lane]; gb += red[w * 33 + 32]; }
     const float ss = __ldcg(&c.scal->adam_step_size[op.opt]), bc = __ldcg(&c.scal->adam_bc2_sqrt[op.opt]);
+    const float tau = __ldcg(&c.scal->tau), omt = __ldcg(&c.scal->one_minus_tau);
     if (k < K) {
       if (op.flags & DW_STORE_GRAD) base[op.pg + k] = g;
       if (op.flags & DW_ADAM) {
         float p = __ldcg(base + op.p + k), mm = __ldcg(base + op.pm + k), vv = __ldcg(base + op.pv + k);
         adam_update(g, p, mm, vv, ss, bc);
         base[op.p + k] = p; base[op.pm + k] = mm; base[op.pv + k] = vv;
-        if (op.flags & DW_POLYAK) base[op.pt + k] = polyak_mix(hp.tau, hp.one_minus_tau, p, __ldcg(base + op.pt + k));
+        if (op.flags & DW_POLYAK) base[op.pt + k] = polyak_mix(tau, omt, p, __ldcg(base + op.pt + k));
       }
     }
     if (tile == 0 && lane == 0) {
@@ -246,7 +247,7 @@ __device__ __noinline__ void tile_dw_head(const Op& op, const FusedCtx& c, int t
         float p = __ldcg(base + op.pb), mm = __ldcg(base + op.pbm), vv = __ldcg(base + op.pbv);
         adam_update(gb, p, mm, vv, ss, bc);
         base[op.pb] = p; base[op.pbm] = mm; base[op.pbv] = vv;
-        if (op.flags & DW_POLYAK) base[op.pbt] = polyak_mix(hp.tau, hp.one_minus_tau, p, __ldcg(base + op.pbt));
+        if (op.flags & DW_POLYAK) base[op.pbt] = polyak_mix(tau, omt, p, __ldcg(base + op.pbt));
       }
     }
   }

@@ -113,7 +113,7 @@ __device__ __forceinline__ void stage_load(float* __restrict__ S, const float* _
 // ---- epilogues ---------------------------------------------------------------------------------------
 struct EpiPre {            // operands prefetched at tile start (latency config, one float4 per thread)
   float4 a, b, c, d;       // FWD: a=bias | DACT: a=aux | DW: a=p b=m c=v d=target
-  float ss, bc;
+  float ss, bc, tau, omt;
   bool valid;
 };
 
@@ -141,6 +141,7 @@ __device__ __forceinline__ void epi_prefetch(const Op& op, const EpiCtx& ctx, in
     if (op.flags & DW_POLYAK) pre.d = __ldcg(reinterpret_cast<const float4*>(base + op.pt + e));
     pre.ss = __ldcg(&ctx.scal->adam_step_size[op.opt]);
     pre.bc = __ldcg(&ctx.scal->adam_bc2_sqrt[op.opt]);
+    if (op.flags & DW_POLYAK) { pre.tau = __ldcg(&ctx.scal->tau); pre.omt = __ldcg(&ctx.scal->one_minus_tau); }
   }
 }
 
@@ -198,7 +199,7 @@ __device__ __forceinline__ void epilogue_row4(const Op& op, const EpiCtx& ctx, i
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           adam_update(v[j], p[j], mm[j], vv[j], pre.ss, pre.bc);
-          if (op.flags & DW_POLYAK) t[j] = polyak_mix(ctx.hp->tau, ctx.hp->one_minus_tau, p[j], t[j]);
+          if (op.flags & DW_POLYAK) t[j] = polyak_mix(pre.tau, pre.omt, p[j], t[j]);
         }
         *reinterpret_cast<float4*>(base + op.p + e) = make_float4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<float4*>(base + op.pm + e) = make_float4(mm[0], mm[1], mm[2], mm[3]);
@@ -220,7 +221,7 @@ __device__ __forceinline__ void epilogue_row4(const Op& op, const EpiCtx& ctx, i
             base[op.pv + e + j] = vv;
             if (op.flags & DW_POLYAK) {
               float* t = base + op.pt + e + j;
-              *t = polyak_mix(ctx.hp->tau, ctx.hp->one_minus_tau, p, __ldcg(t));
+              *t = polyak_mix(__ldcg(&ctx.scal->tau), __ldcg(&ctx.scal->one_minus_tau), p, __ldcg(t));
             }
           }
         }
@@ -229,7 +230,7 @@ __device__ __forceinline__ void epilogue_row4(const Op& op, const EpiCtx& ctx, i
   }
 }
 
-__device__ __forceinline__ void epilogue_bias(const Op& op, const EpiCtx& ctx, int m, float g, const float (&bpre)[6]) {
+__device__ __forceinline__ void epilogue_bias(const Op& op, const EpiCtx& ctx, int m, float g, const float (&bpre)[8]) {
   if (m >= op.M) return;
   float* base = ctx.base;
   if (op.flags & DW_ATOMIC) { atomicAdd(base + op.pbg + m, g); return; }
@@ -241,7 +242,7 @@ __device__ __forceinline__ void epilogue_bias(const Op& op, const EpiCtx& ctx, i
     base[op.pb + m] = p;
     base[op.pbm + m] = mm;
     base[op.pbv + m] = vv;
-    if (op.flags & DW_POLYAK) base[op.pbt + m] = polyak_mix(ctx.hp->tau, ctx.hp->one_minus_tau, p, bpre[3]);
+    if (op.flags & DW_POLYAK) base[op.pbt + m] = polyak_mix(bpre[6], bpre[7], p, bpre[3]);
   }
 }
 
@@ -413,7 +414,7 @@ __device__ __noinline__ void gemm_tile_impl(const Op& op, const EpiCtx& ctx, int
   for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
   EpiPre pre;
   pre.valid = false;
-  float bpre[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // bias-row operands (p, m, v, target, step size, bc2) of dW
+  float bpre[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // bias-row operands (p, m, v, target, step size, bc2, tau, 1 - tau) of dW
 
   // epilogue operands travel while the pipeline fills
   if (C::NV == 1) epi_prefetch<MODE>(op, ctx, m0 + tid / (BN / 4), n0 + (tid % (BN / 4)) * 4, pre);
@@ -424,6 +425,7 @@ __device__ __noinline__ void gemm_tile_impl(const Op& op, const EpiCtx& ctx, int
     if (op.flags & DW_POLYAK) bpre[3] = __ldcg(ctx.base + op.pbt + m0 + tid);
     bpre[4] = __ldcg(&ctx.scal->adam_step_size[op.opt]);
     bpre[5] = __ldcg(&ctx.scal->adam_bc2_sqrt[op.opt]);
+    if (op.flags & DW_POLYAK) { bpre[6] = __ldcg(&ctx.scal->tau); bpre[7] = __ldcg(&ctx.scal->one_minus_tau); }
   }
 
   // NS-deep cp.async ring as ONE rolled loop (one copy of the load and math code per variant keeps the

@@ -214,13 +214,14 @@ __device__ __forceinline__ void small_dw_tile(const Op& op, float* __restrict__ 
   if (kg == 0) {
     const float ss = (op.flags & DW_ADAM) ? __ldcg(&scal->adam_step_size[op.opt]) : 0.f;
     const float bc = (op.flags & DW_ADAM) ? __ldcg(&scal->adam_bc2_sqrt[op.opt]) : 1.f;
+    const float tau = __ldcg(&scal->tau), omt = __ldcg(&scal->one_minus_tau);
     auto apply = [&](float g, i64 p, i64 pm, i64 pv, i64 pt, i64 pg) {
       if (op.flags & DW_STORE_GRAD) base[pg] = g;
       if (op.flags & DW_ADAM) {
         float w = base[p], mm = base[pm], vv = base[pv];
         adam_update(g, w, mm, vv, ss, bc);
         base[p] = w; base[pm] = mm; base[pv] = vv;
-        if ((op.flags & DW_POLYAK) && pt >= 0) base[pt] = polyak_mix(hp.tau, hp.one_minus_tau, w, base[pt]);
+        if ((op.flags & DW_POLYAK) && pt >= 0) base[pt] = polyak_mix(tau, omt, w, base[pt]);
       }
     };
     for (int m = 0; m <= SMALLM_MAX; ++m) {
@@ -463,7 +464,7 @@ __device__ __forceinline__ const float* mlp_row(const float* __restrict__ base, 
 
 __global__ void act_kernel(const float* __restrict__ base, NetRef net, int maxw, const float* __restrict__ s,
                            const float* __restrict__ eps, int deterministic, float* __restrict__ a_out, int A,
-                           float lo, float hi, float scale, unsigned long long seed, unsigned long long counter,
+                           float lo, float hi, float scale, i64 scal_off, unsigned long long counter,
                            int agent0, i64 agent_stride) {
   // grid (rows per agent, agents): blockIdx.y walks a population (vectorised rollouts: one launch for every agent's action)
   extern __shared__ float sm[];
@@ -471,6 +472,7 @@ __global__ void act_kernel(const float* __restrict__ base, NetRef net, int maxw,
   float* b1 = sm + maxw;
   const int agent = agent0 + blockIdx.y;
   base += (i64)agent * agent_stride;
+  const AgentScalars* scal = reinterpret_cast<const AgentScalars*>(base + scal_off);      // the agent's own stream keys
   const int row = blockIdx.y * gridDim.x + blockIdx.x;
   for (int k = threadIdx.x; k < net.in_dim; k += blockDim.x) b0[k] = s[(i64)row * net.in_dim + k];
   __syncthreads();
@@ -483,7 +485,7 @@ __global__ void act_kernel(const float* __restrict__ base, NetRef net, int maxw,
     } else {
       const float ls = fminf(fmaxf(head[A + j], lo), hi);
       const float e = eps ? eps[(i64)row * A + j]
-                          : philox_normal(seed, counter, 3, (uint32_t)blockIdx.x, (uint32_t)j, (uint32_t)agent);
+                          : philox_normal(scal->rng_seed, counter, 3, (uint32_t)blockIdx.x, (uint32_t)j, scal->rng_agent);
       v = tanhf(mu + e * expf(ls)) * scale;                      // models.py:79-84
     }
     a_out[(i64)row * A + j] = v;

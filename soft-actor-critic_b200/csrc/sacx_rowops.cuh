@@ -101,8 +101,8 @@ __device__ __forceinline__ void op_gather(const Op& op, const RowCtx& c, int row
   } else {
     // throughput mode: position (global row) of a keyed bijection on [0, n) -> distinct indices
     const i64 upd = __ldcg(&c.scal->updates);
-    j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, hp.seed,
-                           (unsigned long long)upd, (uint32_t)c.agent);
+    j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, __ldcg(&c.scal->rng_seed),
+                           (unsigned long long)upd, __ldcg(&c.scal->rng_agent));
   }
   const i64 oldest = pushes > cap ? pushes - cap : 0;
   const i64 slot = (oldest + j) % cap;
@@ -152,8 +152,8 @@ __device__ __noinline__ void tile_pi_head(const Op& op, const RowCtx& c, int til
   float e_pre = 0.f;
   if (in && lane < A) {
     if (eps_ext) e_pre = eps_ext[(((i64)c.step * a.n_agents + c.agent) * hp.B + row) * A + lane];
-    else e_pre = philox_normal(hp.seed, (unsigned long long)__ldcg(&c.scal->updates), op.mode, (uint32_t)(hp.row0_global + row),
-                               (uint32_t)lane, (uint32_t)c.agent);
+    else e_pre = philox_normal(__ldcg(&c.scal->rng_seed), (unsigned long long)__ldcg(&c.scal->updates), op.mode, (uint32_t)(hp.row0_global + row),
+                               (uint32_t)lane, __ldcg(&c.scal->rng_agent));
   }
   if (staged) {
     if (c.fresh) {
@@ -226,6 +226,8 @@ __device__ __forceinline__ void tile_pi_tail(const Op& op, const RowCtx& c, int 
   const float* z = base + op.o[0] + (i64)row * op.i[3];
   const float* eps_ext = (op.mode == 1) ? a.eps1_ext : a.eps2_ext;
   const unsigned long long upd = eps_ext ? 0ull : (unsigned long long)__ldcg(&c.scal->updates);
+  const unsigned long long rng_seed = eps_ext ? 0ull : __ldcg(&c.scal->rng_seed);
+  const uint32_t rng_agent = eps_ext ? 0u : __ldcg(&c.scal->rng_agent);
   float lp = 0.f;
   bool bad = false;
   for (int j = 0; j < A; ++j) {
@@ -235,7 +237,7 @@ __device__ __forceinline__ void tile_pi_tail(const Op& op, const RowCtx& c, int 
     const float ls = fminf(fmaxf(ls_raw, hp.log_std_min), hp.log_std_max);
     const float sd = expf(ls);
     const float e = eps_ext ? eps_ext[(((i64)c.step * a.n_agents + c.agent) * hp.B + row) * A + j]
-                            : philox_normal(hp.seed, upd, op.mode, (uint32_t)(hp.row0_global + row), (uint32_t)j, (uint32_t)c.agent);
+                            : philox_normal(rng_seed, upd, op.mode, (uint32_t)(hp.row0_global + row), (uint32_t)j, rng_agent);
     base[op.o[5] + (i64)row * A + j] = e;
     const float zz = mu + e * sd;                      // Normal.rsample: loc + eps * scale
     const float tz = tanhf(zz);
@@ -272,7 +274,7 @@ __device__ __forceinline__ void tile_q_tail(const Op& op, const RowCtx& c, int t
   if (op.mode & 1) {
     const float t0 = act_fwd(op.act_out, __ldcg(base + op.o[0] + row)), t1 = act_fwd(op.act_out, __ldcg(base + op.o[1] + row));
     const float r = __ldcg(base + op.o[6] + row), d = __ldcg(base + op.o[7] + row), lp2 = __ldcg(base + op.o[8] + row);
-    y = r + (hp.gamma * (1.f - d)) * (fminf(t0, t1) - alpha * lp2);
+    y = r + (__ldcg(&c.scal->gamma) * (1.f - d)) * (fminf(t0, t1) - alpha * lp2);
     base[op.o[0] + row] = t0; base[op.o[1] + row] = t1; base[op.o[9] + row] = y;
   }
   if (op.mode & 2) {
@@ -389,7 +391,7 @@ __device__ __noinline__ void tile_q_row(const Op& op, const RowCtx& c, int tile)
     }
     const float r = r_, d = d_, lp2 = lp2_;
     // y = r + gamma * (1 - d) * (min(Q1t, Q2t) - alpha * logpi')      (agent.py:208-210)
-    y = r + (hp.gamma * (1.f - d)) * (fminf(tq[0], tq[1]) - alpha * lp2);
+    y = r + (__ldcg(&c.scal->gamma) * (1.f - d)) * (fminf(tq[0], tq[1]) - alpha * lp2);
     if (lane == 0) {
       base[op.o[9] + row] = y;
       base[op.o[10] + row] = tq[0];
@@ -644,7 +646,7 @@ __device__ __forceinline__ void op_prologue(const Op& op, const RowCtx& c) {
     // python-double bias corrections of torch's _single_tensor_adam
     const double bc1 = 1.0 - pow(0.9, (double)t);
     const double bc2 = 1.0 - pow(0.999, (double)t);
-    s->adam_step_size[o] = (float)(hp.lr[o] / bc1);
+    s->adam_step_size[o] = (float)((s->lr[o] > 0.0 ? s->lr[o] : hp.lr[o]) / bc1);      // per-agent learning rate when set
     s->adam_bc2_sqrt[o] = (float)sqrt(bc2);
   }
 }
@@ -743,17 +745,21 @@ __device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int
     s->metrics[8] = mean_t - hp.target_entropy;
     if (hp.auto_alpha) {
       // alpha_loss = -(log_alpha * (logpi + H).detach()).mean();  d/dlog_alpha = -mean(logpi + H)
-      const double g = -(double)mean_t;
-      const i64 t = s->step[OPT_ALPHA] + 1;
-      s->step[OPT_ALPHA] = t;
-      s->alpha_m = s->alpha_m + (1.0 - 0.9) * (g - s->alpha_m);
-      s->alpha_v = s->alpha_v * 0.999 + (1.0 - 0.999) * g * g;
-      const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
-      const double denom = sqrt(s->alpha_v) / sqrt(bc2) + 1e-8;
-      const double alr = s->alpha_lr > 0.0 ? s->alpha_lr : hp.alpha_lr;      // per-agent override (Optuna trials as a population)
-      s->log_alpha = s->log_alpha - (alr / bc1) * (s->alpha_m / denom);
-      s->alpha = exp(s->log_alpha);
-      s->alpha_f32 = (float)s->alpha;
+      // alpha_lr < 0: temperature frozen -- what the reference does after load_agent, where the optimiser keeps stepping the
+      // pre-load tensor (agent.py:549-554); SAC.load_agent(..., reference_temperature_semantics=True) selects it
+      if (!(s->alpha_lr < 0.0)) {
+        const double g = -(double)mean_t;
+        const i64 t = s->step[OPT_ALPHA] + 1;
+        s->step[OPT_ALPHA] = t;
+        s->alpha_m = s->alpha_m + (1.0 - 0.9) * (g - s->alpha_m);
+        s->alpha_v = s->alpha_v * 0.999 + (1.0 - 0.999) * g * g;
+        const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+        const double denom = sqrt(s->alpha_v) / sqrt(bc2) + 1e-8;
+        const double alr = s->alpha_lr > 0.0 ? s->alpha_lr : hp.alpha_lr;      // per-agent override (Optuna trials as a population)
+        s->log_alpha = s->log_alpha - (alr / bc1) * (s->alpha_m / denom);
+        s->alpha = exp(s->log_alpha);
+        s->alpha_f32 = (float)s->alpha;
+      }
       s->metrics[3] = -mean_lt;
     }
     s->metrics[4] = (float)s->alpha;
@@ -767,21 +773,21 @@ __device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane
 constexpr int FLAT_TILE = 256 * 8;
 // OP_POLYAK: o[0]=online o[1]=target o[2]=count
 __device__ __forceinline__ void op_polyak(const Op& op, const RowCtx& c, int tile) {
-  const Hyper& hp = c.args->hp;
   float* base = c.base;
   const i64 n = op.o[2];
+  const float tau = __ldcg(&c.scal->tau), omt = __ldcg(&c.scal->one_minus_tau);
   for (i64 e = (i64)tile * FLAT_TILE + threadIdx.x; e < n && e < (i64)(tile + 1) * FLAT_TILE; e += 256) {
     const float p = __ldcg(base + op.o[0] + e);
     float* t = base + op.o[1] + e;
-    *t = polyak_mix(hp.tau, hp.one_minus_tau, p, __ldcg(t));
+    *t = polyak_mix(tau, omt, p, __ldcg(t));
   }
 }
 // OP_ADAM_FLAT: o[0]=p o[1]=m o[2]=v o[3]=g o[4]=count o[5]=target or -1 (Polyak after the step)
 __device__ __forceinline__ void op_adam_flat(const Op& op, const RowCtx& c, int tile) {
-  const Hyper& hp = c.args->hp;
   float* base = c.base;
   const i64 n = op.o[4];
   const float ss = __ldcg(&c.scal->adam_step_size[op.opt]), bc = __ldcg(&c.scal->adam_bc2_sqrt[op.opt]);
+  const float tau = __ldcg(&c.scal->tau), omt = __ldcg(&c.scal->one_minus_tau);
   for (i64 e = (i64)tile * FLAT_TILE + threadIdx.x; e < n && e < (i64)(tile + 1) * FLAT_TILE; e += 256) {
     float p = __ldcg(base + op.o[0] + e), m = __ldcg(base + op.o[1] + e), v = __ldcg(base + op.o[2] + e);
     adam_update(__ldcg(base + op.o[3] + e), p, m, v, ss, bc);
@@ -790,7 +796,7 @@ __device__ __forceinline__ void op_adam_flat(const Op& op, const RowCtx& c, int 
     base[op.o[2] + e] = v;
     if (op.o[5] >= 0) {
       float* t = base + op.o[5] + e;
-      *t = polyak_mix(hp.tau, hp.one_minus_tau, p, __ldcg(t));
+      *t = polyak_mix(tau, omt, p, __ldcg(t));
     }
   }
 }

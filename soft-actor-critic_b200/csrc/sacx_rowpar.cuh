@@ -480,8 +480,8 @@ __device__ __noinline__ void rp_gather(const RpCtx& c) {
       const i64 n = pushes < cap ? pushes : cap;
       i64 j;
       if (a.idx_ext) j = a.idx_ext[(i64)c.step * hp.B + row];
-      else j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, hp.seed,
-                                  (unsigned long long)__ldcg(&c.scal->updates), 0u);
+      else j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, __ldcg(&c.scal->rng_seed),
+                                  (unsigned long long)__ldcg(&c.scal->updates), __ldcg(&c.scal->rng_agent));
       const i64 oldest = pushes > cap ? pushes - cap : 0;
       myslot = (oldest + j) % cap;
       if (w0) reinterpret_cast<i64*>(c.base + P.b_idx)[row] = j;
@@ -514,9 +514,9 @@ __device__ __noinline__ void rp_gather(const RpCtx& c) {
     float e1 = 0.f, e2 = 0.f;
     if (row < B && j < A) {
       if (a.eps1_ext) e1 = a.eps1_ext[((i64)c.step * hp.B + row) * A + j];
-      else e1 = philox_normal(hp.seed, (unsigned long long)__ldcg(&c.scal->updates), 1, (uint32_t)(hp.row0_global + row), (uint32_t)j, 0u);
+      else e1 = philox_normal(__ldcg(&c.scal->rng_seed), (unsigned long long)__ldcg(&c.scal->updates), 1, (uint32_t)(hp.row0_global + row), (uint32_t)j, __ldcg(&c.scal->rng_agent));
       if (a.eps2_ext) e2 = a.eps2_ext[((i64)c.step * hp.B + row) * A + j];
-      else e2 = philox_normal(hp.seed, (unsigned long long)__ldcg(&c.scal->updates), 2, (uint32_t)(hp.row0_global + row), (uint32_t)j, 0u);
+      else e2 = philox_normal(__ldcg(&c.scal->rng_seed), (unsigned long long)__ldcg(&c.scal->updates), 2, (uint32_t)(hp.row0_global + row), (uint32_t)j, __ldcg(&c.scal->rng_agent));
       if (w0) { c.base[P.b_eps1 + (i64)row * A + j] = e1; c.base[P.b_eps2 + (i64)row * A + j] = e2; }
     }
     R.eps1[mm][j] = e1; R.eps2[mm][j] = e2;
@@ -673,7 +673,7 @@ __device__ __noinline__ void rp_target_critic(const RpCtx& c) {
     const float st[2] = {rp_add_parts(pt[0]), rp_add_parts(pt[1])};
     const float sq[2] = {rp_add_parts(pq[0]), rp_add_parts(pq[1])};
     const float tq[2] = {act_fwd(P.act_oq, st[0] + bt[0]), act_fwd(P.act_oq, st[1] + bt[1])};
-    const float y = R.r[mm] + (hp.gamma * (1.f - R.d[mm])) * (fminf(tq[0], tq[1]) - alpha * R.lp2[mm]);
+    const float y = R.r[mm] + (__ldcg(&c.scal->gamma) * (1.f - R.d[mm])) * (fminf(tq[0], tq[1]) - alpha * R.lp2[mm]);
     if (w0 && ok) { c.base[P.b_y + row] = y; c.base[P.b_tq[0] + row] = tq[0]; c.base[P.b_tq[1] + row] = tq[1]; }
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {

@@ -159,13 +159,24 @@ __device__ __forceinline__ TcTile tc_decode(const TcParams& P, int tile) {
   return t;
 }
 
+// timing experiments / role trace (SACX_TC_DBG) exist only in builds with -DSACX_DEBUG_HOOKS: the production kernel carries none
+#ifdef SACX_DEBUG_HOOKS
+#define TC_DBG P.dbg
+#define TC_TS(stmt) stmt
+#else
+#define TC_DBG 0
+#define TC_TS(stmt)
+#endif
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMaps maps) {
   extern __shared__ __align__(1024) uint8_t tc_raw[];
   __shared__ __align__(8) uint64_t full[TC_STAGES], ready[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], aux_bar;
   __shared__ uint32_t tmem_base_s;
+#ifdef SACX_DEBUG_HOOKS
   __shared__ long long ts[4][4][3];            // SACX_TC_DBG & 128: per-role timestamps of CTA 0's first 4 tiles
   const long long t_start = clock64();
+#endif
   uint8_t* smem = tc_raw;
   if ((tc_smem(tc_raw) & 1023u) != 0u) __trap();        // swizzled tiles need 1024-byte alignment (declared on tc_raw)
   __shared__ __align__(16) float bias_sm[TC_NMAX];     // FWD: bias row of the epilogue's current tile
@@ -197,12 +208,12 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         const TcOp& o = P.ops[t.op];
         const CUtensorMap* ma = &maps.a[t.op];
         const CUtensorMap* mb = &maps.b[t.op];
-        const int tn_ = (tile - blockIdx.x) / gridDim.x;
-        if (tn_ < 4) ts[0][tn_][0] = clock64() - t_start;
+        TC_TS(const int tn_ = (tile - blockIdx.x) / gridDim.x;)
+        TC_TS(if (tn_ < 4) ts[0][tn_][0] = clock64() - t_start;)
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           tc_mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
-          if (tn_ < 4 && kb == 0) ts[0][tn_][1] = clock64() - t_start;
+          TC_TS(if (tn_ < 4 && kb == 0) ts[0][tn_][1] = clock64() - t_start;)
           tc_mbar_expect_tx(&full[s], (uint32_t)(o.a_bytes + o.b_bytes));
           uint8_t* st = smem + s * TC_STAGE_BYTES;
           const int k = t.k0 + kb * TC_BK;
@@ -212,7 +223,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           if (!o.b_mn) tc_tma_load(st + TC_A_BYTES, mb, &full[s], k, 0, t.agent);
           else
             for (int j = 0; j < o.b_rows; ++j) tc_tma_load(st + TC_A_BYTES + j * TC_SLAB, mb, &full[s], 32 * j, k, t.agent);
-          if (tn_ < 4) ts[0][tn_][2] = clock64() - t_start;
+          TC_TS(if (tn_ < 4) ts[0][tn_][2] = clock64() - t_start;)
         }
       }
     }
@@ -226,13 +237,13 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         const uint32_t buf = tc & 1;
         tc_mbar_wait(&acc_empty[buf], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (tc < 4) ts[2][tc][0] = clock64() - t_start;
+        TC_TS(if (tc < 4) ts[2][tc][0] = clock64() - t_start;)
         const uint32_t tacc = tmem_base + buf * TC_NMAX;
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           tc_mbar_wait(&ready[s], (it / TC_STAGES) & 1);
           tc_fence_after();
-          if (tc < 4 && kb == 0) ts[2][tc][1] = clock64() - t_start;
+          TC_TS(if (tc < 4 && kb == 0) ts[2][tc][1] = clock64() - t_start;)
           const uint32_t hi = tc_smem(smem + s * TC_STAGE_BYTES), lo = hi + TC_HALF;
 #pragma unroll
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
@@ -242,7 +253,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
             const uint64_t bh = o.b_mn ? tc_desc_mn(hi + boff) : tc_desc_k(hi + boff);
             const uint64_t bl = o.b_mn ? tc_desc_mn(lo + boff) : tc_desc_k(lo + boff);
             tc_mma(tacc, al, bh, o.idesc, (kb | k8) != 0);
-            if (!(P.dbg & 2)) {
+            if (!(TC_DBG & 2)) {
               tc_mma(tacc, ah, bl, o.idesc, 1u);
               tc_mma(tacc, ah, bh, o.idesc, 1u);
             }
@@ -250,7 +261,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           tc_commit(&empty[s]);
         }
         tc_commit(&acc_full[buf]);
-        if (tc < 4) ts[2][tc][2] = clock64() - t_start;
+        TC_TS(if (tc < 4) ts[2][tc][2] = clock64() - t_start;)
       }
     }
   } else if (warp >= 6) {
@@ -266,16 +277,16 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) bs[j][e] = 0.f;
-      const int n4 = (P.dbg & 512) ? (TC_A_BYTES >> 4) : ((TC_A_BYTES + o.b_bytes) >> 4);      // 512: timing experiment, B operand not split
+      const int n4 = (TC_DBG & 512) ? (TC_A_BYTES >> 4) : ((TC_A_BYTES + o.b_bytes) >> 4);      // 512: timing experiment, B operand not split
       for (int kb = 0; kb < t.nkb; ++kb, ++it) {
         const int s = it % TC_STAGES;
         tc_mbar_wait(&full[s], (it / TC_STAGES) & 1);
-        { const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 4 && kb == 0) ts[1][tn_][0] = clock64() - t_start; }
+        TC_TS({ const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 4 && kb == 0) ts[1][tn_][0] = clock64() - t_start; })
         float4* hi = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_HALF);
         // six float4 per thread cover a full-width stage (1536 float4): all loads first, then the arithmetic and stores
         constexpr int U = 6;
-        for (int base = st; base < ((P.dbg & 1) ? 0 : n4); base += TC_SPLIT_THREADS * U) {
+        for (int base = st; base < ((TC_DBG & 1) ? 0 : n4); base += TC_SPLIT_THREADS * U) {
           float4 x[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -287,7 +298,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
             const int i = base + u * TC_SPLIT_THREADS;
             if (i < n4) {
               float4 h, l;
-              if (P.dbg & 256) {     // experiment: leave the raw value as "hi" (the tensor core drops the low 13 bits itself)
+              if (TC_DBG & 256) {     // experiment: leave the raw value as "hi" (the tensor core drops the low 13 bits itself)
                 l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xffffe000u);
                 l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xffffe000u);
                 l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xffffe000u);
@@ -311,7 +322,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
         tc_fence_async();
         __syncwarp();
         if (lane == 0) tc_mbar_arrive(&ready[s]);
-        { const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 4) ts[1][tn_][kb == 0 ? 1 : 2] = clock64() - t_start; }
+        TC_TS({ const int tn_ = (tile - blockIdx.x) / gridDim.x; if (st == 0 && tn_ < 4) ts[1][tn_][kb == 0 ? 1 : 2] = clock64() - t_start; })
       }
       if (want_bias) {
         // thread (k-row r = (st % 128) / 8, 16-byte chunk q = st % 8) holds out-features slab*32 + ((q>>1) ^ (r&3))*8 + (q&1)*4 + e
@@ -349,7 +360,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       const uint32_t buf = tc & 1;
       tc_mbar_wait(&acc_full[buf], (tc >> 1) & 1);
       tc_fence_after();
-      if (tid == 0 && tc < 4) ts[3][tc][0] = clock64() - t_start;
+      TC_TS(if (tid == 0 && tc < 4) ts[3][tc][0] = clock64() - t_start;)
       const int row = tid;                                  // row of the tile == TMEM lane
       const int crow = (o.kind == EPI_DW) ? (t.split * o.m_tiles + t.mt) * TC_BM : t.m0;
       const int ncols = (o.N + 31) & ~31;
@@ -376,7 +387,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
           ++auxn;
         }
         uint32_t v[32];
-        if (!(P.dbg & 32)) tc_ld32(tmem_base + buf * TC_NMAX + c0 + ((uint32_t)(warp * 32) << 16), v);
+        if (!(TC_DBG & 32)) tc_ld32(tmem_base + buf * TC_NMAX + c0 + ((uint32_t)(warp * 32) << 16), v);
         else { for (int z = 0; z < 32; ++z) v[z] = 0u; }
         float4* srow = reinterpret_cast<float4*>(sb + row * 128);
         const int sx = row & 7;
@@ -424,9 +435,9 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
             srow[qd ^ sx] = make_float4(__uint_as_float(v[4 * qd]), __uint_as_float(v[4 * qd + 1]), __uint_as_float(v[4 * qd + 2]),
                                         __uint_as_float(v[4 * qd + 3]));
         }
-        if (!(P.dbg & 8)) tc_fence_async();
-        if (!(P.dbg & 64)) tc_bar(1, TC_EPI_WARPS * 32);
-        if (tid == 0 && !(P.dbg & 4)) {
+        if (!(TC_DBG & 8)) tc_fence_async();
+        if (!(TC_DBG & 64)) tc_bar(1, TC_EPI_WARPS * 32);
+        if (tid == 0 && !(TC_DBG & 4)) {
           tc_tma_store(&maps.c[t.op], sb, c0, crow, t.agent);
           tc_bulk_commit();
         }
@@ -436,13 +447,14 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);
-      if (tid == 0 && tc < 4) ts[3][tc][1] = clock64() - t_start;
+      TC_TS(if (tid == 0 && tc < 4) ts[3][tc][1] = clock64() - t_start;)
     }
     if (tid == 0) tc_bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
-  if ((P.dbg & 128) && blockIdx.x == 0 && tid == 0) {
+#ifdef SACX_DEBUG_HOOKS
+  if ((TC_DBG & 128) && blockIdx.x == 0 && tid == 0) {
     const int nt = min(4, (P.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
     printf("tc kernel: %d ops, %d tiles, K0 %d; end %lld cycles\n", P.n_ops, P.total_tiles, P.ops[0].K, clock64() - t_start);
     for (int i = 0; i < nt; ++i)
@@ -450,6 +462,7 @@ sacx_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMap
              "first-ready %lld committed %lld | epi acc-full %lld done %lld\n", i, ts[0][i][0], ts[0][i][1], ts[0][i][2], ts[1][i][0], ts[1][i][1],
              ts[1][i][2], ts[2][i][0], ts[2][i][1], ts[2][i][2], ts[3][i][0], ts[3][i][1]);
   }
+#endif
   if (warp == 5) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -482,6 +495,7 @@ __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant
   const i64 total = (i64)op.M * n4 + op.M;           // weight float4 groups, then one bias element per output row
   const float ss = (op.flags & DW_ADAM) ? __ldcg(&scal->adam_step_size[op.opt]) : 0.f;
   const float bc = (op.flags & DW_ADAM) ? __ldcg(&scal->adam_bc2_sqrt[op.opt]) : 1.f;
+  const float tau = __ldcg(&scal->tau), omt = __ldcg(&scal->one_minus_tau);
   for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
     if (e < (i64)op.M * n4) {
       const int m = (int)(e / n4), n = (int)(e % n4) * 4;
@@ -509,7 +523,7 @@ __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant
             float pp = base[op.p + w + j], mm = base[op.pm + w + j], vv = base[op.pv + w + j];
             adam_update(gg[j], pp, mm, vv, ss, bc);
             base[op.p + w + j] = pp; base[op.pm + w + j] = mm; base[op.pv + w + j] = vv;
-            if (op.flags & DW_POLYAK) base[op.pt + w + j] = polyak_mix(R.hp.tau, R.hp.one_minus_tau, pp, base[op.pt + w + j]);
+            if (op.flags & DW_POLYAK) base[op.pt + w + j] = polyak_mix(tau, omt, pp, base[op.pt + w + j]);
           }
         }
         continue;
@@ -527,7 +541,7 @@ __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           adam_update(gg[j], pp[j], mm[j], vv[j], ss, bc);
-          if (op.flags & DW_POLYAK) tt[j] = polyak_mix(R.hp.tau, R.hp.one_minus_tau, pp[j], tt[j]);
+          if (op.flags & DW_POLYAK) tt[j] = polyak_mix(tau, omt, pp[j], tt[j]);
         }
         *reinterpret_cast<float4*>(base + op.p + w) = make_float4(pp[0], pp[1], pp[2], pp[3]);
         *reinterpret_cast<float4*>(base + op.pm + w) = make_float4(mm[0], mm[1], mm[2], mm[3]);
@@ -545,7 +559,7 @@ __global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const __grid_constant
         float p = base[op.pb + m], mm = base[op.pbm + m], vv = base[op.pbv + m];
         adam_update(g, p, mm, vv, ss, bc);
         base[op.pb + m] = p; base[op.pbm + m] = mm; base[op.pbv + m] = vv;
-        if (op.flags & DW_POLYAK) base[op.pbt + m] = polyak_mix(R.hp.tau, R.hp.one_minus_tau, p, base[op.pbt + m]);
+        if (op.flags & DW_POLYAK) base[op.pbt + m] = polyak_mix(tau, omt, p, base[op.pbt + m]);
       }
     }
   }

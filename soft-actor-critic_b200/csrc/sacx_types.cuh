@@ -77,6 +77,12 @@ struct AgentScalars {
   int nonfinite;
   float dp_mean_t, dp_mean_lt;                       // data parallel: this rank's share of mean(logpi + H), mean(log_alpha (logpi + H))
   int pad2[1];
+  // per-agent hyper-parameters (a population of Optuna trials: hparam_search/scripts/run_search.py:24-39 is generic over any
+  // section/param of the YAML). Initialised from the config by sacx_agent_reset_state / create; overwritten per agent through the layout.
+  double lr[3];                                      // actor / critic / critic learning rates; 0: Hyper.lr
+  float gamma, tau, one_minus_tau;                   // sac.gamma, sac.tau, (float)(1.0 - tau)
+  unsigned rng_agent;                                // second key word of the device RNG streams: the GLOBAL agent id
+  unsigned long long rng_seed;                       // first key of the device index / normal / rollout-noise streams (train.seed or the agent's own seed)
 };
 
 struct RingMeta {          // one per agent, at the head of the agent's ring block

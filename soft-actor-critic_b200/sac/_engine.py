@@ -39,6 +39,7 @@ class SacxConfig(C.Structure):
         ("alpha", C.c_double), ("actor_lr", C.c_double), ("critic_lr", C.c_double), ("alpha_lr", C.c_double),
         ("seed", C.c_uint64),
         ("dp_world", C.c_int32), ("dp_rank", C.c_int32),
+        ("agent_id_base", C.c_int32), ("reserved_i", C.c_int32),
     ]
 
 
@@ -182,7 +183,7 @@ def ptr(t) -> Optional[int]:
 
 
 def make_config(obs_dim: int, act_dim: int, config: dict, n_agents: int = 1, ctas_per_agent: int = 0,
-                dp_world: int = 1, dp_rank: int = 0, batch_size: Optional[int] = None) -> SacxConfig:
+                dp_world: int = 1, dp_rank: int = 0, batch_size: Optional[int] = None, agent_id_base: int = 0) -> SacxConfig:
     """YAML dict (reference: configs/example_config_env.yaml, sac/agent.py:22-115) -> sacx_config."""
     sac, qn, pn, tr = config["sac"], config["q_net"], config["policy_net"], config["train"]
     c = SacxConfig()
@@ -212,4 +213,5 @@ def make_config(obs_dim: int, act_dim: int, config: dict, n_agents: int = 1, cta
     c.actor_lr, c.critic_lr, c.alpha_lr = float(sac["actor_lr"]), float(sac["critic_lr"]), float(sac["alpha_lr"])
     c.seed = int(tr.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
     c.dp_world, c.dp_rank = int(dp_world), int(dp_rank)
+    c.agent_id_base = int(agent_id_base)
     return c

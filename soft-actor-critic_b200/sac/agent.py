@@ -64,8 +64,22 @@ class _EngineAdam(optim.Adam):
         return super().state_dict()
 
     def load_state_dict(self, state_dict) -> None:
+        """torch.optim.Adam.load_state_dict semantics on engine-owned moments: the moments and the step counter go into the
+        arena, the checkpoint's param_groups (lr, betas, eps, ...) replace this optimiser's -- a checkpoint saved with another
+        learning rate resumes with THAT rate, as it does in the reference -- and the rate is pushed into the engine."""
         st = state_dict.get("state", {})
-        step = 0
+        groups = state_dict.get("param_groups", [])
+        if st and len(st) != len(self._moments):
+            raise ValueError(f"loaded state dict has {len(st)} parameter states, this optimizer has {len(self._moments)}")
+        if groups:
+            if len(groups) != 1 or len(groups[0].get("params", [])) != len(self._moments):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+            g = groups[0]
+            if tuple(g.get("betas", (0.9, 0.999))) != (0.9, 0.999) or g.get("eps", 1e-8) != 1e-8 or g.get("weight_decay", 0) != 0 \
+                    or g.get("amsgrad", False) or g.get("maximize", False):
+                raise ValueError("the fused update implements torch.optim.Adam's defaults only (betas (0.9, 0.999), eps 1e-8, "
+                                 "no weight decay / amsgrad / maximize): this checkpoint's optimiser uses something else")
+        step = None
         with torch.no_grad():
             for i, (m, v) in enumerate(self._moments):
                 ent = st.get(i, st.get(str(i)))
@@ -73,10 +87,26 @@ class _EngineAdam(optim.Adam):
                     m.zero_()
                     v.zero_()
                     continue
-                m.copy_(torch.as_tensor(ent["exp_avg"]).to(m.device).reshape(m.shape))
-                v.copy_(torch.as_tensor(ent["exp_avg_sq"]).to(v.device).reshape(v.shape))
-                step = int(float(ent["step"]))
-            self._engine.view("scal.step")[self._opt_index] = step
+                ea, es = torch.as_tensor(ent["exp_avg"]), torch.as_tensor(ent["exp_avg_sq"])
+                if ea.numel() != m.numel() or es.numel() != v.numel():
+                    raise ValueError(f"optimizer state {i}: shape {tuple(ea.shape)} does not match the parameter's {tuple(m.shape)}")
+                m.copy_(ea.to(m.device).reshape(m.shape))
+                v.copy_(es.to(v.device).reshape(v.shape))
+                s_i = int(float(ent["step"]))
+                if step is not None and s_i != step:
+                    raise ValueError("per-parameter Adam step counters differ: the fused update keeps one counter per optimiser")
+                step = s_i
+            self._engine.view("scal.step")[self._opt_index] = step or 0
+            if groups:
+                lr = float(groups[0]["lr"])
+                for k, val in groups[0].items():
+                    if k != "params":
+                        self.param_groups[0][k] = val
+                if self._opt_index < 3:
+                    self._engine.view("scal.lr")[self._opt_index] = lr
+                else:
+                    cur = float(self._engine.view("scal.alpha_lr").item())
+                    self._engine.view("scal.alpha_lr").fill_(-abs(lr) if cur < 0 else lr)
 
     def step(self, closure=None):
         raise RuntimeError("parameters are stepped by the fused CUDA update (SAC.training_step), not by torch")
@@ -472,7 +502,15 @@ class SAC:
         np.random.set_state(snap["numpy_rng"])
         eng.sync()
 
-    def load_agent(self, filepath: str) -> None:
+    def load_agent(self, filepath: str, reference_temperature_semantics: bool = False) -> None:
+        """reference: agent.py:538-554. Accepts the reference's own files, including the (1,) float32 ``log_alpha`` of the
+        shipped checkpoints (today's reference writes a 0-dim float64).
+
+        One deliberate difference, off by default: in the reference ``load_agent`` REBINDS ``self.log_alpha`` to the loaded
+        tensor while ``alpha_optimizer`` keeps the tensor made in ``__init__`` as its parameter, so after a load the
+        temperature never moves again (alpha stays exp(loaded log_alpha)). Here the loaded value and optimiser state go into
+        the live tensor and tuning continues. ``reference_temperature_semantics=True`` reproduces the reference (temperature
+        frozen after the load) -- used by the parity tests that continue a reference run from a checkpoint."""
         ck = torch.load(filepath, map_location=self.device)
         self.engine.sync()
         self.policy_net.load_state_dict(ck["policy_net_state_dict"])
@@ -484,8 +522,16 @@ class SAC:
         self.q1_optimizer.load_state_dict(ck["q1_optimizer_state_dict"])
         self.q2_optimizer.load_state_dict(ck["q2_optimizer_state_dict"])
         if self.auto_entropy:
+            la = torch.as_tensor(ck["log_alpha"]).detach()
             with torch.no_grad():
-                self.log_alpha.copy_(torch.as_tensor(ck["log_alpha"]).detach().to(self.device).double().reshape(-1)[0])
+                self.log_alpha.copy_(la.to(self.device).double().reshape(-1)[0])
             self.alpha_optimizer.load_state_dict(ck["alpha_optimizer_state_dict"])
+            lr = abs(float(self.engine.view("scal.alpha_lr").item())) or float(self.config["sac"]["alpha_lr"])
+            self.engine.view("scal.alpha_lr").fill_(-lr if reference_temperature_semantics else lr)
         torch.cuda.synchronize(self.device)
         self.engine.refresh_alpha()
+        if self.auto_entropy and la.dtype == torch.float32:
+            # the reference's alpha = exp(log_alpha) is evaluated in the loaded tensor's dtype
+            a32 = float(torch.exp(la.reshape(-1)[0].float()))
+            self.engine.view("scal.alpha").fill_(a32)
+            self.engine.view("scal.alpha_f32").fill_(a32)

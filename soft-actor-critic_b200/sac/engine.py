@@ -18,7 +18,8 @@ from . import _engine as E
 
 class UpdateEngine:
     def __init__(self, obs_dim: int, act_dim: int, config: dict, device="cuda", n_agents: int = 1,
-                 ctas_per_agent: int = 0, dp_world: int = 1, dp_rank: int = 0, batch_size: Optional[int] = None):
+                 ctas_per_agent: int = 0, dp_world: int = 1, dp_rank: int = 0, batch_size: Optional[int] = None,
+                 agent_id_base: int = 0):
         E.require_cuda()
         self.lib = E.load()
         self.device = torch.device(device)
@@ -27,7 +28,7 @@ class UpdateEngine:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.obs_dim, self.act_dim, self.n_agents = int(obs_dim), int(act_dim), int(n_agents)
-        self.cfg = E.make_config(obs_dim, act_dim, config, n_agents, ctas_per_agent, dp_world, dp_rank, batch_size)
+        self.cfg = E.make_config(obs_dim, act_dim, config, n_agents, ctas_per_agent, dp_world, dp_rank, batch_size, agent_id_base)
         self.batch_size = int(self.cfg.batch_size)
         floats = C.c_int64()
         E.check(self.lib.sacx_agent_arena_floats(C.byref(self.cfg), C.byref(floats)))

@@ -59,10 +59,15 @@ class SACPopulation:
         self.config = config
         self.obs_dim, self.act_dim = obs_dim, act_dim
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.engine = UpdateEngine(obs_dim, act_dim, config, device=dev, n_agents=self.n_local)
+        # device RNG streams (replay indices, policy noise, rollout noise) are keyed by (seed, GLOBAL agent id): two ranks'
+        # local agent 0 draw different streams; an agent's own seed (seeds[g]) replaces train.seed as its first key
+        self.engine = UpdateEngine(obs_dim, act_dim, config, device=dev, n_agents=self.n_local, agent_id_base=self.agent_ids[0])
         self.ring = ReplayBuffer(config["buffer"]["capacity"], obs_dim, act_dim, device=dev, n_agents=self.n_local)
         self._init_weights(reference_init)
         self.engine.reset_state()
+        if seeds is not None:
+            for a, seed in enumerate(self.seeds):
+                self.engine.view("scal.rng_seed", a).fill_(int(seed))
         self.engine.attach_ring(self.ring)
 
     def _init_weights(self, reference_init: bool) -> None:
@@ -111,10 +116,17 @@ class SACPopulation:
         self.engine.update(None, None, None, n_steps)
 
     # ------------------------------------------------------------------ trials
-    def set_trial(self, agent: int, alpha: Optional[float] = None, alpha_lr: Optional[float] = None) -> None:
-        """Per-agent values of the two hyper-parameters the reference's Optuna study searches
-        (hparam_search/configs/search_space.yaml: ``sac.alpha``, ``sac.alpha_lr``): the initial temperature and the
-        temperature optimiser's learning rate of local agent `agent`. Call before the first update."""
+    # hyper-parameters the engine keeps PER AGENT (scalar block of the arena): every scalar of the YAML's `sac` section
+    TRIAL_KEYS = ("alpha", "alpha_lr", "actor_lr", "critic_lr", "tau", "gamma")
+
+    def set_trial(self, agent: int, alpha: Optional[float] = None, alpha_lr: Optional[float] = None,
+                  actor_lr: Optional[float] = None, critic_lr: Optional[float] = None, tau: Optional[float] = None,
+                  gamma: Optional[float] = None) -> None:
+        """Per-agent values of the `sac.*` scalars for local agent `agent` (one Optuna trial per agent; the reference's driver
+        is generic over any section/param: hparam_search/scripts/run_search.py:24-39; its shipped search space uses
+        ``sac.alpha`` and ``sac.alpha_lr``: hparam_search/configs/search_space.yaml). Same roundings as the reference applies
+        to the config values: learning rates stay python doubles (torch.optim.Adam), gamma / tau / 1 - tau become float32
+        scalars (agent.py:208,288-291), log_alpha = log(alpha) in float64 (agent.py:45-50). Call before the first update."""
         import math
         eng = self.engine
         eng.sync()
@@ -125,16 +137,40 @@ class SACPopulation:
             eng.view("scal.log_alpha", agent).fill_(la)
             eng.view("scal.alpha", agent).fill_(math.exp(la) if self.config["sac"]["auto_entropy_tuning"] else float(np.float32(alpha)))
         if alpha_lr is not None:
+            if not alpha_lr > 0:
+                raise ValueError("alpha_lr must be positive")
             eng.view("scal.alpha_lr", agent).fill_(float(alpha_lr))
+        lr = eng.view("scal.lr", agent)
+        if actor_lr is not None:
+            if not actor_lr > 0:
+                raise ValueError("actor_lr must be positive")
+            lr[0] = float(actor_lr)
+        if critic_lr is not None:
+            if not critic_lr > 0:
+                raise ValueError("critic_lr must be positive")
+            lr[1] = float(critic_lr)
+            lr[2] = float(critic_lr)
+        if tau is not None:
+            if not 0.0 <= tau <= 1.0:
+                raise ValueError("tau must be in [0, 1]")
+            t = eng.view("scal.tau", agent).reshape(-1)
+            t[0] = float(np.float32(tau))
+            t[1] = float(np.float32(1.0 - tau))      # the python double 1.0 - tau rounded once, as in agent.py:290
+        if gamma is not None:
+            eng.view("scal.gamma", agent).fill_(float(np.float32(gamma)))
         eng.refresh_alpha()
 
     def set_trials(self, trials: Sequence[Dict[str, float]]) -> None:
-        """trials[g] = {"alpha": ..., "alpha_lr": ...} for GLOBAL agent g (one Optuna trial per agent); this rank applies its
-        own block. The sequential `subprocess.run` loop of hparam_search/scripts/run_search.py:58-65 becomes one population."""
+        """trials[g] = {"alpha": ..., "alpha_lr": ..., "actor_lr": ..., "critic_lr": ..., "tau": ..., "gamma": ...} (any subset)
+        for GLOBAL agent g (one Optuna trial per agent); this rank applies its own block. The sequential `subprocess.run` loop
+        of hparam_search/scripts/run_search.py:58-65 becomes one population."""
         if len(trials) != self.n_agents_global:
             raise ValueError("one trial per agent expected")
         for a, g in enumerate(self.agent_ids):
-            self.set_trial(a, trials[g].get("alpha"), trials[g].get("alpha_lr"))
+            unknown = set(trials[g]) - set(self.TRIAL_KEYS)
+            if unknown:
+                raise KeyError(f"not a per-agent hyper-parameter: {sorted(unknown)} (per-agent: {self.TRIAL_KEYS})")
+            self.set_trial(a, **{k: trials[g].get(k) for k in self.TRIAL_KEYS})
 
     def act_all(self, states, deterministic: bool = False, eps=None) -> torch.Tensor:
         """One action per local agent from its own observation (vectorised envs): states [n_local, obs] (numpy or tensor) ->

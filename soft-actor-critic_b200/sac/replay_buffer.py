@@ -147,6 +147,7 @@ class ReplayBuffer:
         n = r.shape[0]
         if self._h is None:
             self._allocate(s.reshape(n, -1).shape[1], a.reshape(n, -1).shape[1])
+        self._check_rows(n, s.size, a.size, s2.size, d.shape[0])
         E.check(self._lib.sacx_ring_push_n_host(self._h, agent, n, s.ctypes.data, a.ctypes.data, r.ctypes.data,
                                                 s2.ctypes.data, d.ctypes.data))
 
@@ -158,8 +159,15 @@ class ReplayBuffer:
         n = r.shape[0]
         if self._h is None:
             self._allocate(s.reshape(n, -1).shape[1], a.reshape(n, -1).shape[1])
+        self._check_rows(n, s.numel(), a.numel(), s2.numel(), d.shape[0])
         E.check(self._lib.sacx_ring_push_n_dev(self._h, agent, n, s.data_ptr(), a.data_ptr(), r.data_ptr(),
                                                s2.data_ptr(), d.data_ptr()))
+
+    def _check_rows(self, n: int, s_elems: int, a_elems: int, s2_elems: int, d_elems: int) -> None:
+        """the native push reads n rows of (obs_dim | act_dim | 1 | obs_dim | 1) floats through raw pointers: refuse anything else"""
+        if s_elems != n * self.obs_dim or s2_elems != n * self.obs_dim or a_elems != n * self.act_dim or d_elems != n:
+            raise ValueError(f"push of {n} transitions: expected states/next_states [{n}, {self.obs_dim}], actions [{n}, {self.act_dim}], "
+                             f"rewards/dones [{n}]")
 
     def __len__(self) -> int:
         return 0 if self._h is None else int(self._lib.sacx_ring_len(self._h, 0))
@@ -222,8 +230,12 @@ class ReplayBuffer:
             indices = self.draw_indices(batch_size, agent)
         if not torch.is_tensor(indices):
             indices = torch.as_tensor(np.asarray(indices, dtype=np.int64))
-        idx = indices.to(device=self.device, dtype=torch.int64).contiguous()
+        idx = indices.to(device=self.device, dtype=torch.int64).contiguous().reshape(-1)
         B = idx.shape[0]
+        if B != batch_size:
+            raise ValueError(f"{B} indices given for a batch of {batch_size}")
+        if B and (int(idx.min()) < 0 or int(idx.max()) >= self.size(agent)):      # logical positions of the deque: [0, len)
+            raise ValueError("logical index out of range")
         kw = dict(dtype=torch.float32, device=self.device)
         s, a = torch.empty(B, self.obs_dim, **kw), torch.empty(B, self.act_dim, **kw)
         r, s2, d = torch.empty(B, **kw), torch.empty(B, self.obs_dim, **kw), torch.empty(B, **kw)

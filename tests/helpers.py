@@ -121,7 +121,40 @@ class Golden:
         return [k for k in self.z.files if k.startswith(p)]
 
 
-def numpy_oracle_from_golden(g: Golden, dtype=np.float32):
+class VirtualGolden:
+    """A configuration no golden file was recorded for (ragged batches, odd widths, deep nets): same interface as Golden
+    with K = 0 recorded updates. ReferenceRun then IS the reference for it: oracle/torch_port.py executes the reference's
+    torch op sequence (pinned bit-exact to /root/reference on every recorded configuration by test_oracle_golden.py)."""
+    full, big, stride, store_init, start_ckpt, K = True, False, 1, True, None, 0
+
+    def __init__(self, name, obs, act, cfg, n_fill):
+        self.name, self.obs, self.act, self.cfg, self.n_fill = name, obs, act, cfg, n_fill
+        self.meta = {"obs": obs, "act": act, "n_fill": n_fill, "K": 0, "config": cfg}
+        self._init = None
+
+    def has(self, k):
+        return False
+
+    def ckpt_path(self):
+        return None
+
+    def init_sd(self, tag):
+        if self._init is None:
+            import torch
+            from oracle.torch_port import _init_net
+            rng_state = torch.get_rng_state()
+            c, seed = self.cfg, self.cfg["train"]["seed"]
+            self._init = {}
+            for t, sizes, sd in (("pi", [self.obs] + list(c["policy_net"]["hidden_sizes"]) + [2 * self.act], seed),
+                                 ("q1", [self.obs + self.act] + list(c["q_net"]["hidden_sizes"]) + [1], seed),
+                                 ("q2", [self.obs + self.act] + list(c["q_net"]["hidden_sizes"]) + [1], seed + 1)):
+                ps = _init_net(sizes, sd)
+                self._init[t] = {f"net.{2 * (i // 2)}.{'weight' if i % 2 == 0 else 'bias'}": p.detach().numpy().copy() for i, p in enumerate(ps)}
+            torch.set_rng_state(rng_state)
+        return self._init[tag]
+
+
+def numpy_oracle_from_golden(g, dtype=np.float32):
     from oracle.sac_numpy import SACOracle, Hyper, mlp_from_state_dict
 
     c = g.cfg
@@ -175,11 +208,16 @@ def tensor_err(g: Golden, key, got):
 class ReferenceRun:
     NETS = ("pi", "q1", "q2", "q1t", "q2t")
 
-    def __init__(self, g: Golden, fill=True):
+    def __init__(self, g: Golden, fill=True, strict=False):
+        """strict=True (the CPU suite, same machine as the recording): bit equality with the golden file. strict=False (the
+        GPU box: another CPU, another GEMM blocking in torch's backward): the replay must sit within 1e-5 rel-L2 of every
+        recorded value -- it is then used as the full-tensor stand-in for the reference, next to direct comparisons of the
+        CUDA results with the golden file's own samples."""
         import torch
         from oracle.torch_port import TorchPortSAC
 
         self.g = g
+        self.strict = strict
         self.port = TorchPortSAC(g.obs, g.act, g.cfg, capacity=g.cfg["buffer"]["capacity"])
         if g.start_ckpt:
             self.port.load_checkpoint(torch.load(g.ckpt_path(), map_location="cpu", weights_only=False))
@@ -192,6 +230,10 @@ class ReferenceRun:
         self.k = 0
         self.port.hook_after_critics = self._mid
         self.mid = None
+        # the reference consumes the GLOBAL generators (Python `random`, torch CPU); keep private copies of their states so
+        # that other code seeding them between steps (network constructors, ...) cannot disturb the replay
+        import random
+        self._rng = (random.getstate(), torch.get_rng_state())
 
     # ---- snapshots (numpy copies) ---------------------------------------------------------------------------------
     @staticmethod
@@ -245,6 +287,9 @@ class ReferenceRun:
         import torch
         g, p, k = self.g, self.port, self.k
         B = g.cfg["train"]["batch_size"]
+        outer = (random.getstate(), torch.get_rng_state())
+        random.setstate(self._rng[0])
+        torch.set_rng_state(self._rng[1])
         before = self.state()
         st = random.getstate()
         idx = np.asarray(random.sample(range(len(p.memory)), B), dtype=np.int64)
@@ -254,24 +299,32 @@ class ReferenceRun:
         e2 = torch.empty(B, g.act).normal_().numpy()
         torch.set_rng_state(ts)
         info = p.training_step()
+        self._rng = (random.getstate(), torch.get_rng_state())
+        random.setstate(outer[0])
+        torch.set_rng_state(outer[1])
         out = {"idx": idx, "eps1": e1, "eps2": e2, "before": before, "mid": self.mid, "after": self.state(), "info": info,
                "y": p.last["y"].numpy().copy(), "lp": p.last["lp"].numpy().copy(), "q1": p.last["q1"].numpy().copy(),
                "q2": p.last["q2"].numpy().copy(), "q1_loss": float(p.last["q1_loss"]), "q2_loss": float(p.last["q2_loss"]),
                "policy_loss": float(p.last["policy_loss"]), "gpi": self._grads(p.pi)}
-        if k < g.K:                                     # inside the recorded range: the port IS the reference, bit for bit
+        if k < g.K:                                     # inside the recorded range: the port IS the reference
             gi, ge1, ge2 = g.streams(k)
-            assert np.array_equal(idx, gi) and np.array_equal(e1, ge1) and np.array_equal(e2, ge2)
+            assert np.array_equal(idx, gi) and np.array_equal(e1, ge1) and np.array_equal(e2, ge2)      # streams: always bits
             for key in ("y", "lp"):
                 ref, sel = g.rows(k, key)
-                assert np.array_equal(out[key][sel], ref), key
-            assert out["q1_loss"] == float(g[f"step{k}/q1_loss"])
-            for tag in ("pi", "q1", "q2"):
+                if self.strict:
+                    assert np.array_equal(out[key][sel], ref), key
+                else:
+                    assert rel_l2(out[key][sel], ref) < 1e-5, key
+            if self.strict:
+                assert out["q1_loss"] == float(g[f"step{k}/q1_loss"])
+            for tag in ("pi", "q1", "q2", "q1t", "q2t"):
                 for nm, v in out["after"][tag].items():
                     key = f"step{k}/{tag}/{nm}"
-                    if g.has(key):
-                        assert np.array_equal(v, g[key]), key
+                    if self.strict:
+                        assert np.array_equal(v, g[key]) if g.has(key) else np.array_equal(chk64(v), g[key + "#chk"]), key
                     else:
-                        assert np.array_equal(chk64(v), g[key + "#chk"]), key
+                        e, e2 = tensor_err(g, key, v)
+                        assert e < 1e-5 and (e2 is None or e2 < 1e-5), (key, e, e2)
         self.k += 1
         return out
 
@@ -281,3 +334,46 @@ class ReferenceRun:
         n, cap = self.g.n_fill, self.g.cfg["buffer"]["capacity"]
         rows = idx + max(n - cap, 0)
         return s[rows], a[rows], r[rows], s2[rows], d[rows].astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Discontinuity-aware comparison. relu' (and torch.min routing) make SAC's backward discontinuous: a hidden unit whose
+# pre-activation sits within rounding of zero gets derivative 0 in one correct fp32 implementation and 1 in another, and that
+# ONE (row, unit) moves a whole layer gradient by ~1e-3 rel-L2 (measured: tools/flip_probe.py, profiles/r02_flip_probe.txt --
+# the entire discrepancy of a 2048-row gradient sat in one row; without it 3e-6). The oracle knows which rows those are: the
+# ones where it sees a hidden pre-activation below `thr`. Gradients are therefore compared EXACTLY on all other rows: the
+# contribution of the flagged rows is subtracted on both sides (from the engine's per-row deltas / from the oracle's).
+def oracle_forward_backward(mlp, x, d_out):
+    """NumPy oracle MLP: per-layer inputs h_l (h_0 = x), pre-activations z_l and deltas (gradient w.r.t. z_l), l = 0..L-1."""
+    from oracle.sac_numpy import act_bwd
+    out, cache = mlp.forward(x)
+    L = mlp.n_layers
+    deltas = [None] * L
+    delta = d_out * act_bwd(mlp.out_act, cache["z"][L - 1], cache["h"][L])
+    for l in range(L - 1, -1, -1):
+        deltas[l] = delta
+        if l > 0:
+            delta = (delta @ mlp.W[l]) * act_bwd(mlp.hidden_act, cache["z"][l - 1], cache["h"][l])
+    dx = deltas[0] @ mlp.W[0]
+    return out, cache, deltas, dx
+
+
+def ambiguous_rows(mlp, cache, thr=2e-5):
+    """Rows with a hidden pre-activation within `thr` of the kink of a piecewise-linear activation (none for smooth ones)."""
+    B = cache["z"][0].shape[0]
+    amb = np.zeros(B, dtype=bool)
+    if mlp.hidden_act in ("relu", "leaky_relu"):
+        for z in cache["z"][:-1]:
+            amb |= (np.abs(z) < thr * max(1.0, float(np.sqrt(np.mean(z.astype(np.float64) ** 2))))).any(axis=1)
+    return amb
+
+
+def grads_without_rows(dW, db, deltas, inputs, rows):
+    """(dW_l, db_l) minus the contribution of `rows` (boolean mask): dW_l -= delta_l[rows]^T inputs_l[rows]."""
+    outW, outb = [], []
+    for l in range(len(dW)):
+        d = np.asarray(deltas[l], dtype=np.float64)[rows]
+        h = np.asarray(inputs[l], dtype=np.float64)[rows]
+        outW.append(np.asarray(dW[l], dtype=np.float64) - d.T @ h)
+        outb.append(np.asarray(db[l], dtype=np.float64).ravel() - d.sum(axis=0))
+    return outW, outb

@@ -206,3 +206,99 @@ def test_population_trials_match_single_agents_with_those_hyperparameters():
         assert abs(got - want) < 1e-6 * max(1.0, abs(want)), (ag, got, want)
         la.append(got)
     assert len({round(x, 6) for x in la}) == len(trials)              # the trials really differ
+
+
+@pytest.mark.parametrize("path", ["ffma", "tc"])
+def test_population_trials_full_hyperparameter_vectors(path, monkeypatch):
+    """Every scalar of the YAML's `sac` section per agent (run_search.py:24-39 is generic over section/param): actor_lr,
+    critic_lr, tau, gamma next to alpha / alpha_lr. Each agent of the population must follow a single-agent engine built from a
+    config with that trial's values -- through the one-CTA-per-agent FFMA kernel and through the population tensor-core path."""
+    from sac.engine import UpdateEngine
+    from sac.population import SACPopulation
+    from sac.replay_buffer import ReplayBuffer
+    from test_gpu_parity import _random_nets
+    tc = path == "tc"
+    obs, act = 5, 2
+    B, K, n = (128, 2, 128) if tc else (64, 3, 4)                    # tensor-core population path: >= 16384 rows in total
+    monkeypatch.setenv("SACX_TC_POP", "1" if tc else "0")
+    base = [{"alpha": 0.2, "alpha_lr": 3e-4, "actor_lr": 1e-3, "critic_lr": 3e-5, "tau": 0.05, "gamma": 0.9},
+            {"alpha": 0.004, "alpha_lr": 2e-2, "actor_lr": 1e-5, "critic_lr": 2e-3, "tau": 0.001, "gamma": 0.999},
+            {"critic_lr": 5e-4, "gamma": 0.5},
+            {}]
+    trials = [dict(base[i % 4]) for i in range(n)]
+    cfg = base_config(hidden=(64, 64), batch=B, capacity=600, alpha=0.1)
+    pop = SACPopulation(obs, act, cfg, n, reference_init=False)
+    assert pop.engine.tensor_core()[0] == tc, pop.engine.tensor_core()
+    nets = _random_nets(obs, act, (64, 64), (64, 64), scale=0.2)
+    s, a, r, s2, d = synth_transitions(500, obs, act, 1)
+    for ag in range(n):
+        load_nets(pop.engine, nets, agent=ag)
+    pop.engine.reset_state()
+    pop.set_trials(trials)
+    with pytest.raises(KeyError):
+        pop.set_trials([{"batch_size": 3}] * n)                      # structural keys are not per-agent
+    for ag in range(n):
+        pop.ring.push_batch(s, a, r, s2, d.astype(np.float32), agent=ag)
+    rng = np.random.default_rng(2)
+    idx = np.broadcast_to(rng.integers(0, 500, (K, 1, B)), (K, n, B)).astype(np.int64).copy()
+    e1 = np.broadcast_to(rng.standard_normal((K, 1, B, act)), (K, n, B, act)).astype(np.float32).copy()
+    e2 = np.broadcast_to(rng.standard_normal((K, 1, B, act)), (K, n, B, act)).astype(np.float32).copy()
+    pop.engine.update(dev(idx), dev(e1), dev(e2), K)
+    pop.engine.sync()
+    finals = []
+    for ag in range(4):
+        t = trials[ag]
+        c1 = base_config(hidden=(64, 64), batch=B, capacity=600, alpha=t.get("alpha", 0.1))
+        for k in ("alpha_lr", "actor_lr", "critic_lr", "tau", "gamma"):
+            if k in t:
+                c1["sac"][k] = t[k]
+        monkeypatch.setenv("SACX_ROWPAR", "0")
+        one = UpdateEngine(obs, act, c1)
+        load_nets(one, nets)
+        one.reset_state()
+        rb = ReplayBuffer(600, obs, act)
+        rb.push_batch(s, a, r, s2, d.astype(np.float32))
+        one.attach_ring(rb)
+        one.update(dev(idx[:, ag]), dev(e1[:, ag]), dev(e2[:, ag]), K)
+        one.sync()
+        tol = 1e-4 if tc else 3e-5                                   # 3xTF32 tiles vs FFMA tiles
+        for blk in ("block.params", "block.targets"):
+            assert_close(f"agent {ag} {blk}", pop.engine.view(blk, ag).cpu().numpy(), one.view(blk).cpu().numpy(), tol)
+        assert_close(f"agent {ag} y", pop.engine.view("out.y", ag).cpu().numpy(), one.view("out.y").cpu().numpy(), 2e-5)
+        got, want = float(pop.engine.view("scal.log_alpha", ag)), float(one.view("scal.log_alpha"))
+        assert abs(got - want) < 2e-6 * max(1.0, abs(want)), (ag, got, want)
+        finals.append(pop.engine.view("block.params", ag).cpu().numpy().copy())
+        if n > 4:                                                    # agents 4.. repeat the trials of agents 0..3
+            assert_close(f"agent {ag + 4} == agent {ag}", pop.engine.view("block.params", ag + 4).cpu().numpy(), finals[ag], 1e-6)
+    assert not np.array_equal(finals[0], finals[1]) and not np.array_equal(finals[2], finals[3])
+
+
+def test_population_rng_streams_are_keyed_by_global_agent_and_seed():
+    """Advisor finding (round 1): the device index / normal streams were keyed by the LOCAL agent index, so local agent 0 of
+    two ranks drew identical permutations and noise. Now: (train.seed or the agent's own seed, GLOBAL agent id)."""
+    from sac.population import SACPopulation
+    obs, act, B = 4, 1, 64
+    cfg = base_config(hidden=(32, 32), batch=B, capacity=2000, rng="device")
+    s, a, r, s2, d = (torch.from_numpy(x).cuda() for x in synth_transitions(1500, obs, act, 3))
+
+    def draws(pop):
+        pop.push_device_all(s, a, r, s2, d.float())
+        pop.update(1)
+        pop.engine.sync()
+        return [(pop.engine.view("batch.idx", ag).cpu().numpy().copy(), pop.engine.view("batch.eps1", ag).cpu().numpy().copy(),
+                 pop.engine.act_population(torch.zeros(pop.n_local, 1, obs, device="cuda")).cpu().numpy()[ag].copy())
+                for ag in range(pop.n_local)]
+
+    r0 = draws(SACPopulation(obs, act, cfg, 4, rank=0, world=2, reference_init=False))
+    r1 = draws(SACPopulation(obs, act, cfg, 4, rank=1, world=2, reference_init=False))
+    whole = draws(SACPopulation(obs, act, cfg, 4, rank=0, world=1, reference_init=False))
+    for x in r0 + r1:
+        assert len(np.unique(x[0])) == B
+    assert not np.array_equal(r0[0][0], r1[0][0]) and not np.array_equal(r0[0][1], r1[0][1])       # same local index, other rank
+    for g, x in enumerate(r0 + r1):                    # sharding does not change an agent's streams: global agent g either way
+        assert np.array_equal(x[0], whole[g][0]) and np.array_equal(x[1], whole[g][1])
+    # an agent's own seed replaces train.seed as the first key
+    seeded = draws(SACPopulation(obs, act, cfg, 4, seeds=[11, 12, 13, 14], rank=0, world=1, reference_init=False))
+    again = draws(SACPopulation(obs, act, cfg, 4, seeds=[11, 12, 13, 14], rank=0, world=1, reference_init=False))
+    assert not np.array_equal(seeded[1][0], whole[1][0])
+    assert all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(seeded, again))

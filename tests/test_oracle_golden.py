@@ -170,3 +170,14 @@ def test_select_action_golden():
         st = g["act/state"][None, :]
         assert rel_l2(o.act(st, deterministic=True)[0], g["act/deterministic"]) < 1e-5
         assert rel_l2(o.act(st, eps=g["act/eps"])[0], g["act/stochastic"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["cfg3_pendulum256", "ckpt_tiny_auto", "ckpt_pendulum128"])
+def test_reference_run_helper_is_bit_exact(name):
+    """tests/helpers.py::ReferenceRun (the full-tensor stand-in for the reference used by the GPU suite) in strict mode."""
+    from helpers import ReferenceRun
+    g = Golden(name)
+    ref = ReferenceRun(g, strict=True)
+    for _ in range(g.K):
+        r = ref.step()
+        assert r["mid"] is not None and set(r["after"]) >= {"pi", "q1", "q2", "q1t", "q2t", "adam", "alpha"}
