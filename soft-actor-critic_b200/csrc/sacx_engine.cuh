@@ -54,7 +54,7 @@ struct Engine {
   std::vector<sacx_tensor_desc> lay;
   i64 cur = 0, stride = 0;
   NetLayout pi, q1, q2;
-  i64 P0 = 0, blk = 0, T0 = 0, scal_off = 0;
+  i64 P0 = 0, blk = 0, T0 = 0, scal_off = 0, pi_x = 0;
   i64 n_online = 0, n_critic = 0;
   // batch / scratch
   int ldx = 0;
@@ -190,6 +190,10 @@ struct Engine {
     cur = align4(cur);
     P0 = cur;
     layout_net(pi, "pi", O, cfg.hidden_pi, cfg.n_hidden_pi, 2 * A, cfg.act_hidden_pi, cfg.act_out_pi);
+    // four spare floats behind the policy in every block: in the GRADIENT block they carry this rank's share of the temperature
+    // gradient, so the data-parallel exchange #2 is ONE all-reduce of [policy gradients | share] ("block.g.policy_x")
+    pi_x = cur;
+    cur += 4;
     layout_net(q1, "q1", O + A, cfg.hidden_q, cfg.n_hidden_q, 1, cfg.act_hidden_q, cfg.act_out_q);
     layout_net(q2, "q2", O + A, cfg.hidden_q, cfg.n_hidden_q, 1, cfg.act_hidden_q, cfg.act_out_q);
     blk = align4(cur - P0);
@@ -208,6 +212,7 @@ struct Engine {
     { // contiguous gradient slices for the data-parallel all-reduce
       sacx_tensor_desc d; memset(&d, 0, sizeof d);
       snprintf(d.name, sizeof d.name, "block.g.policy"); d.offset = pi.begin + 3 * blk; d.rows = 1; d.cols = d.ld = (int)(pi.end - pi.begin); lay.push_back(d);
+      snprintf(d.name, sizeof d.name, "block.g.policy_x"); d.cols = d.ld = (int)(pi.end - pi.begin) + 4; lay.push_back(d);
       snprintf(d.name, sizeof d.name, "block.g.critics"); d.offset = q1.begin + 3 * blk; d.cols = d.ld = (int)(q2.end - q1.begin); lay.push_back(d);
     }
     cur = P0 + 4 * blk;
@@ -484,6 +489,7 @@ struct Engine {
     Op o = blank(OP_FINAL);
     o.mode = mode; o.ntiles = 1;
     o.o[0] = b_loss[0]; o.o[1] = b_loss[1]; o.o[2] = b_ploss; o.o[3] = b_lp; o.o[4] = b_q[0]; o.o[5] = b_q[1]; o.o[6] = b_y;
+    o.o[7] = pi_x + 3 * blk;                    // temperature-gradient share next to the policy gradients (data parallel)
     return o;
   }
   Op op_polyak() const {

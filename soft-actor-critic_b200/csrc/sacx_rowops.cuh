@@ -737,11 +737,15 @@ __device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int
     }
     const float mean_t = final_sum<CTA>(acc, red) * invB;           // f32 mean, as in the reference
     const float mean_lt = final_sum<CTA>(accl, red) * invB;
-    if (lane == 0) { s->dp_mean_t = mean_t; s->dp_mean_lt = mean_lt; }
+    if (lane == 0) {
+      s->dp_mean_t = mean_t; s->dp_mean_lt = mean_lt;
+      if (op.mode & 16) { base[op.o[7]] = mean_t; base[op.o[7] + 1] = mean_lt; }      // travels with the policy gradients
+    }
     if (CTA) __syncthreads();
   }
   if ((op.mode & (4 | 32)) && lane == 0) {
-    const float mean_t = s->dp_mean_t, mean_lt = s->dp_mean_lt;
+    const float mean_t = (op.mode & 32) ? __ldcg(base + op.o[7]) : s->dp_mean_t;       // 32: the all-reduced shares
+    const float mean_lt = (op.mode & 32) ? __ldcg(base + op.o[7] + 1) : s->dp_mean_lt;
     s->metrics[8] = mean_t - hp.target_entropy;
     if (hp.auto_alpha) {
       // alpha_loss = -(log_alpha * (logpi + H).detach()).mean();  d/dlog_alpha = -mean(logpi + H)

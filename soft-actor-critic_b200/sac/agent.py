@@ -280,12 +280,20 @@ class SAC:
         self.engine.polyak()
 
     def training_step(self) -> None:
-        """reference: agent.py:302-327 -- one full gradient update, one fused kernel launch."""
+        """reference: agent.py:302-327 -- one full gradient update, one fused kernel launch.
+
+        Host-RNG mode submits the update software-pipelined (H2D of this step's index stream + normals, kernel, D2H of the
+        metrics block; the metrics of the PREVIOUS step are collected while this one runs), so the host draws step t+1 while
+        step t executes. A non-finite policy head -- where the reference's ``Normal(mu, std)`` raises ValueError at once -- is
+        reported here one step late, from the collected metrics."""
         B = self.config["train"]["batch_size"]
         if self.rng_mode == "host":
             idx = np.asarray(self.replay_buffer.draw_indices(B), dtype=np.int64)
             e1, e2 = self._normal(B), self._normal(B)
-            self.engine.update_host(idx, e1, e2, 1, want_metrics=False)
+            m = self.engine.update_host_pipelined(idx, e1, e2, 1)
+            self._host_pending = True
+            if m is not None and m["nonfinite"]:
+                raise ValueError("policy head produced non-finite mean/std (torch Normal would have rejected them)")
         else:
             if len(self.replay_buffer) < B:
                 self.replay_buffer._require(B)
@@ -303,6 +311,9 @@ class SAC:
 
     def last_metrics(self) -> Dict[str, float]:
         """Device-side losses / temperature of the most recent update (synchronises)."""
+        if getattr(self, "_host_pending", False):
+            self.engine.update_host_flush()
+            self._host_pending = False
         m = self.engine.metrics()
         if m["nonfinite"]:
             raise ValueError("policy head produced non-finite mean/std (torch Normal would have rejected them)")

@@ -8,8 +8,8 @@ its only "parallelism" is the Optuna driver launching sequential ``main.py`` sub
                       there is NO collective on the data path -- only an optional gather of scalar metrics.
 ``DataParallelSAC``   one agent, global batch split B/G rows per rank, parameters replicated. The critic step
                       precedes the actor forward (F4), so there are two exchange points per update:
-                      all-reduce(sum) of the critic gradients, then of the policy gradients + the temperature
-                      gradient share. NCCL over NVLink through torch.distributed, on the engine's stream.
+                      all-reduce(sum) of the critic gradients, then ONE all-reduce of the policy gradients with the
+                      temperature-gradient share stored right behind them. NCCL over NVLink through torch.distributed, on the engine's stream.
 """
 from __future__ import annotations
 
@@ -244,14 +244,29 @@ class DataParallelSAC:
         self.engine.reset_state()
         self.engine.attach_ring(self.ring)
         self.g_critics = self.engine.view("block.g.critics").reshape(-1)
-        self.g_policy = self.engine.view("block.g.policy").reshape(-1)
-        self.g_alpha = self.engine.view("scal.dp_alpha").reshape(-1)
-        self.allreduce_seconds = 0.0
+        # exchange #2 is ONE message: the policy gradients with this rank's temperature-gradient share right behind them
+        self.g_policy = self.engine.view("block.g.policy_x").reshape(-1)
+        self.time_exchange = False            # bench: CUDA events around the two exchanges
+        self._events = []
 
     def _allreduce(self, t: torch.Tensor) -> None:
         d = _dist()
         if d is not None and self.world > 1:
-            d.all_reduce(t, op=d.ReduceOp.SUM)
+            if self.time_exchange:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                d.all_reduce(t, op=d.ReduceOp.SUM)
+                e1.record()
+                self._events.append((e0, e1))
+            else:
+                d.all_reduce(t, op=d.ReduceOp.SUM)
+
+    def exchange_ms(self) -> float:
+        """Device time spent inside the all-reduces since the last call (needs time_exchange = True; synchronises)."""
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._events)
+        self._events = []
+        return ms
 
     # The update in three local segments separated by the two exchange points (F4).
     def segment_critic_grads(self, idx=None, eps1=None) -> None:
@@ -275,6 +290,5 @@ class DataParallelSAC:
         self.segment_critic_grads(idx, eps1)
         self._allreduce(self.g_critics)               # exchange #1: 588 KB at BipedalWalker shape
         self.segment_critic_apply_actor_grads(eps2)
-        self._allreduce(self.g_policy)                # exchange #2: 297 KB + the temperature-gradient share
-        self._allreduce(self.g_alpha)
+        self._allreduce(self.g_policy)                # exchange #2: 297 KB, the temperature-gradient share rides along
         self.segment_actor_apply()

@@ -130,9 +130,11 @@ def test_fused_update_teacher_forced_vs_reference(name, path, want, monkeypatch)
         # test_per_phase_teacher_forced_vs_reference, which checks the gradients exactly off those rows). End-to-end bars:
         # critics 1e-4 (2e-4 at batch >= 16384, where the reference's own fp32 batch reduction is 2e-4 from exact), policy 2x.
         pb = 2e-4 if B >= 16384 else 1e-4
-        for tag in ("q1", "q2"):
-            assert_net(eng, tag, r["after"][tag], pb, f"step{k} param")
-        assert_net(eng, "pi", r["after"]["pi"], 3e-4, f"step{k} param")
+        for tag, wbar in (("q1", pb), ("q2", pb), ("pi", 3e-4)):
+            for nm, e in net_errs(eng, tag, r["after"][tag]).items():
+                # (biases start at exactly zero: after one or two Adam steps every element is a few +-lr, i.e. sign(g) of
+                #  noise-level gradient elements decides them -- 2e-3 there, the weights carry the bar)
+                assert e < (wbar if nm.endswith("weight") else 2e-3), f"step{k} param {tag}.{nm}: rel-L2 {e:.3e}"
         tau = float(g.cfg["sac"]["tau"])
         for tag in ("q1t", "q2t"):          # target' = tau p' + (1 - tau) target: its error is tau x the critic's error
             got = read_net(eng, tag, len(r["after"][tag]) // 2)
@@ -146,7 +148,8 @@ def test_fused_update_teacher_forced_vs_reference(name, path, want, monkeypatch)
                 mb = 5e-4 if B >= 16384 else 1e-4         # Adam's m is the gradient: same floor as above
                 e = rel_l2(eng.view(f"m.{tag}.{wb}{l}").cpu().numpy().reshape(m_ref.shape), m_ref)
                 assert e < mb or e < 5e-3 and B >= 1024, f"step{k} m.{tag}.{wb}{l}: rel-L2 {e:.3e}"       # (5e-3: one flipped row)
-                assert_close(f"step{k} v.{tag}.{wb}{l}", eng.view(f"v.{tag}.{wb}{l}").cpu().numpy().reshape(v_ref.shape), v_ref, 2 * mb)
+                e = rel_l2(eng.view(f"v.{tag}.{wb}{l}").cpu().numpy().reshape(v_ref.shape), v_ref)
+                assert e < 2 * mb or e < 1e-2 and B >= 1024, f"step{k} v.{tag}.{wb}{l}: rel-L2 {e:.3e}"
         assert [int(x) for x in eng.view("scal.step").cpu()][:3] == [int(r["after"]["adam"][t]["net.0.weight"][2]) for t in ("pi", "q1", "q2")]
         if auto and not g.start_ckpt:
             # (after load_agent the reference's temperature is frozen -- torch_port.load_checkpoint explains why -- ours keeps
@@ -191,6 +194,38 @@ def _check_layer_grads(eng, what, tag, ref_grads, mlp, x, d_out, amb, delta_name
     return int(amb.sum())
 
 
+def _check_adam_given_own_gradient(eng, what, tag, before, lr, polyak_tau=None, targets_before=None):
+    """Adam (and the Polyak update behind it) as arithmetic: from the reference's state before the step and the gradient THE
+    ENGINE holds (its g.* block, just compared with the reference's off the discontinuities), torch's _single_tensor_adam in
+    NumPy float32 must reproduce the engine's new parameters / moments to rounding -- 2e-6 -- whatever a relu kink did to the
+    gradient. Together with the gradient check this pins the step without Adam's sign(g) amplification of noise-level elements."""
+    from oracle.sac_numpy import AdamState
+    names = list(before[tag].keys())
+    params = [before[tag][nm].copy() for nm in names]
+    st = AdamState(lr, [before["adam"][tag][nm][0].copy() for nm in names], [before["adam"][tag][nm][1].copy() for nm in names],
+                   step=int(before["adam"][tag][names[0]][2]))
+    grads = []
+    for nm in names:
+        l, wb = int(nm.split(".")[1]) // 2, ("W" if nm.endswith("weight") else "b")
+        grads.append(_np(eng.view(f"g.{tag}.{wb}{l}")).reshape(before[tag][nm].shape).copy())
+    return names, params, st, grads
+
+
+def _apply_and_compare(eng, what, tag, names, params, st, grads, tau=None, targets_before=None):
+    st.apply(params, grads)
+    got = read_net(eng, tag, len(names) // 2)
+    for nm, p, m, v in zip(names, params, st.m, st.v):
+        l, wb = int(nm.split(".")[1]) // 2, ("W" if nm.endswith("weight") else "b")
+        assert rel_l2(got[nm], p) < 2e-6, f"{what} Adam on {tag}.{nm}: {rel_l2(got[nm], p):.3e}"
+        assert rel_l2(_np(eng.view(f"m.{tag}.{wb}{l}")).reshape(m.shape), m) < 2e-6, f"{what} m.{tag}.{nm}"
+        assert rel_l2(_np(eng.view(f"v.{tag}.{wb}{l}")).reshape(v.shape), v) < 2e-6, f"{what} v.{tag}.{nm}"
+    if tau is not None:                  # Polyak fused behind the critic step: tau * p_new + (1 - tau) * target_old, products rounded separately
+        gott = read_net(eng, tag + "t", len(names) // 2)
+        for nm, p in zip(names, got.values()):
+            want = (np.float32(tau) * got[nm]).astype(np.float32) + (np.float32(1.0 - tau) * targets_before[nm]).astype(np.float32)
+            assert np.array_equal(gott[nm], want), f"{what} fused Polyak {tag}t.{nm}"
+
+
 @pytest.mark.parametrize("name,path,want", [c for c in CASES if c[2] != "rowpar"])
 def test_per_phase_teacher_forced_vs_reference(name, path, want, monkeypatch):
     """The per-method entry points (sacx_sample_batch, sacx_target, sacx_critic_grads/step, sacx_actor_grads/step,
@@ -227,7 +262,7 @@ def test_per_phase_teacher_forced_vs_reference(name, path, want, monkeypatch):
         assert_close(f"step{k} q1", _np(eng.view("out.q1")).ravel(), r["q1"], 2e-5)
         x = np.concatenate([s, a], axis=1)
         floors = {}
-        if B >= 16384:          # float64 twin of the critic gradients: the reference's own distance from exact arithmetic
+        if True:                # float64 twin of the critic gradients: the reference's own distance from exact arithmetic
             o64 = numpy_oracle_from_golden(g, np.float64)
             for tag in ("q1", "q2"):
                 net = mlp_from_state_dict(r["before"][tag], qn["hidden_layers_act"], qn["output_activation"], np.float64)
@@ -247,9 +282,14 @@ def test_per_phase_teacher_forced_vs_reference(name, path, want, monkeypatch):
             flagged += _check_layer_grads(eng, f"step{k}", tag, r["mid"]["g" + tag], mlp, x, d_out, amb,
                                           [f"delta.{tag}.{l}" for l in range(Lq - 1)] + [f"scr.dout{c + 1}"],
                                           ["batch.sa"] + [f"act.{tag}.h{l}" for l in range(Lq - 1)], 5e-5, floors.get(tag))
+        pend = {tag: _check_adam_given_own_gradient(eng, f"step{k}", tag, r["before"], float(g.cfg["sac"]["critic_lr"])) for tag in ("q1", "q2")}
         eng.critic_step(dev(r["y"]))
         for tag in ("q1", "q2"):
-            assert_net(eng, tag, r["mid"][tag], 2e-4 if B >= 16384 else 1e-4, f"step{k} param")
+            # sacx_critic_step is the reference's update_q_networks (no Polyak); against the reference's post-step critics the bar
+            # allows for Adam's lr * sign(g) on noise-level elements (3e-4 for weights; biases start at exactly zero)
+            _apply_and_compare(eng, f"step{k}", tag, *pend[tag])
+            for nm, e in net_errs(eng, tag, r["mid"][tag]).items():
+                assert e < (3e-4 if nm.endswith("weight") else 2e-3), f"step{k} param {tag}.{nm}: {e:.3e}"
         load_nets(eng, {"q1": r["mid"]["q1"], "q2": r["mid"]["q2"]})          # teacher-force the critics
         # ---- a8: actor
         lp = torch.empty(B, device="cuda")
@@ -263,17 +303,17 @@ def test_per_phase_teacher_forced_vs_reference(name, path, want, monkeypatch):
                 w_dst[...] = w_src
         o.alpha = np.float32(r["before"]["alpha"])
         ag = o.actor_grads(s, r["eps2"])
-        for nm, v in r["gpi"].items():                                # the oracle's closed forms == the reference's autograd
-            l = int(nm.split(".")[1]) // 2
-            assert rel_l2(ag["dW"][l] if nm.endswith("weight") else ag["db"][l], v) < (5e-4 if B >= 16384 else 2e-5), nm
         _, pcache = o.pi.forward(s)
         xa = np.concatenate([s, ag["a"]], axis=1)
         amb = ambiguous_rows(o.pi, pcache)
         for net in (o.q1, o.q2):
             amb |= ambiguous_rows(net, net.forward(xa)[1])
-        amb |= np.abs(ag["q1"] - ag["q2"]) < 2e-5 * np.maximum(1.0, np.abs(ag["q1"]))            # torch.min routing
+        # torch.min routing: near-ties are ambiguous; EXACT ties are not (the shipped InvertedPendulum checkpoint has bit-identical
+        # twin critics -- Q1 == Q2 on every row -- and both sides split the gradient 1/2 - 1/2, agent.py:248 / torch.min backward)
+        dq = np.abs(ag["q1"] - ag["q2"])
+        amb |= (dq > 0) & (dq < 2e-5 * np.maximum(1.0, np.abs(ag["q1"])))
         floor_pi = None
-        if B >= 16384:
+        if True:
             o64 = numpy_oracle_from_golden(g, np.float64)
             for tag, cfgk in (("pi", pn), ("q1", qn), ("q2", qn)):
                 src = r["before"]["pi"] if tag == "pi" else r["mid"][tag]
@@ -286,13 +326,21 @@ def test_per_phase_teacher_forced_vs_reference(name, path, want, monkeypatch):
             for l in range(Lp):
                 floor_pi[f"net.{2 * l}.weight"] = rel_l2(r["gpi"][f"net.{2 * l}.weight"], ag64["dW"][l])
                 floor_pi[f"net.{2 * l}.bias"] = rel_l2(r["gpi"][f"net.{2 * l}.bias"], ag64["db"][l])
+        # the oracle's closed forms (models.py:79-87 differentiated by hand) against the reference's autograd: equal up to the
+        # reference's own distance from exact arithmetic (its Gaussian quadratic term cancels only approximately in fp32 when
+        # sigma is small -- trained policies -- and its batch reductions are fp32)
+        for nm, v in r["gpi"].items():
+            l = int(nm.split(".")[1]) // 2
+            e = rel_l2(ag["dW"][l] if nm.endswith("weight") else ag["db"][l], v)
+            assert e < max(2e-5, 2.0 * floor_pi[nm]), (nm, e, floor_pi[nm])
         flagged += _check_layer_grads(eng, f"step{k}", "pi", r["gpi"], o.pi, s, ag["d_head"], amb,
                                       [f"delta.pi.{l}" for l in range(Lp - 1)] + ["scr.dhead"],
                                       ["batch.spi"] + [f"act.pia.h{l}" for l in range(Lp - 1)], 5e-5, floor_pi)
+        pend_pi = _check_adam_given_own_gradient(eng, f"step{k}", "pi", r["before"], float(g.cfg["sac"]["actor_lr"]))
         eng.actor_step(dev(r["eps2"]), lp)
-        # Adam's first steps are lr * sign(g): a flagged row can turn the sign of the noise-level elements of a gradient, so the
-        # parameter bar is 3e-4 when rows were flagged (the gradients themselves were just checked exactly)
-        assert_net(eng, "pi", r["after"]["pi"], 3e-4 if amb.any() else 1e-4, f"step{k} param")
+        _apply_and_compare(eng, f"step{k}", "pi", *pend_pi)
+        for nm, e in net_errs(eng, "pi", r["after"]["pi"]).items():
+            assert e < (3e-4 if nm.endswith("weight") else 2e-3), f"step{k} param pi.{nm}: {e:.3e}"
         if auto and not g.start_ckpt:
             info = eng.alpha_step(dev(r["lp"]), want_metrics=True)
             assert abs(float(eng.view("scal.log_alpha").item()) - r["after"]["log_alpha"]) < 1e-6

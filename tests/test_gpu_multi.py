@@ -35,8 +35,7 @@ def _lockstep_update(ranks, idx=None, e1=None, e2=None):
     allreduce("g_critics")
     for r, dp in enumerate(ranks):
         dp.segment_critic_apply_actor_grads(sl(e2, r))
-    allreduce("g_policy")
-    allreduce("g_alpha")
+    allreduce("g_policy")                       # policy gradients + the temperature-gradient share: one message
     for dp in ranks:
         dp.segment_actor_apply()
 
