@@ -138,6 +138,24 @@ int sacx_ring_gather_host(sacx_ring_t r, int32_t agent, const int64_t* logical_i
 int sacx_ring_sample_indices(sacx_ring_t r, int32_t agent, uint64_t seed, uint64_t counter, int32_t B,
                              int64_t* logical_idx_dev);
 
+/* ---------------------------------------------------------------- DonkeyVae producer: device-side observation assembly
+ * (SURVEY section 8f-4). Replaces the NumPy bookkeeping of DonkeyCarEnv/donkey_gym/envs/vae_env.py:175-210 (postprocessing_step:
+ * command-history roll, [latent | history] frame, frame stack with zeroing at episode end) and :253-266 (reset) for a latent
+ * that already lives on the device (DonkeyCarEnv/ae/autoencoder.py:64-89 encodes on cuda), and stores the transition
+ * (previous stack, action, reward, new stack, done) into the replay ring without a host bounce.
+ * Observation width = n_stack * (z_size + n_commands * n_command_history): 3 * (32 + 2 * 20) = 216 in the shipped setup. */
+typedef struct sacx_obs_s* sacx_obs_t;
+int sacx_obs_create(int32_t z_size, int32_t n_commands, int32_t n_command_history, int32_t n_stack, sacx_obs_t* out);
+int sacx_obs_destroy(sacx_obs_t h);
+int32_t sacx_obs_dim(sacx_obs_t h);
+/* env.reset(): history and stack zeroed, newest frame = [latent | 0]. obs_out_dev (nullable) receives the stacked observation. */
+int sacx_obs_reset(sacx_obs_t h, const float* latent_dev, float* obs_out_dev, void* cuda_stream);
+/* env.step() post-processing. The action comes from the device (action_dev) or the host (action_host, <= 2 commands); with a
+ * ring the transition is pushed on the ring's stream (ring dims must be (sacx_obs_dim, n_commands)), else cuda_stream is used. */
+int sacx_obs_step(sacx_obs_t h, const float* latent_dev, const float* action_dev /* nullable */, const float* action_host /* nullable */,
+                  float reward, int32_t done, sacx_ring_t ring /* nullable */, int32_t agent, float* obs_out_dev /* nullable */,
+                  void* cuda_stream);
+
 /* ---------------------------------------------------------------- agent
  * One arena of float32 words per agent holds parameters (nn.Linear layout [out,in]), target
  * parameters, Adam moments, gradients, temperature scalars (f64), batch and activation scratch.

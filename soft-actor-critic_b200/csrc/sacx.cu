@@ -732,6 +732,71 @@ int sacx_ring_sample_indices(sacx_ring_t h, int32_t agent, uint64_t seed, uint64
   return SACX_OK;
 }
 
+// ---------------------------------------------------------------------------------------- DonkeyVae observation assembly
+struct sacx_obs_s {
+  int z = 0, n_cmd = 0, n_hist = 0, n_stack = 0, F = 0, S = 0;
+  float* dev = nullptr;          // [hist H | stack S | prev S | act n_cmd | r, d]
+  float* hist() { return dev; }
+  float* stack() { return dev + n_cmd * n_hist; }
+  float* prev() { return stack() + S; }
+  float* act() { return prev() + S; }
+  float* rd() { return act() + n_cmd; }
+};
+
+int sacx_obs_create(int32_t z_size, int32_t n_commands, int32_t n_command_history, int32_t n_stack, sacx_obs_t* out) {
+  if (!out || z_size <= 0 || n_commands <= 0 || n_command_history < 0 || n_stack < 1) return fail(SACX_ERR_INVALID, "obs_create: bad arguments");
+  sacx_obs_s* h = new sacx_obs_s();
+  h->z = z_size; h->n_cmd = n_commands; h->n_hist = n_command_history; h->n_stack = n_stack;
+  h->F = z_size + n_commands * n_command_history; h->S = h->F * n_stack;
+  if ((size_t)(n_commands * n_command_history + h->S) * 4 > 40000) { delete h; return fail(SACX_ERR_INVALID, "obs_create: observation too wide"); }
+  const size_t floats = (size_t)n_commands * n_command_history + 2 * (size_t)h->S + n_commands + 2;
+  if (cudaMalloc((void**)&h->dev, floats * 4) != cudaSuccess) { delete h; return fail(SACX_ERR_CUDA, "obs_create: cudaMalloc failed"); }
+  cudaMemset(h->dev, 0, floats * 4);
+  *out = h;
+  return SACX_OK;
+}
+int sacx_obs_destroy(sacx_obs_t h) {
+  if (!h) return SACX_OK;
+  if (h->dev) cudaFree(h->dev);
+  delete h;
+  return SACX_OK;
+}
+int32_t sacx_obs_dim(sacx_obs_t h) { return h ? h->S : 0; }
+
+static int obs_launch(sacx_obs_t h, const float* latent, const float* action_dev, float a0, float a1, float reward, int done, int reset,
+                      cudaStream_t st) {
+  const size_t smem = (size_t)(h->n_cmd * h->n_hist + h->S) * 4;
+  obs_assemble_kernel<<<1, 256, smem, st>>>(h->hist(), h->stack(), h->prev(), reset ? nullptr : h->act(), reset ? nullptr : h->rd(), latent,
+                                            action_dev, a0, a1, reward, done, reset, h->z, h->n_cmd, h->n_hist, h->n_stack);
+  SACX_CUDA(cudaGetLastError());
+  return SACX_OK;
+}
+
+int sacx_obs_reset(sacx_obs_t h, const float* latent_dev, float* obs_out_dev, void* stream) {
+  if (!h || !latent_dev) return fail(SACX_ERR_INVALID, "obs_reset: bad arguments");
+  int rc = obs_launch(h, latent_dev, nullptr, 0.f, 0.f, 0.f, 0, 1, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (obs_out_dev) SACX_CUDA(cudaMemcpyAsync(obs_out_dev, h->stack(), (size_t)h->S * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SACX_OK;
+}
+
+int sacx_obs_step(sacx_obs_t h, const float* latent_dev, const float* action_dev, const float* action_host, float reward, int32_t done,
+                  sacx_ring_t ring, int32_t agent, float* obs_out_dev, void* stream) {
+  if (!h || !latent_dev || (!action_dev && !action_host)) return fail(SACX_ERR_INVALID, "obs_step: bad arguments");
+  if (!action_dev && h->n_cmd > 2) return fail(SACX_ERR_INVALID, "obs_step: host actions carry at most 2 commands");
+  cudaStream_t st = ring ? ring->r.stream : (cudaStream_t)stream;
+  if (ring && (ring->r.O != h->S || ring->r.A != h->n_cmd)) return fail(SACX_ERR_INVALID, "obs_step: ring dimensions do not match the assembled observation");
+  const float a0 = action_host ? action_host[0] : 0.f, a1 = (action_host && h->n_cmd > 1) ? action_host[1] : 0.f;
+  int rc = obs_launch(h, latent_dev, action_dev, a0, a1, reward, done, 0, st);
+  if (rc) return rc;
+  if (ring) {        // (previous stack, action, reward, new stack, done): straight from device staging into the ring
+    rc = sacx_ring_push_n_dev(ring, agent, 1, h->prev(), h->act(), h->rd(), h->stack(), h->rd() + 1);
+    if (rc) return rc;
+  }
+  if (obs_out_dev) SACX_CUDA(cudaMemcpyAsync(obs_out_dev, h->stack(), (size_t)h->S * 4, cudaMemcpyDeviceToDevice, st));
+  return SACX_OK;
+}
+
 // ---------------------------------------------------------------------------------------- agent API
 int sacx_agent_arena_floats(const sacx_config* cfg, int64_t* out) {
   int rc = validate(cfg);

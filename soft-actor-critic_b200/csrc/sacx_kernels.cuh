@@ -409,6 +409,44 @@ __global__ void ring_indices_kernel(const float* __restrict__ rb, i64 cap, unsig
   out[i] = (i64)feistel_index((unsigned long long)i, (unsigned long long)n, seed, counter, (uint32_t)agent);
 }
 
+// ---- device-side observation assembly of the DonkeyVae producer ------------------------------------------------
+// reference: DonkeyCarEnv/donkey_gym/envs/vae_env.py:175-210 (postprocessing_step) and :253-266 (reset). The VAE latent is
+// already on the device (ae/autoencoder.py encodes on cuda); the 2 x n_command_history command history is rolled, the
+// [latent | history] frame appended to the n_stack frame stack (zeroed first when the episode ended), and the transition
+// (previous stack, action, reward, new stack, done) is left in device staging for sacx_ring_push_n_dev -- no host bounce.
+//   hist  [n_cmd * n_hist]        command history (oldest first)
+//   stack [n_stack * frame]       frame stack (oldest first), frame = z + n_cmd * n_hist
+//   prev  [n_stack * frame]       out: the stack before this step (the transition's state)
+// One CTA; every thread reads what it needs before the barrier and writes after it (in-place roll).
+__global__ void obs_assemble_kernel(float* __restrict__ hist, float* __restrict__ stack, float* __restrict__ prev, float* __restrict__ act_out,
+                                    float* __restrict__ rd_out, const float* __restrict__ latent, const float* __restrict__ action,
+                                    float a0, float a1, float reward, int done, int reset, int z, int n_cmd, int n_hist, int n_stack) {
+  extern __shared__ float sm[];
+  const int H = n_cmd * n_hist, F = z + H, S = n_stack * F;
+  float* nh = sm;            // new history [H]
+  float* ns = sm + H;        // new stack [S]
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float v;
+    if (reset) v = 0.f;
+    else if (i < H - n_cmd) v = hist[i + n_cmd];                                  // np.roll(history, -n_cmd)
+    else { const int j = i - (H - n_cmd); v = action ? action[j] : (j == 0 ? a0 : a1); }      // history[-n_cmd:] = action
+    nh[i] = v;
+  }
+  for (int i = threadIdx.x; i < S; i += blockDim.x) prev[i] = stack[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    float v;
+    if (i >= S - F) { const int j = i - (S - F); v = j < z ? latent[j] : nh[j - z]; }          // newest frame = [latent | history]
+    else v = (reset || done) ? 0.f : prev[i + F];                                 // np.roll(stack, -F); zeroed on reset / done
+    ns[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) hist[i] = nh[i];
+  for (int i = threadIdx.x; i < S; i += blockDim.x) stack[i] = ns[i];
+  if (threadIdx.x < n_cmd && act_out) act_out[threadIdx.x] = action ? action[threadIdx.x] : (threadIdx.x == 0 ? a0 : a1);
+  if (threadIdx.x == 0 && rd_out) { rd_out[0] = reward; rd_out[1] = done ? 1.f : 0.f; }
+}
+
 // external batch -> the arena's batch buffers (staged API): X_sa=[s|a], X_pi=[s|.], X_s2=[s2|.], r, d
 __global__ void load_batch_kernel(float* __restrict__ base, i64 x_sa, i64 x_s2, i64 x_pi, i64 r_off, i64 d_off, int ldx,
                                   int O, int A, int B, const float* __restrict__ s, const float* __restrict__ a,

@@ -85,6 +85,11 @@ SYMBOLS = {
     "sacx_ring_gather_host": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "sacx_ring_resync": (C.c_int, [_P]),
     "sacx_ring_sample_indices": (C.c_int, [_P, _I32, _U64, _U64, _I32, _P]),
+    "sacx_obs_create": (C.c_int, [_I32, _I32, _I32, _I32, C.POINTER(_P)]),
+    "sacx_obs_destroy": (C.c_int, [_P]),
+    "sacx_obs_dim": (_I32, [_P]),
+    "sacx_obs_reset": (C.c_int, [_P, _P, _P, _P]),
+    "sacx_obs_step": (C.c_int, [_P, _P, _P, _P, _F, _I32, _P, _I32, _P, _P]),
     "sacx_agent_arena_floats": (C.c_int, [C.POINTER(SacxConfig), C.POINTER(_I64)]),
     "sacx_agent_create": (C.c_int, [C.POINTER(SacxConfig), _P, C.POINTER(_P)]),
     "sacx_agent_destroy": (C.c_int, [_P]),
