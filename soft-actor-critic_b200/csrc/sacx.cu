@@ -26,7 +26,8 @@ constexpr int STAGE_ROWS = 4096;
 struct Ring {
   int O, A, n_agents, W;
   i64 cap, stride;                      // float words per agent block
-  i64 off_s, off_a, off_r, off_s2, off_d;
+  i64 off_s, off_a, off_r, off_s2, off_d;   // field offsets inside a packed record, ring header included
+  int RS = 0;                           // floats per record
   float* dev = nullptr;
   bool own = false;
   float* h_rows = nullptr;              // pinned staging [STAGE_ROWS, W]
@@ -44,14 +45,12 @@ struct Ring {
   void* scr_host = nullptr; size_t scr_host_bytes = 0;
   long long launches = 0;
 
+  // packed records [s | s2 | a | r | d | pad], RS = align4(2O + A + 2) floats each, behind the 32-byte ring header
+  static int record_floats(int O, int A) { return (2 * O + A + 2 + 3) & ~3; }
   static void offsets(int O, int A, i64 cap, i64& s, i64& a, i64& r, i64& s2, i64& d, i64& total) {
-    i64 c = (i64)(sizeof(RingMeta) / 4);
-    s = c; c = align4(c + cap * O);
-    a = c; c = align4(c + cap * A);
-    r = c; c = align4(c + cap);
-    s2 = c; c = align4(c + cap * O);
-    d = c; c = align4(c + cap);
-    total = (c + 127) & ~(i64)127;
+    const i64 hdr = (i64)(sizeof(RingMeta) / 4);
+    s = hdr; s2 = hdr + O; a = hdr + 2 * O; r = hdr + 2 * O + A; d = r + 1;
+    total = (hdr + cap * record_floats(O, A) + 127) & ~(i64)127;
   }
   i64 len(int agent) const { return std::min(pushes[agent], cap); }
   float* block(int agent) const { return dev + (i64)agent * stride; }
@@ -67,7 +66,7 @@ struct Ring {
     if (staged == 0) return SACX_OK;
     SACX_CUDA(cudaMemcpyAsync(d_rows, h_rows, (size_t)staged * W * sizeof(float), cudaMemcpyHostToDevice, stream));
     SACX_CUDA(cudaMemcpyAsync(d_hdr, h_hdr, (size_t)staged * sizeof(StageHdr), cudaMemcpyHostToDevice, stream));
-    ring_scatter_kernel<<<(staged + 7) / 8, 256, 0, stream>>>(dev, stride, cap, off_s, off_a, off_r, off_s2, off_d, O, A,
+    ring_scatter_kernel<<<(staged + 7) / 8, 256, 0, stream>>>(dev, stride, cap, off_s, off_a, off_r, off_s2, off_d, RS, O, A,
                                                               d_rows, d_hdr, staged);
     ++launches;
     SACX_CUDA(cudaGetLastError());
@@ -114,7 +113,7 @@ static int engine_launch(Engine* e, int plan_id, int pb, int pe, int n_steps, co
   if (e->ring) {
     Ring* r = e->ring;
     a.ring = r->dev; a.ring_stride = r->stride; a.ring_capacity = r->cap;
-    a.ring_s = r->off_s; a.ring_a = r->off_a; a.ring_r = r->off_r; a.ring_s2 = r->off_s2; a.ring_d = r->off_d;
+    a.ring_s = r->off_s; a.ring_a = r->off_a; a.ring_r = r->off_r; a.ring_s2 = r->off_s2; a.ring_d = r->off_d; a.ring_rs = r->RS;
   }
   const Plan* dplan = e->d_plans + plan_id;
   auto launch = [&](int p0, int p1, int steps, dim3 grid, bool coop) -> int {
@@ -223,7 +222,7 @@ static int engine_launch_rp(Engine* e, int n_steps, const RunArgs& proto) {
   if (e->ring) {
     Ring* r = e->ring;
     a.ring = r->dev; a.ring_stride = r->stride; a.ring_capacity = r->cap;
-    a.ring_s = r->off_s; a.ring_a = r->off_a; a.ring_r = r->off_r; a.ring_s2 = r->off_s2; a.ring_d = r->off_d;
+    a.ring_s = r->off_s; a.ring_a = r->off_a; a.ring_r = r->off_r; a.ring_s2 = r->off_s2; a.ring_d = r->off_d; a.ring_rs = r->RS;
   }
   a.rp_part = e->d_rp_part;
   a.rp_maps = e->d_rp_maps;
@@ -543,6 +542,7 @@ int sacx_ring_create(int32_t O, int32_t A, int64_t cap, int32_t n_agents, void* 
   r.O = O; r.A = A; r.cap = cap; r.n_agents = n_agents; r.W = 2 * O + A + 2;
   i64 total;
   Ring::offsets(O, A, cap, r.off_s, r.off_a, r.off_r, r.off_s2, r.off_d, total);
+  r.RS = Ring::record_floats(O, A);
   r.stride = total;
   r.pushes.assign(n_agents, 0);
   r.stage_limit = (int)std::min<i64>(STAGE_ROWS, cap);
@@ -621,7 +621,7 @@ int sacx_ring_push_n_dev(sacx_ring_t h, int32_t agent, int64_t n, const float* s
   int rc = r.flush();
   if (rc) return rc;
   ring_scatter_dev_kernel<<<(unsigned)((n + 7) / 8), 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2,
-                                                                         r.off_d, r.O, r.A, s, a, reward, s2, done, r.pushes[agent], (int)n);
+                                                                         r.off_d, r.RS, r.O, r.A, s, a, reward, s2, done, r.pushes[agent], (int)n);
   ++r.launches;
   SACX_CUDA(cudaGetLastError());
   r.pushes[agent] += n;
@@ -666,17 +666,16 @@ int sacx_ring_gather(sacx_ring_t h, int32_t agent, const int64_t* idx_dev, int32
   int rc = r.flush();
   if (rc) return rc;
   auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
-  const bool vec = (r.O % 4 == 0) && (r.A % 4 == 0) && (r.off_s % 4 == 0) && (r.off_s2 % 4 == 0) && (r.off_a % 4 == 0) && al16(r.block(agent)) &&
-                   al16(s) && al16(s2) && al16(a) && 2 * (r.O / 4) + r.A / 4 + 2 <= 256;
+  const bool vec = (r.O % 4 == 0) && (r.A % 4 == 0) && al16(r.block(agent)) && al16(s) && al16(s2) && al16(a) && r.RS / 4 <= 256;
   if (vec) {
-    const int pieces = 2 * (r.O / 4) + r.A / 4 + 2;
+    const int pieces = r.RS / 4;                // 16-byte pieces of a packed record (the last one holds r, d)
     int tl = 0;
     while ((1 << tl) < pieces) ++tl;
     const i64 threads = (i64)B << tl;
     ring_gather_vec_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2,
-                                                                                    r.off_d, r.O, r.A, (const i64*)idx_dev, B, s, a, rr, s2, d, tl);
+                                                                                    r.off_d, r.RS, r.O, r.A, (const i64*)idx_dev, B, s, a, rr, s2, d, tl);
   } else {
-    ring_gather_kernel<<<(B + 7) / 8, 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2, r.off_d, r.O, r.A,
+    ring_gather_kernel<<<(B + 7) / 8, 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2, r.off_d, r.RS, r.O, r.A,
                                                           (const i64*)idx_dev, B, s, a, rr, s2, d);
   }
   ++r.launches;

@@ -302,9 +302,15 @@ struct StageHdr {
   i64 push_no;
 };
 
-// staged AoS rows [s | a | r | s2 | d] -> SoA ring slots (push_no % capacity); bumps the agent's push count
+// Ring layout: one PACKED record per slot, [s (O) | s2 (O) | a (A) | r | d | pad] = RS floats (RS = 2O + A + 2 rounded up to a
+// multiple of 4, so records start 16-byte aligned; BipedalWalker: 56 floats = 224 B = seven 32-byte sectors). A sampled
+// transition is one contiguous read instead of five pieces in five arrays: the round-1 SoA ring moved 2.9x the algorithmic
+// bytes from DRAM on a 1M-row gather (every piece cost its own 64-byte granules). Field f of slot k lives at
+// rb[off_f + k * RS + i]; off_* are the field offsets inside the record plus the ring header.
+
+// staged host rows [s | a | r | s2 | d] -> ring records (slot = push_no % capacity); bumps the agent's push count
 __global__ void ring_scatter_kernel(float* __restrict__ ring, i64 ring_stride, i64 cap, i64 off_s, i64 off_a, i64 off_r,
-                                    i64 off_s2, i64 off_d, int O, int A, const float* __restrict__ rows,
+                                    i64 off_s2, i64 off_d, int RS, int O, int A, const float* __restrict__ rows,
                                     const StageHdr* __restrict__ hdr, int n) {
   const int W = 2 * O + A + 2;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -312,16 +318,16 @@ __global__ void ring_scatter_kernel(float* __restrict__ ring, i64 ring_stride, i
   if (row >= n) return;
   const StageHdr h = hdr[row];
   float* rb = ring + (i64)h.agent * ring_stride;
-  const i64 slot = h.push_no % cap;
+  float* rec = rb + (h.push_no % cap) * RS;
   const float* src = rows + (i64)row * W;
   for (int k = lane; k < O; k += 32) {
-    rb[off_s + slot * O + k] = src[k];
-    rb[off_s2 + slot * O + k] = src[O + A + 1 + k];
+    rec[off_s + k] = src[k];
+    rec[off_s2 + k] = src[O + A + 1 + k];
   }
-  for (int k = lane; k < A; k += 32) rb[off_a + slot * A + k] = src[O + k];
+  for (int k = lane; k < A; k += 32) rec[off_a + k] = src[O + k];
   if (lane == 0) {
-    rb[off_r + slot] = src[O + A];
-    rb[off_d + slot] = src[2 * O + A + 1];
+    rec[off_r] = src[O + A];
+    rec[off_d] = src[2 * O + A + 1];
     atomicMax(reinterpret_cast<unsigned long long*>(&reinterpret_cast<RingMeta*>(rb)->pushes),
               (unsigned long long)(h.push_no + 1));
   }
@@ -329,31 +335,31 @@ __global__ void ring_scatter_kernel(float* __restrict__ ring, i64 ring_stride, i
 
 // rows already on the device (SoA inputs) for one agent
 __global__ void ring_scatter_dev_kernel(float* __restrict__ rb, i64 cap, i64 off_s, i64 off_a, i64 off_r, i64 off_s2,
-                                        i64 off_d, int O, int A, const float* __restrict__ s, const float* __restrict__ a,
+                                        i64 off_d, int RS, int O, int A, const float* __restrict__ s, const float* __restrict__ a,
                                         const float* __restrict__ r, const float* __restrict__ s2,
                                         const float* __restrict__ d, i64 push0, int n) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
-  const i64 slot = (push0 + row) % cap;
+  float* rec = rb + ((push0 + row) % cap) * RS;
   for (int k = lane; k < O; k += 32) {
-    rb[off_s + slot * O + k] = s[(i64)row * O + k];
-    rb[off_s2 + slot * O + k] = s2[(i64)row * O + k];
+    rec[off_s + k] = s[(i64)row * O + k];
+    rec[off_s2 + k] = s2[(i64)row * O + k];
   }
-  for (int k = lane; k < A; k += 32) rb[off_a + slot * A + k] = a[(i64)row * A + k];
+  for (int k = lane; k < A; k += 32) rec[off_a + k] = a[(i64)row * A + k];
   if (lane == 0) {
-    rb[off_r + slot] = r[row];
-    rb[off_d + slot] = d[row];
+    rec[off_r] = r[row];
+    rec[off_d] = d[row];
     if (row == n - 1)
       atomicMax(reinterpret_cast<unsigned long long*>(&reinterpret_cast<RingMeta*>(rb)->pushes),
                 (unsigned long long)(push0 + n));
   }
 }
 
-// uniform-index gather: one warp per sampled row; logical deque position -> ring slot.
+// uniform-index gather, any dimensions: one warp per sampled row; logical deque position -> ring slot.
 // Streaming loads (ld.global.cs): every row is touched once per update and the 1M-row ring does not fit L2.
 __global__ void ring_gather_kernel(const float* __restrict__ rb, i64 cap, i64 off_s, i64 off_a, i64 off_r, i64 off_s2,
-                                   i64 off_d, int O, int A, const i64* __restrict__ idx, int B, float* __restrict__ s,
+                                   i64 off_d, int RS, int O, int A, const i64* __restrict__ idx, int B, float* __restrict__ s,
                                    float* __restrict__ a, float* __restrict__ r, float* __restrict__ s2,
                                    float* __restrict__ d) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -361,42 +367,45 @@ __global__ void ring_gather_kernel(const float* __restrict__ rb, i64 cap, i64 of
   if (row >= B) return;
   const i64 pushes = reinterpret_cast<const RingMeta*>(rb)->pushes;
   const i64 oldest = pushes > cap ? pushes - cap : 0;
-  const i64 slot = (oldest + idx[row]) % cap;
-  if (s) for (int k = lane; k < O; k += 32) s[(i64)row * O + k] = __ldcs(rb + off_s + slot * O + k);
-  if (s2) for (int k = lane; k < O; k += 32) s2[(i64)row * O + k] = __ldcs(rb + off_s2 + slot * O + k);
-  if (a) for (int k = lane; k < A; k += 32) a[(i64)row * A + k] = __ldcs(rb + off_a + slot * A + k);
+  const i64 j = idx[row];
+  const bool in = j >= 0 && j < (pushes < cap ? pushes : cap);          // a position outside the deque reads nothing: zero row
+  const float* rec = rb + ((oldest + (in ? j : 0)) % cap) * RS;
+  if (s) for (int k = lane; k < O; k += 32) s[(i64)row * O + k] = in ? __ldcs(rec + off_s + k) : 0.f;
+  if (s2) for (int k = lane; k < O; k += 32) s2[(i64)row * O + k] = in ? __ldcs(rec + off_s2 + k) : 0.f;
+  if (a) for (int k = lane; k < A; k += 32) a[(i64)row * A + k] = in ? __ldcs(rec + off_a + k) : 0.f;
   if (lane == 0) {
-    if (r) r[row] = __ldcs(rb + off_r + slot);
-    if (d) d[row] = __ldcs(rb + off_d + slot);
+    if (r) r[row] = in ? __ldcs(rec + off_r) : 0.f;
+    if (d) d[row] = in ? __ldcs(rec + off_d) : 0.f;
   }
 }
 
-// The same gather with one THREAD per 16-byte piece of a row instead of one warp per row (obs and act dimensions multiples
-// of 4, 16-byte aligned fields): a BipedalWalker row is 6 + 6 + 1 pieces + r + d = 15 -> 16 threads, two rows per warp, every
-// load of a row in flight at once. The warp-per-row kernel above issued five load instructions with 24 / 24 / 4 / 1 / 1
-// active lanes and reached 0.35 TB/s (read + write) on 1M rows (tools/gather_bench.py, profiles/).
+// The same gather with one THREAD per 16-byte piece of the record (obs and act dimensions multiples of 4): a BipedalWalker
+// record is 14 pieces -> 16 threads, two rows per warp, the whole record in flight at once and read as consecutive sectors.
+// Piece p of the record holds 4 floats of s (p < O/4), of s2, of a, or the (r, d, pad, pad) tail.
 __global__ void ring_gather_vec_kernel(const float* __restrict__ rb, i64 cap, i64 off_s, i64 off_a, i64 off_r, i64 off_s2,
-                                       i64 off_d, int O, int A, const i64* __restrict__ idx, int B, float* __restrict__ s,
+                                       i64 off_d, int RS, int O, int A, const i64* __restrict__ idx, int B, float* __restrict__ s,
                                        float* __restrict__ a, float* __restrict__ r, float* __restrict__ s2,
                                        float* __restrict__ d, int tpr_log2) {
   const i64 gt = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const int row = (int)(gt >> tpr_log2), piece = (int)(gt & ((1 << tpr_log2) - 1));
   if (row >= B) return;
   const int cs = O >> 2, ca = A >> 2;
-  if (piece >= 2 * cs + ca + 2) return;
+  if (piece > 2 * cs + ca) return;
   const i64 pushes = reinterpret_cast<const RingMeta*>(rb)->pushes;
   const i64 oldest = pushes > cap ? pushes - cap : 0;
-  const i64 slot = (oldest + __ldg(idx + row)) % cap;
+  const i64 j = __ldg(idx + row);
+  const bool in = j >= 0 && j < (pushes < cap ? pushes : cap);          // a position outside the deque reads nothing: zero row
+  const float* rec = rb + off_s + ((oldest + (in ? j : 0)) % cap) * RS;           // off_s: first field of the record
+  const float4 v = in ? __ldcs(reinterpret_cast<const float4*>(rec) + piece) : make_float4(0.f, 0.f, 0.f, 0.f);
   if (piece < cs) {
-    if (s) reinterpret_cast<float4*>(s + (i64)row * O)[piece] = __ldcs(reinterpret_cast<const float4*>(rb + off_s + slot * O) + piece);
+    if (s) reinterpret_cast<float4*>(s + (i64)row * O)[piece] = v;
   } else if (piece < 2 * cs) {
-    if (s2) reinterpret_cast<float4*>(s2 + (i64)row * O)[piece - cs] = __ldcs(reinterpret_cast<const float4*>(rb + off_s2 + slot * O) + piece - cs);
+    if (s2) reinterpret_cast<float4*>(s2 + (i64)row * O)[piece - cs] = v;
   } else if (piece < 2 * cs + ca) {
-    if (a) reinterpret_cast<float4*>(a + (i64)row * A)[piece - 2 * cs] = __ldcs(reinterpret_cast<const float4*>(rb + off_a + slot * A) + piece - 2 * cs);
-  } else if (piece == 2 * cs + ca) {
-    if (r) r[row] = __ldcs(rb + off_r + slot);
+    if (a) reinterpret_cast<float4*>(a + (i64)row * A)[piece - 2 * cs] = v;
   } else {
-    if (d) d[row] = __ldcs(rb + off_d + slot);
+    if (r) r[row] = v.x;
+    if (d) d[row] = v.y;
   }
 }
 

@@ -109,8 +109,9 @@ __device__ __forceinline__ void op_gather(const Op& op, const RowCtx& c, int row
   float* base = c.base;
   const int O = hp.obs, A = hp.act, ldx = op.i[0];
   if (lane == 0) reinterpret_cast<i64*>(base + op.o[5])[row] = j;
-  const float* rs = ring + a.ring_s + slot * O;
-  const float* rs2 = ring + a.ring_s2 + slot * O;
+  const float* rec = ring + slot * a.ring_rs;            // packed record [s | s2 | a | r | d]
+  const float* rs = rec + a.ring_s;
+  const float* rs2 = rec + a.ring_s2;
   float* xsa = base + op.o[0] + (i64)row * ldx;
   float* xs2 = base + op.o[1] + (i64)row * ldx;
   float* xpi = base + op.o[2] + (i64)row * ldx;
@@ -120,11 +121,11 @@ __device__ __forceinline__ void op_gather(const Op& op, const RowCtx& c, int row
     xpi[k] = v;
     xs2[k] = __ldcs(rs2 + k);
   }
-  const float* ra = ring + a.ring_a + slot * A;
+  const float* ra = rec + a.ring_a;
   for (int k = lane; k < A; k += 32) xsa[O + k] = __ldcs(ra + k);
   if (lane == 0) {
-    base[op.o[3] + row] = __ldcs(ring + a.ring_r + slot);
-    base[op.o[4] + row] = __ldcs(ring + a.ring_d + slot);
+    base[op.o[3] + row] = __ldcs(rec + a.ring_r);
+    base[op.o[4] + row] = __ldcs(rec + a.ring_d);
   }
 }
 

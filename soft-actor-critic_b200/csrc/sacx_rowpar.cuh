@@ -96,6 +96,8 @@ struct RpCtx {
   int rank, step, row0;
   RpTrace* tr;
   uint64_t* wbar;         // one mbarrier per weight slot (TMA-staged slices)
+  const struct RpLaunch* L;   // per-launch constants (push count, stream keys, update counter at launch)
+  i64* slots;             // ring slots of the current row block's rows (shared memory)
 };
 
 #define RP_SMEM extern __shared__ __align__(1024) float rp_dyn_smem[]; float* const smem_raw = rp_dyn_smem
@@ -458,107 +460,102 @@ __device__ __forceinline__ float rp_sum8(float v) {     // sum over the 8 lanes 
 }
 
 // ---- row ops --------------------------------------------------------------------------------------------------------
-// ring rows -> the three input buffers (a2/a3), the update's normals; rank 0 mirrors the batch into the arena.
-// Warp w owns rows 2w and 2w+1; all ring loads of a thread are in flight before the first is used.
-__device__ __noinline__ void rp_gather(const RpCtx& c) {
+// ring records -> the three input buffers (a2/a3), the update's normals; rank 0 mirrors the batch into the arena.
+// Warp 0 turns the 16 rows' logical indices into ring slots (host index stream, or the keyed Feistel bijection) while warps
+// 1-7 draw the update's 2 x 16 x A normals (one Philox call per thread); then every thread pulls its share of the 16 packed
+// records [s | s2 | a | r | d] -- consecutive threads read consecutive floats of a record -- with all its loads in flight
+// before the first is used. Per-launch constants (push count, stream keys, update counter at launch) come from RpLaunch.
+struct RpLaunch { i64 pushes, upd0, oldest_slot; unsigned long long rng_seed; unsigned rng_agent, pad; };
+
+__device__ __noinline__ void rp_gather(const RpCtx& c, const RpLaunch& L, i64* __restrict__ slots) {
   RP_SMEM;
   const RunArgs& a = *c.args;
   const Hyper& hp = a.hp;
   const RpProgram& P = *c.P;
   RpRows& R = *c.R;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, O = P.O, A = P.A, ldx = P.ldx, B = hp.B;
+  const int tid = threadIdx.x, O = P.O, A = P.A, ldx = P.ldx, B = hp.B;
   const float* __restrict__ ring = a.ring;
   const i64 cap = a.ring_capacity;
   float* xsa = smem_raw + P.sm_xbuf, *xs2 = xsa + RP_RB * ldx, *xpi = xs2 + RP_RB * ldx;
   const bool w0 = c.rank == 0;
-  // lanes 0 / 1: ring slot of rows 2w / 2w+1
-  i64 myslot = -1;
-  if (lane < 2) {
-    const int row = c.row0 + 2 * warp + lane;
+  const unsigned long long upd = (unsigned long long)(L.upd0 + c.step);
+  if (tid < RP_RB) {
+    const int row = c.row0 + tid;
+    i64 slot = -1;
     if (row < B) {
-      const i64 pushes = reinterpret_cast<const RingMeta*>(ring)->pushes;
-      const i64 n = pushes < cap ? pushes : cap;
+      const i64 n = L.pushes < cap ? L.pushes : cap;
       i64 j;
       if (a.idx_ext) j = a.idx_ext[(i64)c.step * hp.B + row];
-      else j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, __ldcg(&c.scal->rng_seed),
-                                  (unsigned long long)__ldcg(&c.scal->updates), __ldcg(&c.scal->rng_agent));
-      const i64 oldest = pushes > cap ? pushes - cap : 0;
-      myslot = (oldest + j) % cap;
+      else j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, L.rng_seed, upd, L.rng_agent);
+      slot = L.oldest_slot + j;                      // slot of the oldest survivor (computed once per launch) + logical position
+      if (slot >= cap) slot -= cap;                  // both < cap: one conditional subtraction replaces the 64-bit modulo
       if (w0) reinterpret_cast<i64*>(c.base + P.b_idx)[row] = j;
     }
+    slots[tid] = slot;
+  } else if (tid >= 32) {
+    // normals: element i = (which, row of the block, action dim); lanes with dim >= A idle
+    for (int i = tid - 32; i < 2 * RP_RB * RP_MAXA; i += 224) {
+      const int which = i >> 7, mm = (i >> 3) & (RP_RB - 1), j = i & (RP_MAXA - 1), row = c.row0 + mm;
+      float e = 0.f;
+      if (row < B && j < A) {
+        const float* ext = which ? a.eps2_ext : a.eps1_ext;
+        if (ext) e = ext[((i64)c.step * hp.B + row) * A + j];
+        else e = philox_normal(L.rng_seed, upd, 1 + which, (uint32_t)(hp.row0_global + row), (uint32_t)j, L.rng_agent);
+        if (w0) c.base[(which ? P.b_eps2 : P.b_eps1) + (i64)row * A + j] = e;
+      }
+      if (which) R.eps2[mm][j] = e; else R.eps1[mm][j] = e;
+    }
   }
-  const i64 slot0 = __shfl_sync(0xffffffffu, myslot, 0), slot1 = __shfl_sync(0xffffffffu, myslot, 1);
-  // ring loads: per row 2O + A + 2 floats; lane covers columns lane, lane + 32, ...
-  const int W = 2 * O + A + 2;
-  constexpr int MAXC = 8;                 // columns per lane per row (W <= 256)
-  float v0[MAXC], v1[MAXC];
+  RP_TRACE(2100);
+  __syncthreads();
+  // the 16 records: element e = (row, column of the record); W = 2O + A + 2 <= 256 -> at most 16 elements per thread
+  const int W = 2 * O + A + 2, total = RP_RB * W;
+  constexpr int MAXE = 16;
+  float v[MAXE];
 #pragma unroll
-  for (int u = 0; u < MAXC; ++u) {
-    const int col = lane + 32 * u;
-    v0[u] = 0.f; v1[u] = 0.f;
-    if (col < W) {
-      i64 off;            // field offset of this column for slot s: off + s * stride
-      int stride;
-      if (col < O) { off = a.ring_s + col; stride = O; }
-      else if (col < O + A) { off = a.ring_a + (col - O); stride = A; }
-      else if (col < 2 * O + A) { off = a.ring_s2 + (col - O - A); stride = O; }
-      else if (col == 2 * O + A) { off = a.ring_r; stride = 1; }
-      else { off = a.ring_d; stride = 1; }
-      if (slot0 >= 0) v0[u] = __ldcs(ring + off + slot0 * stride);
-      if (slot1 >= 0) v1[u] = __ldcs(ring + off + slot1 * stride);
+  for (int u = 0; u < MAXE; ++u) {
+    const int e = tid + 256 * u;
+    v[u] = 0.f;
+    if (e < total) {
+      const int mm = e / W, col = e - mm * W;
+      const i64 slot = slots[mm];
+      if (slot >= 0) v[u] = __ldcs(ring + a.ring_s + slot * a.ring_rs + col);      // record = [s | s2 | a | r | d]: ring_s is its first field
     }
   }
-  // normals of the update (lanes 16..31: row 2w + (l >> 3), action dim l & 7) while the ring rows travel
-  if (lane >= 16) {
-    const int l = lane - 16, mm = 2 * warp + (l >> 3), j = l & 7, row = c.row0 + mm;
-    float e1 = 0.f, e2 = 0.f;
-    if (row < B && j < A) {
-      if (a.eps1_ext) e1 = a.eps1_ext[((i64)c.step * hp.B + row) * A + j];
-      else e1 = philox_normal(__ldcg(&c.scal->rng_seed), (unsigned long long)__ldcg(&c.scal->updates), 1, (uint32_t)(hp.row0_global + row), (uint32_t)j, __ldcg(&c.scal->rng_agent));
-      if (a.eps2_ext) e2 = a.eps2_ext[((i64)c.step * hp.B + row) * A + j];
-      else e2 = philox_normal(__ldcg(&c.scal->rng_seed), (unsigned long long)__ldcg(&c.scal->updates), 2, (uint32_t)(hp.row0_global + row), (uint32_t)j, __ldcg(&c.scal->rng_agent));
-      if (w0) { c.base[P.b_eps1 + (i64)row * A + j] = e1; c.base[P.b_eps2 + (i64)row * A + j] = e2; }
-    }
-    R.eps1[mm][j] = e1; R.eps2[mm][j] = e2;
-  }
+  RP_TRACE(2101);
   // padding columns (finite zeros: they meet zero-padded weights in the K loop)
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int mm = 2 * warp + h;
-    for (int col = O + lane; col < ldx; col += 32) {
-      if (col >= O + A) xsa[mm * ldx + col] = 0.f;
-      xs2[mm * ldx + col] = 0.f; xpi[mm * ldx + col] = 0.f;
-    }
+  for (int i = tid; i < RP_RB * (ldx - O); i += 256) {
+    const int mm = i / (ldx - O), col = O + i - mm * (ldx - O);
+    if (col >= O + A) xsa[mm * ldx + col] = 0.f;
+    xs2[mm * ldx + col] = 0.f; xpi[mm * ldx + col] = 0.f;
   }
+  RP_TRACE(2102);
 #pragma unroll
-  for (int u = 0; u < MAXC; ++u) {
-    const int col = lane + 32 * u;
-    if (col < W) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int mm = 2 * warp + h, row = c.row0 + mm;
-        const float v = h ? v1[u] : v0[u];
-        const bool ok = (h ? slot1 : slot0) >= 0;
-        if (col < O) {
-          xsa[mm * ldx + col] = v; xpi[mm * ldx + col] = v;
-          if (w0 && ok) { c.base[P.x_sa + (i64)row * P.gldx + col] = v; c.base[P.x_pi + (i64)row * P.gldx + col] = v; }
-        } else if (col < O + A) {
-          xsa[mm * ldx + col] = v;
-          if (w0 && ok) c.base[P.x_sa + (i64)row * P.gldx + col] = v;
-        } else if (col < 2 * O + A) {
-          const int k = col - O - A;
-          xs2[mm * ldx + k] = v;
-          if (w0 && ok) c.base[P.x_s2 + (i64)row * P.gldx + k] = v;
-        } else if (col == 2 * O + A) {
-          R.r[mm] = v;
-          if (w0 && ok) c.base[P.b_r + row] = v;
-        } else {
-          R.d[mm] = v;
-          if (w0 && ok) c.base[P.b_d + row] = v;
-        }
+  for (int u = 0; u < MAXE; ++u) {
+    const int e = tid + 256 * u;
+    if (e < total) {
+      const int mm = e / W, col = e - mm * W, row = c.row0 + mm;
+      const bool ok = w0 && slots[mm] >= 0;
+      const float x = v[u];
+      if (col < O) {
+        xsa[mm * ldx + col] = x; xpi[mm * ldx + col] = x;
+        if (ok) { c.base[P.x_sa + (i64)row * P.gldx + col] = x; c.base[P.x_pi + (i64)row * P.gldx + col] = x; }
+      } else if (col < 2 * O) {
+        xs2[mm * ldx + col - O] = x;
+        if (ok) c.base[P.x_s2 + (i64)row * P.gldx + col - O] = x;
+      } else if (col < 2 * O + A) {
+        xsa[mm * ldx + col - O] = x;                       // action columns sit behind the state in X_sa
+        if (ok) c.base[P.x_sa + (i64)row * P.gldx + col - O] = x;
+      } else if (col == 2 * O + A) {
+        R.r[mm] = x;
+        if (ok) c.base[P.b_r + row] = x;
+      } else {
+        R.d[mm] = x;
+        if (ok) c.base[P.b_d + row] = x;
       }
     }
   }
+  RP_TRACE(2103);
   __syncthreads();
 }
 
@@ -835,6 +832,8 @@ struct RpSync {            // barrier state that lives across phases and updates
   unsigned wphase;         // parity bit per weight slot (TMA mbarriers)
 };
 
+// (forceinline on purpose: a single out-of-line copy shared by phases A and C measured 19% SLOWER -- 158.6 vs 133.8 us per
+//  update -- although it shrinks the kernel from 389 KB to 276 KB of SASS: the instruction footprint is not what limits it)
 __device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, RpSync& sy) {
   RP_SMEM;
   const RpProgram& P = *c.P;
@@ -857,7 +856,7 @@ __device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, RpS
     }
     RP_TRACE(2000 + st.row_op);
     switch (st.row_op) {
-      case RPR_GATHER: rp_gather(c); break;
+      case RPR_GATHER: rp_gather(c, *c.L, c.slots); break;
       case RPR_PI_HEADS: rp_pi_heads(c); break;
       case RPR_TARGET_CRITIC: rp_target_critic(c); break;
       case RPR_RELOAD: rp_reload(c); break;
@@ -900,6 +899,8 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   __shared__ Phase sphase[2];
   __shared__ RpTrace trace;
   __shared__ __align__(8) uint64_t wbar[RP_NWSLOT];
+  __shared__ RpLaunch launch;
+  __shared__ i64 row_slots[RP_RB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < RP_NWSLOT; ++i) rp_mbar_init(&wbar[i], 8);      // one arrival per warp and job
@@ -915,14 +916,21 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
     int* odst = reinterpret_cast<int*>(sops);
     for (int i = tid; i < nops * (int)(sizeof(Op) / 4); i += 256) odst[i] = osrc[i];
     if (tid < 2) sphase[tid] = gplan->phases[tid];
-    if (tid == 0) { trace.buf = nullptr; trace.n = 0; trace.cap = 0; }
+    if (tid == 0) {
+      trace.buf = nullptr; trace.n = 0; trace.cap = 0;
+      // constant for the whole launch: nothing pushes into the ring or touches the stream keys while the kernel runs
+      const AgentScalars* sc = reinterpret_cast<const AgentScalars*>(args.arena + args.scal_off);
+      launch.pushes = args.ring ? reinterpret_cast<const RingMeta*>(args.ring)->pushes : 0;
+      launch.upd0 = sc->updates; launch.rng_seed = sc->rng_seed; launch.rng_agent = sc->rng_agent; launch.pad = 0;
+      launch.oldest_slot = launch.pushes > args.ring_capacity ? (launch.pushes - args.ring_capacity) % args.ring_capacity : 0;
+    }
   }
   __syncthreads();
   const int rank = blockIdx.x % RP_CS, gid = blockIdx.x / RP_CS, ngr = gridDim.x / RP_CS;
   float* base = args.arena;
   AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
   const int B = args.hp.B, nrb = (B + RP_RB - 1) / RP_RB;
-  RpCtx c{base, scal, &args, &sprog, &rows, args.rp_part + (i64)gid * sprog.part_stride, args.barrier + 64 * (1 + gid), rank, 0, 0, &trace, wbar};
+  RpCtx c{base, scal, &args, &sprog, &rows, args.rp_part + (i64)gid * sprog.part_stride, args.barrier + 64 * (1 + gid), rank, 0, 0, &trace, wbar, &launch, row_slots};
   // dW phases reuse the tile code of the tile-parallel kernel; their shared memory aliases the row-parallel buffers
   float* wsm = smem_raw;
   float* gsm = smem_raw + WSM_FLOATS;
@@ -953,7 +961,7 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
           while (oi + 1 < p.op0 + p.nops && t >= sops[oi + 1].tile0) ++oi;
           const Op& op = sops[oi];
           const int lt = t - op.tile0;
-          if (op.type == OP_GEMM) gemm_tile<CfgSmall>(op, ec, lt, gsm);
+          if (op.type == OP_GEMM) gemm_tile_impl<CfgSmall, 2>(op, ec, lt, gsm);      // only dW tiles live in these phases
           else if (op.type == OP_FINAL) { if (warp == 0) op_final(op, rc, lane); }
         }
       }

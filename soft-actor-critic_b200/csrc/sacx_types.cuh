@@ -107,7 +107,8 @@ struct RunArgs {
   i64 ring_stride;           // float words per agent ring block
   i64 ring_capacity;
   // ring field offsets (float words from the agent's ring block)
-  i64 ring_s, ring_a, ring_r, ring_s2, ring_d;
+  i64 ring_s, ring_a, ring_r, ring_s2, ring_d;   // field offsets inside a record (+ ring header): element i of field f of slot k = ring[f + k * ring_rs + i]
+  i64 ring_rs;               // floats per packed record [s | s2 | a | r | d | pad]
   const i64* idx_ext;        // [n_steps, n_agents, B] or null
   const float* eps1_ext;     // [n_steps, n_agents, B, A] or null
   const float* eps2_ext;

@@ -229,13 +229,16 @@ class ReplayBuffer:
         if indices is None:
             indices = self.draw_indices(batch_size, agent)
         if not torch.is_tensor(indices):
-            indices = torch.as_tensor(np.asarray(indices, dtype=np.int64))
+            host = np.asarray(indices, dtype=np.int64).reshape(-1)
+            if host.size and (host.min() < 0 or host.max() >= self.size(agent)):      # logical positions of the deque: [0, len)
+                raise ValueError("logical index out of range")
+            indices = torch.as_tensor(host)
+        # (a device tensor is not read back for validation -- that would put a sync into every gather; the kernels themselves
+        #  never read outside the ring: a position outside [0, len) yields a zero row)
         idx = indices.to(device=self.device, dtype=torch.int64).contiguous().reshape(-1)
         B = idx.shape[0]
         if B != batch_size:
             raise ValueError(f"{B} indices given for a batch of {batch_size}")
-        if B and (int(idx.min()) < 0 or int(idx.max()) >= self.size(agent)):      # logical positions of the deque: [0, len)
-            raise ValueError("logical index out of range")
         kw = dict(dtype=torch.float32, device=self.device)
         s, a = torch.empty(B, self.obs_dim, **kw), torch.empty(B, self.act_dim, **kw)
         r, s2, d = torch.empty(B, **kw), torch.empty(B, self.obs_dim, **kw), torch.empty(B, **kw)

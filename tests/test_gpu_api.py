@@ -291,3 +291,33 @@ def test_population_act_all_matches_per_agent_act():
         one = pop.engine.act(torch.as_tensor(states[ag:ag + 1]).cuda(), eps[ag], deterministic=False, agent=ag).cpu().numpy()[0]
         assert np.array_equal(sto[ag], one)
     assert np.all(np.abs(sto) <= 1.0) and not np.array_equal(det, sto)
+
+
+def test_gather_never_reads_outside_the_ring():
+    """Advisor finding (round 1): shapes of batched pushes are validated; host index lists are range-checked; a DEVICE index
+    tensor is not read back (no sync per gather) -- the kernels return a zero row for a position outside [0, len)."""
+    from sac.replay_buffer import ReplayBuffer
+    rb = ReplayBuffer(100, 8, 4)
+    n = 60
+    s = np.arange(n * 8, dtype=np.float32).reshape(n, 8) + 1
+    a = np.ones((n, 4), np.float32)
+    rb.push_batch(s, a, np.arange(n), s + 0.5, np.zeros(n))
+    with pytest.raises(ValueError):
+        rb.push_batch(s[:, :7], a, np.arange(n), s, np.zeros(n))              # wrong observation width
+    with pytest.raises(ValueError):
+        rb.push_batch(s, a, np.arange(n), s, np.zeros(n - 1))                 # one done flag short
+    with pytest.raises(ValueError):
+        rb.push_device(torch.zeros(4, 8).cuda(), torch.zeros(4, 3).cuda(), torch.zeros(4).cuda(), torch.zeros(4, 8).cuda(), torch.zeros(4).cuda())
+    with pytest.raises(ValueError, match="out of range"):
+        rb.sample_tensors(3, indices=[0, 5, 60])
+    with pytest.raises(ValueError, match="out of range"):
+        rb.sample_tensors(2, indices=[-1, 5])
+    idx = torch.tensor([3, -7, 59, 60, 10**12], dtype=torch.int64, device="cuda")
+    b = rb.sample_tensors(5, indices=idx)
+    got = b.state.cpu().numpy()
+    assert np.array_equal(got[0], s[3]) and np.array_equal(got[2], s[59])
+    assert not got[1].any() and not got[3].any() and not got[4].any() and b.reward.cpu().numpy()[3] == 0.0
+    odd = ReplayBuffer(50, 3, 2)                                             # dimensions that are not multiples of 4: scalar kernel
+    odd.push_batch(np.ones((10, 3), np.float32), np.ones((10, 2), np.float32), np.ones(10), np.ones((10, 3)), np.zeros(10))
+    bo = odd.sample_tensors(3, indices=torch.tensor([0, 10, -1], dtype=torch.int64, device="cuda"))
+    assert bo.state.cpu().numpy()[0].all() and not bo.state.cpu().numpy()[1:].any()

@@ -1,5 +1,5 @@
 """Replay-ring gather alone ("gather-only GB/s"): uniform-index gather of (s, a, r, s', done)
-from a 1M-transition BipedalWalker-shape ring (216 MB, SoA) through the C ABI (sacx_ring_gather), device indices.
+from a 1M-transition BipedalWalker-shape ring (224 MB of packed 224-byte records) through the C ABI (sacx_ring_gather), device indices.
    python tools/gather_bench.py            -> one JSON line per batch size; run on the GPU box."""
 import json
 import os
@@ -41,4 +41,4 @@ for B in (256, 4096, 65536, 1_000_000):
                       "algorithmic_read_bytes": alg, "read_GBps": round(alg / us / 1e3, 1),
                       "read_plus_write_GBps": round((2 * alg + 8 * B) / us / 1e3, 1), "hbm_peak_GBps": peak,
                       "frac_of_peak_rw": round((2 * alg + 8 * B) / us / 1e3 / peak, 4),
-                      "note": "rows are 96 B / 16 B / 4 B / 4 B pieces: ~9-10 32-byte sectors (288-320 B) fetched per 216 B row"}))
+                      "note": "packed records [s | s2 | a | r | d | pad]: 224 B = seven 32-byte sectors per 216 B row"}))
