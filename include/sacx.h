@@ -133,6 +133,10 @@ int sacx_ring_gather(sacx_ring_t r, int32_t agent, const int64_t* logical_idx_de
                      float* s_dev, float* a_dev, float* r_dev, float* s2_dev, float* d_dev);
 int sacx_ring_gather_host(sacx_ring_t r, int32_t agent, const int64_t* logical_idx_host, int32_t B,
                           float* s_host, float* a_host, float* r_host, float* s2_host, float* d_host);
+/* host helper of ReplayBuffer.sample's index stream (replay_buffer.py:39 -> random.sample -> _randbelow_with_getrandbits): applies
+ * the stdlib's accept/reject rule, in order, to `n_words` raw 32-bit Mersenne-Twister words fetched in bulk by the binding;
+ * appends to out[have..k), returns the new count (-1: bad arguments). No device involved. */
+int32_t sacx_index_filter(const uint32_t* words_host, int32_t n_words, uint64_t n, int32_t bits, int64_t* out_host, int32_t have, int32_t k);
 /* device index generation used by the throughput mode: B distinct logical positions in [0, n)
  * from a keyed Feistel bijection (exactly without replacement; not the MT19937 stream) */
 int sacx_ring_sample_indices(sacx_ring_t r, int32_t agent, uint64_t seed, uint64_t counter, int32_t B,

@@ -716,6 +716,34 @@ int sacx_ring_gather_host(sacx_ring_t h, int32_t agent, const int64_t* idx, int3
   return SACX_OK;
 }
 
+// Host helper of the reference-stream index draw (random.sample(range(n), k) on CPython's Mersenne Twister): the binding
+// fetches the generator's raw 32-bit words in bulk (random.getrandbits(32 * w)) and this routine applies the stdlib's
+// accept/reject rule to them in order -- keep the top `bits` bits of a word, reject values >= n and values already
+// selected (Lib/random.py: sample(), set-based branch; _randbelow_with_getrandbits) -- appending to out[have..k).
+// Returns the new number of selected positions. Plain host code: no device is touched.
+int32_t sacx_index_filter(const uint32_t* words, int32_t n_words, uint64_t n, int32_t bits, int64_t* out, int32_t have, int32_t k) {
+  if (!words || !out || n_words < 0 || have < 0 || k < have || bits < 1 || bits > 32) return -1;
+  static thread_local std::vector<int64_t> table;
+  size_t cap = 64;
+  while (cap < (size_t)k * 4) cap <<= 1;
+  table.assign(cap, -1);
+  auto slot_of = [&](int64_t v) { return (size_t)((uint64_t)v * 0x9E3779B97F4A7C15ull >> 17) & (cap - 1); };
+  auto insert = [&](int64_t v) -> bool {          // false when v is already present
+    size_t s = slot_of(v);
+    while (table[s] >= 0) { if (table[s] == v) return false; s = (s + 1) & (cap - 1); }
+    table[s] = v;
+    return true;
+  };
+  for (int32_t i = 0; i < have; ++i) insert(out[i]);
+  const int shift = 32 - bits;
+  for (int32_t i = 0; i < n_words && have < k; ++i) {
+    const uint64_t v = (uint64_t)(words[i] >> shift);
+    if (v >= n) continue;
+    if (insert((int64_t)v)) out[have++] = (int64_t)v;
+  }
+  return have;
+}
+
 int sacx_ring_sample_indices(sacx_ring_t h, int32_t agent, uint64_t seed, uint64_t counter, int32_t B, int64_t* out_dev) {
   if (!h || !out_dev || B <= 0) return fail(SACX_ERR_INVALID, "ring_sample_indices: bad arguments");
   Ring& r = h->r;
@@ -887,6 +915,9 @@ int sacx_agent_create(const sacx_config* cfg, float* arena_dev, sacx_agent_t* ou
   SACX_CUDA(cudaMalloc((void**)&e.d_barrier, sizeof(unsigned) * 64 * 4096));
   SACX_CUDA(cudaMemset(e.d_barrier, 0, sizeof(unsigned) * 64 * 4096));
   { const char* bm = getenv("SACX_BARRIER"); e.barrier_mode = bm ? atoi(bm) : 1; }
+  // graph replay of the host-path step is opt-in (SACX_GRAPH=1): measured on the B200 box it LOSES to four plain stream
+  // operations at this size -- 6186 vs 6444 updates/s end to end (cudaGraphLaunch costs the host more than it saves the device)
+  { const char* gm = getenv("SACX_GRAPH"); e.graph_mode = (gm && atoi(gm) != 0) ? 1 : 0; }
   SACX_CUDA(cudaMallocHost((void**)&e.pinned_metrics, sizeof(sacx_metrics)));
   if ((rc = engine_init_scalars(&e))) { sacx_agent_destroy(h); return rc; }
   *out = h;
@@ -907,7 +938,11 @@ int sacx_agent_destroy(sacx_agent_t h) {
   if (e.pinned_metrics) cudaFreeHost(e.pinned_metrics);
   if (e.pinned_io) cudaFreeHost(e.pinned_io);
   if (e.dev_io) cudaFree(e.dev_io);
-  for (auto& io : e.slots) { if (io.pinned) cudaFreeHost(io.pinned); if (io.dev) cudaFree(io.dev); if (io.done) cudaEventDestroy(io.done); }
+  for (auto& io : e.slots) {
+    if (io.gexec) cudaGraphExecDestroy(io.gexec);
+    if (io.pinned) cudaFreeHost(io.pinned); if (io.dev) cudaFree(io.dev); if (io.done) cudaEventDestroy(io.done);
+  }
+  if (e.cap_stream) cudaStreamDestroy(e.cap_stream);
   delete h;
   return SACX_OK;
 }
@@ -1062,6 +1097,7 @@ static int host_update_submit(Engine& e, int slot, const int64_t* idx, const flo
   const size_t total = b_idx + (e1 ? b_eps : 0) + (e2 ? b_eps : 0) + sizeof(AgentScalars) + 256;
   if (io.busy) { SACX_CUDA(cudaEventSynchronize(io.done)); io.busy = false; }
   if (total > io.bytes) {
+    if (io.gexec) { cudaGraphExecDestroy(io.gexec); io.gexec = nullptr; }       // its copy nodes point into the old buffers
     if (io.pinned) cudaFreeHost(io.pinned);
     if (io.dev) cudaFree(io.dev);
     io.pinned = io.dev = nullptr; io.bytes = 0;
@@ -1077,17 +1113,61 @@ static int host_update_submit(Engine& e, int slot, const int64_t* idx, const flo
   if (idx) { memcpy(hp + off, idx, b_idx); d_idx = (const i64*)(dp + off); off += b_idx; }
   if (e1) { memcpy(hp + off, e1, b_eps); d_e1 = (const float*)(dp + off); off += b_eps; }
   if (e2) { memcpy(hp + off, e2, b_eps); d_e2 = (const float*)(dp + off); off += b_eps; }
-  if (off) SACX_CUDA(cudaMemcpyAsync(dp, hp, off, cudaMemcpyHostToDevice, e.stream));
   int rc = need_ring(e, idx == nullptr);
   if (rc) return rc;
+  io.metrics_off = (off + 255) & ~(size_t)255;
   RunArgs a;
   memset(&a, 0, sizeof a);
   a.idx_ext = d_idx; a.eps1_ext = d_e1; a.eps2_ext = d_e2;
-  rc = e.rp ? engine_launch_rp(&e, n_steps, a) : engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
-  if (rc) return rc;
-  // the step's result travels back right behind the kernel (metrics block of agent 0)
-  io.metrics_off = (off + 255) & ~(size_t)255;
-  SACX_CUDA(cudaMemcpyAsync(hp + io.metrics_off, e.arena + e.scal_off, sizeof(AgentScalars), cudaMemcpyDeviceToHost, e.stream));
+  // the stream operations of one step; `st` is the caller's stream, or the capture stream while the graph is recorded
+  auto enqueue = [&](cudaStream_t st) -> int {
+    const cudaStream_t keep = e.stream;
+    e.stream = st;
+    int r2 = SACX_OK;
+    do {
+      if (off && cudaMemcpyAsync(dp, hp, off, cudaMemcpyHostToDevice, st) != cudaSuccess) { r2 = fail(SACX_ERR_CUDA, "update_host: H2D copy failed"); break; }
+      r2 = e.rp ? engine_launch_rp(&e, n_steps, a) : engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
+      if (r2) break;
+      // the step's result travels back right behind the kernel (metrics block of agent 0)
+      if (cudaMemcpyAsync(hp + io.metrics_off, e.arena + e.scal_off, sizeof(AgentScalars), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        r2 = fail(SACX_ERR_CUDA, "update_host: metrics D2H copy failed");
+    } while (0);
+    e.stream = keep;
+    return r2;
+  };
+  // graph replay for the single-launch paths (row-parallel kernel, tile-parallel persistent kernel); the tensor-core path is a
+  // sequence of ~40 launches per update whose grouping depends on the plan and stays on plain stream order
+  const bool graphable = e.graph_mode && (e.rp || !e.tc);
+  bool launched = false;
+  if (graphable) {
+    const unsigned long long key = ((unsigned long long)n_steps << 40) ^ ((unsigned long long)off << 8) ^ (idx ? 1ull : 0) ^ (e1 ? 2ull : 0) ^
+                                   (e2 ? 4ull : 0) ^ ((unsigned long long)(uintptr_t)(e.ring ? e.ring->dev : nullptr) << 3) ^
+                                   ((unsigned long long)(uintptr_t)dp << 1) ^ (e.rp ? 0x8000000000000000ull : 0);
+    if (!io.gexec || io.gkey != key) {
+      if (io.gexec) { cudaGraphExecDestroy(io.gexec); io.gexec = nullptr; }
+      bool ok = true;
+      if (!e.cap_stream) ok = cudaStreamCreateWithFlags(&e.cap_stream, cudaStreamNonBlocking) == cudaSuccess;
+      cudaGraph_t g = nullptr;
+      const long long launches_before = e.launches;
+      if (ok) ok = cudaStreamBeginCapture(e.cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        const int r2 = enqueue(e.cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(e.cap_stream, &g);
+        ok = (r2 == SACX_OK) && ce == cudaSuccess && g;
+      }
+      if (ok) ok = cudaGraphInstantiate(&io.gexec, g, 0) == cudaSuccess;
+      if (g) cudaGraphDestroy(g);
+      e.launches = launches_before;                      // recording is not launching
+      if (!ok) { cudaGetLastError(); io.gexec = nullptr; e.graph_mode = 0; }
+      else io.gkey = key;
+    }
+    if (io.gexec) {
+      SACX_CUDA(cudaGraphLaunch(io.gexec, e.stream));
+      ++e.launches;                                      // one fused-kernel launch per replay
+      launched = true;
+    }
+  }
+  if (!launched) { rc = enqueue(e.stream); if (rc) return rc; }
   SACX_CUDA(cudaEventRecord(io.done, e.stream));
   io.busy = true;
   return SACX_OK;

@@ -74,7 +74,15 @@ struct Engine {
   size_t pinned_io_bytes = 0;
   void* dev_io = nullptr;
   size_t dev_io_bytes = 0;
-  struct IoSlot { void* pinned = nullptr; void* dev = nullptr; size_t bytes = 0, metrics_off = 0; cudaEvent_t done = nullptr; bool busy = false; };
+  struct IoSlot {
+    void* pinned = nullptr; void* dev = nullptr; size_t bytes = 0, metrics_off = 0; cudaEvent_t done = nullptr; bool busy = false;
+    // the step (H2D of the index stream / normals -> barrier reset -> fused kernel -> metrics D2H) as an instantiated CUDA graph:
+    // every address in it is fixed per slot, so one submission is ONE cudaGraphLaunch instead of four stream operations
+    cudaGraphExec_t gexec = nullptr;
+    unsigned long long gkey = 0;          // what the graph was built for (n_steps, which streams are given, payload, ring identity)
+  };
+  cudaStream_t cap_stream = nullptr;      // private stream the graphs are captured on (the caller's may be the legacy default stream)
+  int graph_mode = 1;                     // SACX_GRAPH=0 disables; set to 0 when capture / instantiation fails once
   IoSlot slots[2];
   unsigned long long host_calls = 0;
   bool pipelined_pending = false;

@@ -508,34 +508,30 @@ __device__ __noinline__ void rp_gather(const RpCtx& c, const RpLaunch& L, i64* _
   }
   RP_TRACE(2100);
   __syncthreads();
-  // the 16 records: element e = (row, column of the record); W = 2O + A + 2 <= 256 -> at most 16 elements per thread
-  const int W = 2 * O + A + 2, total = RP_RB * W;
+  // the 16 records: 16 threads per record, thread (mm, c0) takes columns c0, c0 + 16, ... of record mm (W = 2O + A + 2 <= 256
+  // -> at most 16 per thread; 4 at BipedalWalker shape); all loads of a thread are in flight before the first is used
+  const int W = 2 * O + A + 2, mm = tid >> 4, c0 = tid & 15, row = c.row0 + mm;
+  const i64 slot = slots[mm];
+  const float* __restrict__ rec = ring + a.ring_s + (slot >= 0 ? slot : 0) * a.ring_rs;      // record = [s | s2 | a | r | d]: ring_s is its first field
   constexpr int MAXE = 16;
   float v[MAXE];
 #pragma unroll
   for (int u = 0; u < MAXE; ++u) {
-    const int e = tid + 256 * u;
-    v[u] = 0.f;
-    if (e < total) {
-      const int mm = e / W, col = e - mm * W;
-      const i64 slot = slots[mm];
-      if (slot >= 0) v[u] = __ldcs(ring + a.ring_s + slot * a.ring_rs + col);      // record = [s | s2 | a | r | d]: ring_s is its first field
-    }
+    const int col = c0 + 16 * u;
+    v[u] = (col < W && slot >= 0) ? __ldcs(rec + col) : 0.f;
   }
   RP_TRACE(2101);
   // padding columns (finite zeros: they meet zero-padded weights in the K loop)
-  for (int i = tid; i < RP_RB * (ldx - O); i += 256) {
-    const int mm = i / (ldx - O), col = O + i - mm * (ldx - O);
+  for (int col = O + c0; col < ldx; col += 16) {
     if (col >= O + A) xsa[mm * ldx + col] = 0.f;
     xs2[mm * ldx + col] = 0.f; xpi[mm * ldx + col] = 0.f;
   }
   RP_TRACE(2102);
+  const bool ok = w0 && slot >= 0;
 #pragma unroll
   for (int u = 0; u < MAXE; ++u) {
-    const int e = tid + 256 * u;
-    if (e < total) {
-      const int mm = e / W, col = e - mm * W, row = c.row0 + mm;
-      const bool ok = w0 && slots[mm] >= 0;
+    const int col = c0 + 16 * u;
+    if (col < W) {
       const float x = v[u];
       if (col < O) {
         xsa[mm * ldx + col] = x; xpi[mm * ldx + col] = x;

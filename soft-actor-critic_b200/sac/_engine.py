@@ -84,6 +84,7 @@ SYMBOLS = {
     "sacx_ring_gather": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "sacx_ring_gather_host": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "sacx_ring_resync": (C.c_int, [_P]),
+    "sacx_index_filter": (_I32, [C.c_char_p, _I32, _U64, _I32, _P, _I32, _I32]),
     "sacx_ring_sample_indices": (C.c_int, [_P, _I32, _U64, _U64, _I32, _P]),
     "sacx_obs_create": (C.c_int, [_I32, _I32, _I32, _I32, C.POINTER(_P)]),
     "sacx_obs_destroy": (C.c_int, [_P]),

@@ -210,6 +210,16 @@ class SAC:
             return None
         return torch.empty(rows, self.action_size).normal_().numpy()
 
+    def _normal_pair(self, rows: int):
+        """The two consecutive draws of one update (pi(s'), then pi(s)). torch's CPU normal_ fills 16-element blocks
+        independently (uniforms first, Box-Muller inside each block), so ONE draw of 2 x rows x A elements is the same stream as
+        two draws of rows x A whenever rows x A is a multiple of 16 (tests/test_binding_cpu.py pins this); otherwise two draws."""
+        n = rows * self.action_size
+        if n % 16 == 0 and n >= 16:
+            both = torch.empty(2, rows, self.action_size).normal_().numpy()
+            return both[0], both[1]
+        return self._normal(rows), self._normal(rows)
+
     # ------------------------------------------------------------------ buffer side
     def store_transition(self, state: Any, action: Any, reward: float, next_state: Any, done: bool) -> None:
         """reference: agent.py:126-135."""
@@ -289,7 +299,7 @@ class SAC:
         B = self.config["train"]["batch_size"]
         if self.rng_mode == "host":
             idx = np.asarray(self.replay_buffer.draw_indices(B), dtype=np.int64)
-            e1, e2 = self._normal(B), self._normal(B)
+            e1, e2 = self._normal_pair(B)
             m = self.engine.update_host_pipelined(idx, e1, e2, 1)
             self._host_pending = True
             if m is not None and m["nonfinite"]:

@@ -50,28 +50,19 @@ def sample_range(n: int, k: int):
         setsize += 4 ** math.ceil(math.log(k * 3, 4))
     if not (0 < k <= n) or n <= setsize or bits > 32 or type(random.getrandbits.__self__) is not random.Random:
         return random.sample(range(n), k)
-    shift = 32 - bits
     getrandbits = random.getrandbits
-    # one bulk draw of k words (the stdlib loop consumes at least k), filtered in numpy ...
-    words = np.frombuffer(getrandbits(32 * k).to_bytes(4 * k, "little"), dtype="<u4")
-    cand = words >> shift
-    out = cand[cand < n].tolist()
-    selected = set(out)
-    if len(selected) != len(out):                 # a repeated value inside the bulk (rare): keep first occurrences, in order
-        selected, kept = set(), []
-        for j in out:
-            if j not in selected:
-                selected.add(j)
-                kept.append(j)
-        out = kept
-    # ... and the few selections lost to rejections finish with the stdlib's own loop
-    while len(out) < k:
-        j = getrandbits(bits)
-        while j >= n or j in selected:
-            j = getrandbits(bits)
-        selected.add(j)
-        out.append(j)
-    return out
+    # Rounds of bulk draws. The stdlib loop consumes one 32-bit word per attempt and keeps attempting until k positions are
+    # selected, so drawing exactly as many words as selections are still missing never reads a word it would not have read;
+    # the accept/reject rule itself (value >= n, value selected before) runs in libsacx (sacx_index_filter, plain host code).
+    lib = E.load()
+    out = np.empty(k, dtype=np.int64)
+    have = 0
+    while have < k:
+        need = k - have
+        have = lib.sacx_index_filter(getrandbits(32 * need).to_bytes(4 * need, "little"), need, n, bits, out.ctypes.data, have, k)
+        if have < 0:
+            raise RuntimeError("sacx_index_filter rejected its arguments")
+    return out                                                # int64 array (what the gather takes); same values as the stdlib's list
 
 
 class ReplayBuffer:

@@ -167,3 +167,17 @@ def test_bulk_index_stream_is_the_stdlib_stream():
         oldest = max(c["pushes"] - c["capacity"], 0)
         for ids in c["push_ids"]:
             assert [oldest + j for j in sample_range(n, c["k"])] == ids
+
+
+def test_one_normal_draw_equals_two_consecutive_draws():
+    """SAC._normal_pair: torch's CPU normal_ on 2*n elements == two consecutive normal_ draws of n elements when n % 16 == 0
+    (what the reference consumes per update: models.py:82-83 called twice, agent.py:204,241)."""
+    import torch
+    for rows, act in ((256, 4), (8, 2), (1024, 2), (64, 1), (48, 3)):
+        assert (rows * act) % 16 == 0
+        torch.manual_seed(5)
+        a, b = torch.empty(rows, act).normal_(), torch.empty(rows, act).normal_()
+        after = torch.get_rng_state()
+        torch.manual_seed(5)
+        both = torch.empty(2, rows, act).normal_()
+        assert torch.equal(both[0], a) and torch.equal(both[1], b) and torch.equal(torch.get_rng_state(), after)
