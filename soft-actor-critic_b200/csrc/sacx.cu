@@ -226,7 +226,22 @@ static int engine_launch_rp(Engine* e, int n_steps, const RunArgs& proto) {
   }
   a.rp_part = e->d_rp_part;
   a.rp_maps = e->d_rp_maps;
-  SACX_CUDA(cudaMemsetAsync(e->d_barrier, 0, sizeof(unsigned) * 64 * (1 + RP_MAX_GROUPS), e->stream));
+  // two counter sets of its own (behind the tile-parallel kernel's region of d_barrier): launch L spins on set L & 1 and zeroes the
+  // other one for launch L + 1; both start zeroed at create. (During stream capture the choice would be frozen into the graph.)
+  {
+    unsigned* sets = e->d_barrier + 64 * 2048;
+    const size_t set_words = 64 * (1 + RP_MAX_GROUPS);
+    const int cur = (int)(e->rp_launch_no & 1);
+    a.barrier = sets + cur * set_words;
+    a.barrier_next = sets + (cur ^ 1) * set_words;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(e->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+      a.barrier = e->d_barrier; a.barrier_next = nullptr;
+      SACX_CUDA(cudaMemsetAsync(e->d_barrier, 0, sizeof(unsigned) * set_words, e->stream));
+    } else {
+      ++e->rp_launch_no;
+    }
+  }
   const Plan* dplan = e->d_plans + PLAN_RP;
   const RpProgram* dprog = e->d_prog;
   void* kargs[] = {(void*)&dplan, (void*)&dprog, (void*)&a};
@@ -1119,6 +1134,8 @@ static int host_update_submit(Engine& e, int slot, const int64_t* idx, const flo
   RunArgs a;
   memset(&a, 0, sizeof a);
   a.idx_ext = d_idx; a.eps1_ext = d_e1; a.eps2_ext = d_e2;
+  const bool direct_metrics = e.rp;          // the row-parallel kernel writes the metrics block into the pinned slot itself
+  if (direct_metrics) a.metrics_host = reinterpret_cast<float*>(hp + io.metrics_off);
   // the stream operations of one step; `st` is the caller's stream, or the capture stream while the graph is recorded
   auto enqueue = [&](cudaStream_t st) -> int {
     const cudaStream_t keep = e.stream;
@@ -1129,7 +1146,8 @@ static int host_update_submit(Engine& e, int slot, const int64_t* idx, const flo
       r2 = e.rp ? engine_launch_rp(&e, n_steps, a) : engine_launch(&e, PLAN_FUSED, 0, -1, n_steps, a, false);
       if (r2) break;
       // the step's result travels back right behind the kernel (metrics block of agent 0)
-      if (cudaMemcpyAsync(hp + io.metrics_off, e.arena + e.scal_off, sizeof(AgentScalars), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      if (!direct_metrics &&
+          cudaMemcpyAsync(hp + io.metrics_off, e.arena + e.scal_off, sizeof(AgentScalars), cudaMemcpyDeviceToHost, st) != cudaSuccess)
         r2 = fail(SACX_ERR_CUDA, "update_host: metrics D2H copy failed");
     } while (0);
     e.stream = keep;

@@ -97,6 +97,7 @@ struct Engine {
   RpProgram* d_prog = nullptr;
   float* d_rp_part = nullptr;
   int rp_grid = 0, rp_smem_bytes = 0;
+  unsigned long long rp_launch_no = 0;  // parity selects the barrier counter set of a launch
   bool rp_tma = true;              // weight slices by TMA where the layout allows (SACX_RP_TMA=0: cp.async everywhere)
   void* d_rp_maps = nullptr;       // device array of CUtensorMap, one per job
   std::string rp_why;

@@ -920,6 +920,10 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
       launch.upd0 = sc->updates; launch.rng_seed = sc->rng_seed; launch.rng_agent = sc->rng_agent; launch.pad = 0;
       launch.oldest_slot = launch.pushes > args.ring_capacity ? (launch.pushes - args.ring_capacity) % args.ring_capacity : 0;
     }
+    // the next launch's barrier counters (the two sets alternate): zeroed here, off the critical path, instead of by a memset
+    // operation in front of every launch
+    if (blockIdx.x == 0 && args.barrier_next)
+      for (int i = tid; i < 64 * (1 + RP_MAX_GROUPS); i += 256) args.barrier_next[i] = 0u;
   }
   __syncthreads();
   const int rank = blockIdx.x % RP_CS, gid = blockIdx.x / RP_CS, ngr = gridDim.x / RP_CS;
@@ -958,7 +962,20 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
           const Op& op = sops[oi];
           const int lt = t - op.tile0;
           if (op.type == OP_GEMM) gemm_tile_impl<CfgSmall, 2>(op, ec, lt, gsm);      // only dW tiles live in these phases
-          else if (op.type == OP_FINAL) { if (warp == 0) op_final(op, rc, lane); }
+          else if (op.type == OP_FINAL) {
+            if (warp == 0) {
+              op_final(op, rc, lane);
+              if (args.metrics_host && step + 1 == args.n_steps) {
+                // the step's result goes straight into pinned host memory (visible to the host once the kernel has completed):
+                // no device-to-host copy operation behind the launch
+                __syncwarp();
+                __threadfence();
+                const float* src = reinterpret_cast<const float*>(scal);
+                for (int i = lane; i < (int)(sizeof(AgentScalars) / 4); i += 32) args.metrics_host[i] = __ldcg(src + i);
+                __threadfence_system();
+              }
+            }
+          }
         }
       }
       const bool very_last = (ph == 3) && (step + 1 == args.n_steps);

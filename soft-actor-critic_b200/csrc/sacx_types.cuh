@@ -117,7 +117,9 @@ struct RunArgs {
   int n_steps, n_agents;
   int phase_begin, phase_end;
   int ctas_per_agent;
-  unsigned* barrier;         // [agent_slots] monotonic counters (zeroed before launch)
+  unsigned* barrier;         // [agent_slots] monotonic counters (zero when the launch starts)
+  unsigned* barrier_next;    // row-parallel kernel: the counter set of the NEXT launch, zeroed by this one (no memset per launch)
+  float* metrics_host;       // row-parallel kernel: pinned host copy of the scalar block, written by the kernel itself, or null
   i64 scal_off;
   unsigned long long* dbg;   // optional [n_steps][n_phases][gridDim.x][2] clock64 at barrier arrive / release
   unsigned long long* dbg2;  // optional [n_steps][n_phases][gridDim.x][8] intra-tile timestamps of the CTA's last GEMM tile
