@@ -358,7 +358,10 @@ def measure(name, args, rank, world, local_rank, barrier, dist, steps, warmup, w
         runner.dp.time_exchange = False
         extra["allreduce_ms_per_update"] = xms / steps
         extra["allreduce_share"] = xms / ev0.elapsed_time(ev1)
-        extra["limiter"] = "two latency-class ncclAllReduce (588 KB critics, 297 KB policy + temperature share) per update"
+        extra["exchange"] = "two ncclAllReduce per update on the engine stream: 588 KB critic gradients; 297 KB policy gradients + temperature share"
+        extra["limiter"] = ("the two all-reduces" if extra["allreduce_share"] > 0.25 else
+                            "not the exchange: per-update fixed cost that does not shrink with the per-rank batch (about 38 launches per "
+                            "update and the parameter-sized passes: dW split reduction, Adam, Polyak)")
     clk = None
     if clocks is not None:
         if sum(reps) < 1500:                                         # a longer stretch for the clock sampler (outside the timed region)
