@@ -686,9 +686,11 @@ int sacx_ring_gather(sacx_ring_t h, int32_t agent, const int64_t* idx_dev, int32
     const int pieces = r.RS / 4;                // 16-byte pieces of a packed record (the last one holds r, d)
     int tl = 0;
     while ((1 << tl) < pieces) ++tl;
-    const i64 threads = (i64)B << tl;
-    ring_gather_vec_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2,
-                                                                                    r.off_d, r.RS, r.O, r.A, (const i64*)idx_dev, B, s, a, rr, s2, d, tl);
+    const i64 threads = (i64)((B + 1) / 2) << tl;     // two rows per thread
+    const i64 pushes = r.pushes[agent];               // everything staged was flushed above: the device header holds the same count
+    const i64 oldest_slot = pushes > r.cap ? (pushes - r.cap) % r.cap : 0;
+    ring_gather_vec_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, r.stream>>>(r.block(agent), r.cap, oldest_slot, std::min(pushes, r.cap), r.off_s,
+                                                                                    r.RS, r.O, r.A, (const i64*)idx_dev, B, s, a, rr, s2, d, tl);
   } else {
     ring_gather_kernel<<<(B + 7) / 8, 256, 0, r.stream>>>(r.block(agent), r.cap, r.off_s, r.off_a, r.off_r, r.off_s2, r.off_d, r.RS, r.O, r.A,
                                                           (const i64*)idx_dev, B, s, a, rr, s2, d);

@@ -382,30 +382,47 @@ __global__ void ring_gather_kernel(const float* __restrict__ rb, i64 cap, i64 of
 // The same gather with one THREAD per 16-byte piece of the record (obs and act dimensions multiples of 4): a BipedalWalker
 // record is 14 pieces -> 16 threads, two rows per warp, the whole record in flight at once and read as consecutive sectors.
 // Piece p of the record holds 4 floats of s (p < O/4), of s2, of a, or the (r, d, pad, pad) tail.
-__global__ void ring_gather_vec_kernel(const float* __restrict__ rb, i64 cap, i64 off_s, i64 off_a, i64 off_r, i64 off_s2,
-                                       i64 off_d, int RS, int O, int A, const i64* __restrict__ idx, int B, float* __restrict__ s,
-                                       float* __restrict__ a, float* __restrict__ r, float* __restrict__ s2,
-                                       float* __restrict__ d, int tpr_log2) {
+__global__ void ring_gather_vec_kernel(const float* __restrict__ rb, i64 cap, i64 oldest_slot, i64 n_valid, i64 off_s, int RS, int O, int A,
+                                       const i64* __restrict__ idx, int B, float* __restrict__ s, float* __restrict__ a,
+                                       float* __restrict__ r, float* __restrict__ s2, float* __restrict__ d, int tpr_log2) {
+  // every thread owns the same 16-byte piece of TWO rows (row, row + ceil(B / 2)): two independent record reads in flight per
+  // thread before the first store
   const i64 gt = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = (int)(gt >> tpr_log2), piece = (int)(gt & ((1 << tpr_log2) - 1));
-  if (row >= B) return;
+  const int half = (B + 1) >> 1;
+  const int row0 = (int)(gt >> tpr_log2), piece = (int)(gt & ((1 << tpr_log2) - 1));
+  if (row0 >= half) return;
   const int cs = O >> 2, ca = A >> 2;
   if (piece > 2 * cs + ca) return;
-  const i64 pushes = reinterpret_cast<const RingMeta*>(rb)->pushes;
-  const i64 oldest = pushes > cap ? pushes - cap : 0;
-  const i64 j = __ldg(idx + row);
-  const bool in = j >= 0 && j < (pushes < cap ? pushes : cap);          // a position outside the deque reads nothing: zero row
-  const float* rec = rb + off_s + ((oldest + (in ? j : 0)) % cap) * RS;           // off_s: first field of the record
-  const float4 v = in ? __ldcs(reinterpret_cast<const float4*>(rec) + piece) : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (piece < cs) {
-    if (s) reinterpret_cast<float4*>(s + (i64)row * O)[piece] = v;
-  } else if (piece < 2 * cs) {
-    if (s2) reinterpret_cast<float4*>(s2 + (i64)row * O)[piece - cs] = v;
-  } else if (piece < 2 * cs + ca) {
-    if (a) reinterpret_cast<float4*>(a + (i64)row * A)[piece - 2 * cs] = v;
-  } else {
-    if (r) r[row] = v.x;
-    if (d) d[row] = v.y;
+  // slot of the oldest survivor and the deque length come from the host (it owns the push counter): no header read, and one
+  // conditional subtraction instead of a 64-bit modulo per thread
+  int rows[2] = {row0, row0 + half};
+  float4 v[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rows[u] < B) {
+      const i64 j = __ldg(idx + rows[u]);
+      if (j >= 0 && j < n_valid) {                                        // a position outside the deque reads nothing: zero row
+        i64 slot = oldest_slot + j;
+        if (slot >= cap) slot -= cap;
+        v[u] = __ldcs(reinterpret_cast<const float4*>(rb + off_s + slot * RS) + piece);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int row = rows[u];
+    if (row >= B) continue;
+    if (piece < cs) {
+      if (s) __stcs(reinterpret_cast<float4*>(s + (i64)row * O) + piece, v[u]);
+    } else if (piece < 2 * cs) {
+      if (s2) __stcs(reinterpret_cast<float4*>(s2 + (i64)row * O) + piece - cs, v[u]);
+    } else if (piece < 2 * cs + ca) {
+      if (a) __stcs(reinterpret_cast<float4*>(a + (i64)row * A) + piece - 2 * cs, v[u]);
+    } else {
+      if (r) r[row] = v[u].x;
+      if (d) d[row] = v[u].y;
+    }
   }
 }
 

@@ -33,6 +33,23 @@ for B in (256, 4096, 65536, 1_000_000):
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
+    # the same gather into PREALLOCATED outputs straight through the C ABI (what the fused update's consumers see; the call above
+    # also allocates five fresh torch tensors per call)
+    from sac import _engine as E
+    kw = dict(dtype=torch.float32, device="cuda")
+    so, ao, ro, s2o, do = torch.empty(B, O, **kw), torch.empty(B, A, **kw), torch.empty(B, **kw), torch.empty(B, O, **kw), torch.empty(B, **kw)
+    call = lambda ix: E.check(rb._lib.sacx_ring_gather(rb.handle, 0, ix.data_ptr(), B, so.data_ptr(), ao.data_ptr(), ro.data_ptr(), s2o.data_ptr(), do.data_ptr()))
+    for i in range(3):
+        call(idx[i % 4])
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(reps):
+        call(idx[i % 4])
+    k1.record()
+    torch.cuda.synchronize()
+    us_k = k0.elapsed_time(k1) * 1e3 / reps
+    assert np.array_equal(so.cpu().numpy(), s[idx[(reps - 1) % 4].cpu().numpy()])
     # check one batch against the host copy (bit-exact)
     j = idx[(reps - 1) % 4].cpu().numpy()
     assert np.array_equal(out.state.cpu().numpy(), s[j]) and np.array_equal(out.reward.cpu().numpy(), r[j])
@@ -41,4 +58,6 @@ for B in (256, 4096, 65536, 1_000_000):
                       "algorithmic_read_bytes": alg, "read_GBps": round(alg / us / 1e3, 1),
                       "read_plus_write_GBps": round((2 * alg + 8 * B) / us / 1e3, 1), "hbm_peak_GBps": peak,
                       "frac_of_peak_rw": round((2 * alg + 8 * B) / us / 1e3 / peak, 4),
+                      "preallocated_us_per_call": round(us_k, 2), "preallocated_read_plus_write_GBps": round((2 * alg + 8 * B) / us_k / 1e3, 1),
+                      "preallocated_frac_of_peak_rw": round((2 * alg + 8 * B) / us_k / 1e3 / peak, 4),
                       "note": "packed records [s | s2 | a | r | d | pad]: 224 B = seven 32-byte sectors per 216 B row"}))
