@@ -50,7 +50,7 @@ struct Engine {
   sacx_config cfg;
   int n_sms = 0, max_ctas = 0;
   bool large = false, grads_atomic = false;
-  int grid_x = 1, grid_y = 1, smem_bytes = 0, barrier_mode = 1;
+  int grid_x = 1, grid_y = 1, smem_bytes = 0, barrier_mode = 1, rp_barrier_mode = 7;
   std::vector<sacx_tensor_desc> lay;
   i64 cur = 0, stride = 0;
   NetLayout pi, q1, q2;

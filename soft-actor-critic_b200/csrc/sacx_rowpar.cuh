@@ -164,19 +164,30 @@ __device__ __forceinline__ void rp_mma3(float (&c0)[4], float (&c1)[4], float (&
 }
 
 // ---- group barrier: 8 CTAs, arrivals on one L2 line, release flag on another ----------------------------------------
-__device__ __forceinline__ void rp_group_barrier(unsigned* counter, unsigned& epoch) {
+__device__ __forceinline__ void rp_group_barrier(unsigned* counter, unsigned& epoch, int mode) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += RP_CS;
-    unsigned* flag = counter + 32;
     unsigned old, v;
     asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
-    if (old + 1 == epoch) {
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    if (mode & 2) {
+      // eight CTAs: poll the arrival counter itself -- one L2 hop less than "last arriver publishes a flag"
+      if (old + 1 != epoch) {
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while ((int)(v - epoch) < 0);
+      } else {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
     } else {
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-      } while ((int)(v - epoch) < 0);
+      unsigned* flag = counter + 32;
+      if (old + 1 == epoch) {
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+      } else {
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while ((int)(v - epoch) < 0);
+      }
     }
   }
   __syncthreads();
@@ -878,7 +889,7 @@ __device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, RpS
       rp_job(jb, c, sl);
       RP_TRACE(5000 + j);
     }
-    if (s + 1 < s1) rp_group_barrier(c.gbar, sy.gepoch);
+    if (s + 1 < s1) rp_group_barrier(c.gbar, sy.gepoch, c.args->barrier_mode);
     RP_TRACE(6000 + s);
   }
   cp_async_wait<0>();
@@ -981,7 +992,7 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
       const bool very_last = (ph == 3) && (step + 1 == args.n_steps);
       RP_TRACE(7000 + ph);
       if (dbg) dbg[ph * dstride] = clock64();
-      if (!very_last) group_barrier(counter, epoch, args.barrier_mode);
+      if (!very_last) group_barrier(counter, epoch, (args.barrier_mode & 4) ? 0 : 1);
       if (dbg) dbg[ph * dstride + 1] = clock64();
     }
   }
