@@ -324,7 +324,7 @@ static int engine_setup_tc(Engine* e) {
   {  // light row kernel: staging area for the widest head (falls back to global reads beyond 48 KB)
     const int A = e->cfg.act_dim, Kp = e->pi.dims[e->pi.L()], Kq = e->q1.dims[e->q1.L()], H0 = e->q1.dims[1];
     int need = std::max(std::max(2 * A * Kp + 2 * A, 4 * Kq), 2 * A * H0 + 2 * A * Kp);
-    const int small_floats = std::max(64 * SMALLK_MAX, 4 * 64 * (SMALLM_MAX + 1));      // small-K forward input tile / narrow dW reduction
+    const int small_floats = std::max(2 * 64 * SMALLK_MAX, 4 * 64 * (SMALLM_MAX + 1));  // small-K forward input + weight tiles / narrow dW reduction
     need = std::max(need, small_floats);
     e->rows_tsm_floats = std::max(std::min(rup(need, 4), 12288), small_floats);
     e->rows_smem_bytes = (WSM_FLOATS + e->rows_tsm_floats) * 4;

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
   float* wsm = smem_raw + (SMEM_OPS * sizeof(Op)) / 4;
   float* gsm = wsm + WSM_FLOATS;
   __shared__ Phase sphase[MAX_PHASES];
+  __shared__ uint32_t gcache[8 * GCACHE_WORDS];            // OP_GATHER: per-warp cache of the sampler keys / ring header
+  if (threadIdx.x < 8 * GCACHE_WORDS) gcache[threadIdx.x] = 0xffffffffu;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int op_lo = gplan->phases[args.phase_begin].op0;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
     float* base = args.arena + (i64)agent * args.agent_stride;
     AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
     RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, C::SMEM_FLOATS, nullptr};
+    rc.gcache = gcache + warp * GCACHE_WORDS;
     EpiCtx ec{base, scal, &args.hp, nullptr, gsm + C::SMEM_FLOATS};
     const FusedCtx fcx{base, scal, &args.hp, gsm + C::SMEM_FLOATS};
     const bool last_agent = (agent + (int)gridDim.y >= args.n_agents);
@@ -159,6 +162,8 @@ __device__ __forceinline__ void small_fwd_tile_k(const Op& op, float* __restrict
     base[op.c + (i64)m * op.ldc + n] = act == SACX_ACT_RELU ? fmaxf(s + bias, 0.f) : act_fwd(act, s + bias);
   }
 }
+// (a 4 x 4 output block per thread with 16-byte stores was tried for K <= 8: its weight reads from shared memory are
+//  16-way bank-conflicted at this K and it measured 45% slower -- 584 vs 402 us per phase for a 1024-agent population)
 __device__ __forceinline__ void small_fwd_tile(const Op& op, float* __restrict__ base, int tile, float* __restrict__ xs) {
   if (op.K <= 8) small_fwd_tile_k<8>(op, base, tile, xs);
   else if (op.K <= 16) small_fwd_tile_k<16>(op, base, tile, xs);
@@ -242,6 +247,8 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
   extern __shared__ __align__(16) float rows_raw[];
   __shared__ Op sops[ROWS_SMEM_OPS];
   __shared__ float fred[8];
+  __shared__ uint32_t gcache[8 * GCACHE_WORDS];            // OP_GATHER: per-warp cache of the sampler keys / ring header
+  if (threadIdx.x < 8 * GCACHE_WORDS) gcache[threadIdx.x] = 0xffffffffu;
   float* wsm = rows_raw;
   float* tsm = rows_raw + WSM_FLOATS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -259,6 +266,7 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
     float* base = args.arena + (i64)agent * args.agent_stride;
     AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
     RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, tsm, tsm_floats, nullptr};
+    rc.gcache = gcache + warp * GCACHE_WORDS;
     int last_oi = -1;
     rc.pf_rows = 2 * (int)gridDim.x * ROWS_PER_TILE;
     for (int t = blockIdx.x; t < ph.ntiles; t += gridDim.x) {

@@ -123,17 +123,16 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   return x;
 }
 
-__device__ __noinline__ unsigned long long feistel_index(unsigned long long i, unsigned long long n,
-                                                            unsigned long long seed, unsigned long long counter,
-                                                            uint32_t agent) {
+// the bijection's round keys: one Philox block per (update counter, agent, seed) -- the same for every row of an update
+__device__ __forceinline__ void feistel_key(unsigned long long seed, unsigned long long counter, uint32_t agent, uint32_t (&key)[4]) {
+  philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), 0x1D8E4E27u, agent, (uint32_t)seed, (uint32_t)(seed >> 32), key);
+}
+__device__ __forceinline__ unsigned long long feistel_apply(unsigned long long i, unsigned long long n, const uint32_t (&key)[4]) {
   if (n <= 1) return 0;
   int bits = 64 - __clzll((long long)(n - 1));
   int half = (bits + 1) >> 1;
   if (half < 1) half = 1;
   const uint32_t mask = (half >= 32) ? 0xFFFFFFFFu : ((1u << half) - 1u);
-  uint32_t key[4];
-  philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), 0x1D8E4E27u, agent, (uint32_t)seed,
-                (uint32_t)(seed >> 32), key);
   unsigned long long x = i;
   do {
     uint32_t L = (uint32_t)(x >> half) & mask, R = (uint32_t)x & mask;
@@ -147,6 +146,13 @@ __device__ __noinline__ unsigned long long feistel_index(unsigned long long i, u
     x = ((unsigned long long)L << half) | R;
   } while (x >= n);
   return x;
+}
+__device__ __noinline__ unsigned long long feistel_index(unsigned long long i, unsigned long long n,
+                                                            unsigned long long seed, unsigned long long counter,
+                                                            uint32_t agent) {
+  uint32_t key[4];
+  feistel_key(seed, counter, agent, key);
+  return feistel_apply(i, n, key);
 }
 
 }  // namespace sacx

@@ -30,7 +30,12 @@ struct RowCtx {
   unsigned long long* t;   // optional timestamps (profiling aid)
   int pf_rows = 0;         // light kernel: row distance to the tile this CTA runs two iterations from now (L2 prefetch), 0 = off
   int fresh = 1;           // 0: this CTA's previous tile belonged to the same op and agent -> the staged weights in tsm are still valid
+  // OP_GATHER, cached per thread across the rows it gathers for one (agent, update): the sampler's round keys, the ring's push
+  // count and the slot of the oldest survivor -- one Philox block, one header read and one 64-bit modulo per update, not per row
+  // (kept in the warp's shared scratch, not in registers: [0] agent [1] step [2..5] keys [6..7] pushes [8..9] oldest slot)
+  uint32_t* gcache = nullptr;
 };
+constexpr int GCACHE_WORDS = 12;
 #define SACX_RSTAMP(i) do { if (c.t && threadIdx.x == 0) c.t[i] = clock64(); } while (0)
 
 // ---- staging helpers -------------------------------------------------------------------------------
@@ -86,26 +91,40 @@ __device__ __noinline__ float warp_dot_any(const float* __restrict__ h, const fl
 
 // ---------------------------------------------------------------- OP_GATHER
 // o[0]=X_sa o[1]=X_s2 o[2]=X_pi o[3]=r o[4]=d o[5]=idx(i64)  i[0]=ldx
-__device__ __forceinline__ void op_gather(const Op& op, const RowCtx& c, int row, int lane) {
+__device__ __forceinline__ void op_gather(const Op& op, RowCtx& c, int row, int lane) {
   const RunArgs& a = *c.args;
   const Hyper& hp = a.hp;
   if (row >= hp.B) return;
   const float* ring = a.ring + (i64)c.agent * a.ring_stride;
-  const RingMeta* meta = reinterpret_cast<const RingMeta*>(ring);
-  const i64 pushes = meta->pushes;
   const i64 cap = a.ring_capacity;
-  const i64 n = pushes < cap ? pushes : cap;
+  uint32_t* gc = c.gcache;
+  if ((int)gc[0] != c.agent || (int)gc[1] != c.step) {       // first row of this (agent, update) on this warp
+    __syncwarp();
+    if (lane == 0) {
+      const i64 pushes = reinterpret_cast<const RingMeta*>(ring)->pushes;
+      const i64 oldest_slot = pushes > cap ? (pushes - cap) % cap : 0;
+      uint32_t key[4] = {0u, 0u, 0u, 0u};
+      if (!a.idx_ext)
+        feistel_key(__ldcg(&c.scal->rng_seed), (unsigned long long)__ldcg(&c.scal->updates), __ldcg(&c.scal->rng_agent), key);
+      gc[2] = key[0]; gc[3] = key[1]; gc[4] = key[2]; gc[5] = key[3];
+      gc[6] = (uint32_t)pushes; gc[7] = (uint32_t)((unsigned long long)pushes >> 32);
+      gc[8] = (uint32_t)oldest_slot; gc[9] = (uint32_t)((unsigned long long)oldest_slot >> 32);
+      gc[0] = (uint32_t)c.agent; gc[1] = (uint32_t)c.step;
+    }
+    __syncwarp();
+  }
+  const i64 g_pushes = (i64)(((unsigned long long)gc[7] << 32) | gc[6]), g_oldest_slot = (i64)(((unsigned long long)gc[9] << 32) | gc[8]);
+  const i64 n = g_pushes < cap ? g_pushes : cap;
   i64 j;
   if (a.idx_ext) {
     j = a.idx_ext[((i64)c.step * a.n_agents + c.agent) * hp.B + row];
   } else {
     // throughput mode: position (global row) of a keyed bijection on [0, n) -> distinct indices
-    const i64 upd = __ldcg(&c.scal->updates);
-    j = (i64)feistel_index((unsigned long long)(hp.row0_global + row), (unsigned long long)n, __ldcg(&c.scal->rng_seed),
-                           (unsigned long long)upd, __ldcg(&c.scal->rng_agent));
+    const uint32_t key[4] = {gc[2], gc[3], gc[4], gc[5]};
+    j = (i64)feistel_apply((unsigned long long)(hp.row0_global + row), (unsigned long long)n, key);
   }
-  const i64 oldest = pushes > cap ? pushes - cap : 0;
-  const i64 slot = (oldest + j) % cap;
+  i64 slot = g_oldest_slot + j;                                // both < capacity: a conditional subtraction replaces the modulo
+  if (slot >= cap) slot -= cap;
   float* base = c.base;
   const int O = hp.obs, A = hp.act, ldx = op.i[0];
   if (lane == 0) reinterpret_cast<i64*>(base + op.o[5])[row] = j;

@@ -945,7 +945,7 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   // dW phases reuse the tile code of the tile-parallel kernel; their shared memory aliases the row-parallel buffers
   float* wsm = smem_raw;
   float* gsm = smem_raw + WSM_FLOATS;
-  RowCtx rc{base, scal, &args, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};
+  RowCtx rc{base, scal, &args, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};      // (no OP_GATHER here: gcache stays null)
   EpiCtx ec{base, scal, &args.hp, nullptr, gsm + CfgSmall::SMEM_FLOATS};
   unsigned epoch = 0;
   RpSync sy{0u, 0u};
