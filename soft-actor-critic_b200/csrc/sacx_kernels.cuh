@@ -151,15 +151,20 @@ __device__ __forceinline__ void small_fwd_tile_k(const Op& op, float* __restrict
   for (int k = 0; k < KB; ++k) w[k] = (k < op.K) ? __ldg(base + op.b + (i64)n * op.b_sn + k) : 0.f;
   const float bias = __ldg(base + op.bias + n);
   const int act = op.act;
+  float* out = base + op.c + (i64)(tm * 64 + r0) * op.ldc + n;
+  const int rows = min(16, op.M - (tm * 64 + r0));
 #pragma unroll 4
   for (int r = 0; r < 16; ++r) {
-    const int m = tm * 64 + r0 + r;
-    if (m >= op.M) break;
-    const float* x = xs + (r0 + r) * KB;               // same address in every lane of the warp: broadcast
-    float s = 0.f;
+    if (r >= rows) break;
+    // the row is the same address in every lane of the warp: 16-byte broadcast loads, KB / 4 per row instead of KB
+    const float4* x4 = reinterpret_cast<const float4*>(xs + (r0 + r) * KB);
+    float s = bias;
 #pragma unroll
-    for (int k = 0; k < KB; ++k) s = fmaf(x[k], w[k], s);
-    base[op.c + (i64)m * op.ldc + n] = act == SACX_ACT_RELU ? fmaxf(s + bias, 0.f) : act_fwd(act, s + bias);
+    for (int q = 0; q < KB / 4; ++q) {
+      const float4 xv = x4[q];
+      s = fmaf(xv.x, w[4 * q], s); s = fmaf(xv.y, w[4 * q + 1], s); s = fmaf(xv.z, w[4 * q + 2], s); s = fmaf(xv.w, w[4 * q + 3], s);
+    }
+    out[(i64)r * op.ldc] = act == SACX_ACT_RELU ? fmaxf(s, 0.f) : act_fwd(act, s);
   }
 }
 // (a 4 x 4 output block per thread with 16-byte stores was tried for K <= 8: its weight reads from shared memory are
