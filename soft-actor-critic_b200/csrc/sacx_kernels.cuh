@@ -135,27 +135,38 @@ __device__ __forceinline__ bool small_fwd_ok(const Op& o) {
 // KB) in shared memory first, so the inner loop has no global load and no predicate. (Profile history: one 32-wide bucket
 // ran 32 predicated steps per output for a K = 5 layer -- instruction-bound; per-row global loads -- latency-bound.)
 // Called by all 256 threads of the CTA (two barriers inside); xs: 64 * KB floats of shared memory.
+// Tiles are enumerated ROW-BLOCK-minor (tile = tn * tiles_m + tm): with gridDim.x dividing tiles_m a CTA keeps its row block
+// while it walks the column tiles -- and the second critic of the phase, which reads the same input -- so the 64 x K input rows
+// are staged ONCE per CTA (`reuse_x`: the caller saw the same input matrix and row block in its previous tile) instead of once
+// per tile behind two barriers and a dependent global round trip (8 per CTA before: ~400 us per phase for a 1024-agent
+// population against a 90 us store floor).
 template <int KB>
-__device__ __forceinline__ void small_fwd_tile_k(const Op& op, float* __restrict__ base, int tile, float* __restrict__ xs) {
-  const int tm = tile / op.tiles_n, tn = tile % op.tiles_n;
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * KB; i += 256) {
-    const int r = i / KB, k = i % KB, m = tm * 64 + r;
-    xs[i] = (m < op.M && k < op.K) ? __ldcg(base + op.a + (i64)m * op.a_sm + k) : 0.f;
+__device__ __forceinline__ void small_fwd_tile_k(const Op& op, float* __restrict__ base, int tile, float* __restrict__ xs, bool reuse_x) {
+  // the op lives in shared memory: its fields go to registers once (left in place the compiler re-read them around every global
+  // store -- the profile of this tile showed ~50 instructions per output row, most of them such reloads and address arithmetic)
+  const int M = op.M, N = op.N, K = op.K, ldc = op.ldc, a_sm = op.a_sm, b_sn = op.b_sn, act = op.act;
+  const i64 oa = op.a, ob = op.b, oc = op.c, obias = op.bias;
+  const int tiles_m = (M + 63) >> 6;
+  const int tm = tile % tiles_m, tn = tile / tiles_m;
+  if (!reuse_x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * KB; i += 256) {
+      const int r = i / KB, k = i % KB, m = tm * 64 + r;
+      xs[i] = (m < M && k < K) ? __ldcg(base + oa + (i64)m * a_sm + k) : 0.f;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int n = tn * 64 + (threadIdx.x & 63), r0 = (threadIdx.x >> 6) * 16;
-  if (n >= op.N) return;
+  if (n >= N) return;
   float w[KB];
 #pragma unroll
-  for (int k = 0; k < KB; ++k) w[k] = (k < op.K) ? __ldg(base + op.b + (i64)n * op.b_sn + k) : 0.f;
-  const float bias = __ldg(base + op.bias + n);
-  const int act = op.act;
-  float* out = base + op.c + (i64)(tm * 64 + r0) * op.ldc + n;
-  const int rows = min(16, op.M - (tm * 64 + r0));
-#pragma unroll 4
+  for (int k = 0; k < KB; ++k) w[k] = (k < K) ? __ldg(base + ob + (i64)n * b_sn + k) : 0.f;
+  const float bias = __ldg(base + obias + n);
+  float* __restrict__ out = base + oc + (i64)(tm * 64 + r0) * ldc + n;
+  const int rows = min(16, M - (tm * 64 + r0));
+  const bool relu = act == SACX_ACT_RELU;
+#pragma unroll
   for (int r = 0; r < 16; ++r) {
-    if (r >= rows) break;
     // the row is the same address in every lane of the warp: 16-byte broadcast loads, KB / 4 per row instead of KB
     const float4* x4 = reinterpret_cast<const float4*>(xs + (r0 + r) * KB);
     float s = bias;
@@ -164,15 +175,17 @@ __device__ __forceinline__ void small_fwd_tile_k(const Op& op, float* __restrict
       const float4 xv = x4[q];
       s = fmaf(xv.x, w[4 * q], s); s = fmaf(xv.y, w[4 * q + 1], s); s = fmaf(xv.z, w[4 * q + 2], s); s = fmaf(xv.w, w[4 * q + 3], s);
     }
-    out[(i64)r * op.ldc] = act == SACX_ACT_RELU ? fmaxf(s, 0.f) : act_fwd(act, s);
+    const float o = relu ? fmaxf(s, 0.f) : act_fwd(act, s);
+    if (r < rows) { *out = o; }
+    out += ldc;
   }
 }
 // (a 4 x 4 output block per thread with 16-byte stores was tried for K <= 8: its weight reads from shared memory are
 //  16-way bank-conflicted at this K and it measured 45% slower -- 584 vs 402 us per phase for a 1024-agent population)
-__device__ __forceinline__ void small_fwd_tile(const Op& op, float* __restrict__ base, int tile, float* __restrict__ xs) {
-  if (op.K <= 8) small_fwd_tile_k<8>(op, base, tile, xs);
-  else if (op.K <= 16) small_fwd_tile_k<16>(op, base, tile, xs);
-  else small_fwd_tile_k<SMALLK_MAX>(op, base, tile, xs);
+__device__ __forceinline__ void small_fwd_tile(const Op& op, float* __restrict__ base, int tile, float* __restrict__ xs, bool reuse_x) {
+  if (op.K <= 8) small_fwd_tile_k<8>(op, base, tile, xs, reuse_x);
+  else if (op.K <= 16) small_fwd_tile_k<16>(op, base, tile, xs, reuse_x);
+  else small_fwd_tile_k<SMALLK_MAX>(op, base, tile, xs, reuse_x);
 }
 
 // weight gradient of a narrow output layer whose delta rows TMA cannot address (policy head with 2A not a multiple of 4:
@@ -273,6 +286,8 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
     RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, tsm, tsm_floats, nullptr};
     rc.gcache = gcache + warp * GCACHE_WORDS;
     int last_oi = -1;
+    i64 sm_a = -1;                                  // input matrix / row block of the small-K tile staged last (uniform over the CTA)
+    int sm_ld = 0, sm_k = 0, sm_tm = -1;
     rc.pf_rows = 2 * (int)gridDim.x * ROWS_PER_TILE;
     for (int t = blockIdx.x; t < ph.ntiles; t += gridDim.x) {
       int oi = ph.op0;
@@ -288,7 +303,13 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
       switch (op.type) {
         case OP_GEMM:
           if (op.cfg & 2) break;                      // tensor-core kernel
-          if (small_fwd_ok(op)) { small_fwd_tile(op, base, lt, tsm); last_oi = -2; }       // (these tiles use the staging area themselves)
+          if (small_fwd_ok(op)) {                   // (these tiles use the staging area themselves)
+            const int tm_ = lt % ((op.M + 63) >> 6);
+            const bool reuse = last_oi == -3 && sm_a == op.a && sm_ld == op.a_sm && sm_k == op.K && sm_tm == tm_;
+            small_fwd_tile(op, base, lt, tsm, reuse);
+            sm_a = op.a; sm_ld = op.a_sm; sm_k = op.K; sm_tm = tm_;
+            last_oi = -3;                           // -3: the staging area holds a small-K input tile (any other op re-stages)
+          }
           else if (small_dw_ok(op)) { small_dw_tile(op, base, scal, args.hp, lt, tsm); last_oi = -2; }
           break;
         case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
