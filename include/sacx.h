@@ -100,7 +100,8 @@ int         sacx_sizeof_metrics(void);
 int         sacx_sizeof_tensor_desc(void);
 
 /* ---------------------------------------------------------------- replay ring
- * Device-resident SoA ring: s[N,O] a[N,A] r[N] s2[N,O] d[N] per agent.  Push number p
+ * Device-resident ring of packed records [s (O) | s2 (O) | a (A) | r | d | pad] (2O + A + 2 floats rounded up to a multiple
+ * of 4) behind a 32-byte header per agent: a sampled transition is one contiguous read.  Push number p
  * lands in slot p % capacity, so logical deque position j (0 = oldest survivor,
  * reference deque(maxlen): sac/replay_buffer.py:19,30) is slot (max(p-N,0)+j) % N.   */
 int64_t sacx_ring_bytes(int32_t obs_dim, int32_t act_dim, int64_t capacity, int32_t n_agents);
@@ -179,7 +180,7 @@ int sacx_agent_reset_state(sacx_agent_t h);
 /* re-derive alpha (f32/f64) from log_alpha after a checkpoint load (agent.py:549-554) */
 int sacx_agent_refresh_alpha(sacx_agent_t h);
 int sacx_agent_grid(sacx_agent_t h, int32_t* ctas_per_agent, int32_t* agent_slots, int32_t* smem_bytes);
-/* which kernel executes sacx_update: 1 = row-parallel cluster kernel (8-CTA clusters own 16-row blocks, 3xTF32 tensor-core
+/* which kernel executes sacx_update: 1 = row-parallel kernel (software groups of 8 CTAs own 16-row blocks, 3xTF32 tensor-core
  * tiles), 0 = tile-parallel persistent kernel (any shape). reason (may be NULL) receives a short text when 0. */
 int sacx_agent_path(sacx_agent_t h, char* reason, int32_t capacity);
 /* 1 when the MLP GEMMs of this agent run on the tcgen05 tensor-core path (single agent, batch >= SACX_TC_MIN_BATCH,

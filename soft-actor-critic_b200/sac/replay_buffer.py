@@ -4,7 +4,7 @@ Reference: /root/reference/sac/replay_buffer.py -- ``Transition`` (:6-8), ``Repl
 (:12-19, ``deque(maxlen=capacity)``), ``push`` (:21-30), ``sample`` (:32-39, ``random.sample`` on the
 deque, ``ValueError`` when under-filled), ``__len__`` (:41-42).
 
-Here the storage is a struct-of-arrays ring in HBM owned by libsacx (``sacx_ring_*``): pushes go
+Here the storage is a ring of packed records ``[s | s2 | a | r | d]`` in HBM owned by libsacx (``sacx_ring_*``): pushes go
 through a pinned host staging block, sampling is a coalesced gather kernel.  The sampling *semantics*
 are the reference's: ``sample`` draws ``random.sample(range(len), batch_size)`` from Python's global
 Mersenne Twister -- the very index stream ``random.sample(deque, k)`` consumes -- and maps
@@ -186,7 +186,7 @@ class ReplayBuffer:
 
     # ------------------------------------------------------------------ exact-resume image
     def image(self) -> torch.Tensor:
-        """The whole ring (headers with the push counters + SoA fields) as one CPU tensor."""
+        """The whole ring (headers with the push counters + packed records) as one CPU tensor."""
         E.check(self._lib.sacx_ring_flush(self._h))
         torch.cuda.synchronize(self.device)
         return self._store.detach().cpu()
