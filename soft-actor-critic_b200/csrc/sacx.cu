@@ -442,19 +442,18 @@ static int engine_setup_tc(Engine* e) {
   return SACX_OK;
 }
 
-// tensor maps of the row-parallel kernel's TMA-staged weight slices (needs the arena address)
+// tensor maps of the row-parallel kernel: the TMA-staged weight slices of the jobs, then the dW tiles' operands (needs the arena
+// address). Either set failing to encode leaves its consumers on their cp.async path.
 static int engine_setup_rp_tma(Engine* e) {
   if (!e->rp) return SACX_OK;
   RpProgram& P = e->h_prog;
-  bool any = false;
-  for (int j = 0; j < P.n_jobs; ++j) any = any || P.jobs[j].tma;
-  if (!any) return SACX_OK;
-  auto clear = [&]() { for (int j = 0; j < P.n_jobs; ++j) P.jobs[j].tma = 0; cudaGetLastError(); };
+  Plan& plan = e->h_plans[PLAN_RP];
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
-  std::vector<CUtensorMap> maps(P.n_jobs);
+  const bool have = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn;
+  std::vector<CUtensorMap> maps(P.n_jobs + 2 * plan.n_ops);
   memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
-  bool ok = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn;
+  bool ok = have;
   for (int j = 0; ok && j < P.n_jobs; ++j) {
     const RpJob& jb = P.jobs[j];
     if (!jb.tma) continue;
@@ -466,9 +465,34 @@ static int engine_setup_rp_tma(Engine* e) {
     ok = ((TcEncodeFn)fn)(&maps[j], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e->arena + jb.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
-  if (ok && cudaMalloc(&e->d_rp_maps, sizeof(CUtensorMap) * maps.size()) != cudaSuccess) ok = false;
-  if (ok && cudaMemcpy(e->d_rp_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
-  if (!ok) { clear(); if (e->d_rp_maps) { cudaFree(e->d_rp_maps); e->d_rp_maps = nullptr; } }
+  if (!ok) { for (int j = 0; j < P.n_jobs; ++j) P.jobs[j].tma = 0; cudaGetLastError(); }
+  // dW operands: dy [batch][M] and x [batch][N], boxes of 64 batch rows x 32 columns
+  const char* dw_env = getenv("SACX_RP_DW_TMA");               // 0: keep the dW tiles on the FFMA / cp.async tile (A/B measurements)
+  bool ok_dw = have && !(dw_env && atoi(dw_env) == 0);
+  for (int k = 0; k < plan.n_ops; ++k) { plan.ops[k].i[2] = 0; plan.ops[k].i[3] = 0; }
+  for (int k = 0; ok_dw && k < plan.n_ops; ++k) {
+    Op& o = plan.ops[k];
+    if (o.type != OP_GEMM || o.epi != EPI_DW || o.a_sm != 1 || o.b_sn != 1 || (o.a & 3) || (o.b & 3) || (o.a_sk & 3) || (o.b_sk & 3)) continue;
+    if (o.K > RP_DW_MAXK || o.cfg != 0) continue;            // (cfg 0: the 32 x 32 tile grid this kernel walks)
+    for (int w = 0; ok_dw && w < 2; ++w) {
+      cuuint64_t dims[2] = {(cuuint64_t)(w ? o.N : o.M), (cuuint64_t)o.K}, strides[1] = {(cuuint64_t)(w ? o.b_sk : o.a_sk) * 4};
+      cuuint32_t box[2] = {32, (cuuint32_t)RP_DW_CHUNK}, estr[2] = {1, 1};
+      ok_dw = ((TcEncodeFn)fn)(&maps[P.n_jobs + 2 * k + w], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e->arena + (w ? o.b : o.a), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (ok_dw) { o.i[2] = P.n_jobs + 2 * k + 1; o.i[3] = P.n_jobs + 2 * k + 2; }
+  }
+  if (!ok_dw) { for (int k = 0; k < plan.n_ops; ++k) { plan.ops[k].i[2] = 0; plan.ops[k].i[3] = 0; } cudaGetLastError(); }
+  if (e->d_rp_maps) { cudaFree(e->d_rp_maps); e->d_rp_maps = nullptr; }
+  bool up = cudaMalloc(&e->d_rp_maps, sizeof(CUtensorMap) * maps.size()) == cudaSuccess;
+  up = up && cudaMemcpy(e->d_rp_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!up) {
+    for (int j = 0; j < P.n_jobs; ++j) P.jobs[j].tma = 0;
+    for (int k = 0; k < plan.n_ops; ++k) { plan.ops[k].i[2] = 0; plan.ops[k].i[3] = 0; }
+    if (e->d_rp_maps) { cudaFree(e->d_rp_maps); e->d_rp_maps = nullptr; }
+    cudaGetLastError();
+  }
   SACX_CUDA(cudaMemcpy(e->d_prog, &e->h_prog, sizeof(RpProgram), cudaMemcpyHostToDevice));
   return SACX_OK;
 }

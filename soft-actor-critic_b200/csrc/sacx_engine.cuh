@@ -99,7 +99,7 @@ struct Engine {
   int rp_grid = 0, rp_smem_bytes = 0;
   unsigned long long rp_launch_no = 0;  // parity selects the barrier counter set of a launch
   bool rp_tma = true;              // weight slices by TMA where the layout allows (SACX_RP_TMA=0: cp.async everywhere)
-  void* d_rp_maps = nullptr;       // device array of CUtensorMap, one per job
+  void* d_rp_maps = nullptr;       // device array of CUtensorMap: one per job, then two (dy, x) per dW op of the tile-parallel phases
   std::string rp_why;
   // tensor-core path (sacx_tc.cuh): single agent at large batch; per plan phase the TC-eligible GEMM ops in groups of <= 4
   struct TcGroup { TcParams p; TcMaps maps; int grid = 0; bool has_red = false; TcRedParams red; int red_blocks = 0; };
@@ -994,7 +994,8 @@ struct Engine {
     P.sm_wslot = off; off += RP_NWSLOT * P.wslot_floats;
     P.sm_red = off; off += RP_RED;
     P.sm_otile = off; P.sm_pw = off;
-    off = std::max(off, WSM_FLOATS + CfgSmall::SMEM_FLOATS);      // the dW tiles alias the same region
+    off = std::max(off, WSM_FLOATS + CfgSmall::SMEM_FLOATS);
+    off = std::max(off, RP_DW_SMEM);      // the dW tiles alias the same region
     P.sm_total = off;
     // partial-sum scratch of one group (global memory): [slot][rank][16][J]
     const int J[RPP_N] = {2 * A, 2 * A, 1, 1, 1, 1, A, A};

@@ -833,6 +833,167 @@ __device__ __noinline__ void rp_pi_bwd(const RpCtx& c) {
   __syncthreads();
 }
 
+// ---- weight-gradient tile on the tensor cores (phases B and D) ------------------------------------------------------------
+// dW[32 x 32] = dy^T x over the whole batch (K = batch <= RP_DW_MAXK rows) with the same 3xTF32 m16n8k8 arithmetic as the
+// forward / backward jobs. What bounds a dW tile here is not arithmetic but getting 2 x K x 128 B of operands from L2 into the SM:
+// the FFMA tile of sacx_gemm.cuh (and a first tensor-core version of this one) staged them with 16-byte cp.async copies, which
+// this SM issues at ~14 B/clk -- 9-10 K of a tile's 14 K cycles went to the copies. Here ONE thread asks the TMA unit for the
+// operands, a [64 rows x 32 floats] box of dy and of x per 64-row chunk (tensor maps built at engine creation, sacx.cu:
+// engine_setup_rp_tma; 128B swizzle; columns past M / N and rows past the batch arrive as zeros), one mbarrier per chunk.
+// Both operands are batch-major in global memory -- dy [batch][out], x [batch][in] -- and stay that way in shared memory; the
+// tile's 32 output rows / columns are assigned to MMA fragment positions through a permutation chosen so that, under the
+// swizzle, every fragment load touches 32 distinct banks. Warp w owns k-step w of every chunk (8 MMA tiles x 3 terms per
+// chunk), the eight warps' partial tiles meet in shared memory, and the epilogue is the FFMA tile's (gradient store / Adam /
+// Polyak on the tile itself); its operands (p, m, v, target) travel into shared memory by cp.async while the chunks load --
+// each thread copies exactly the four float4 it will consume. Bias gradient = column sums of dy, taken from the staged chunks.
+constexpr int RP_DW_MAXK = 512, RP_DW_CHUNK = 64, RP_DW_BOX = RP_DW_CHUNK * 32, RP_DW_NBAR = RP_DW_MAXK / RP_DW_CHUNK;
+constexpr int RP_DW_STAGE = 2 * RP_DW_MAXK * 32 + 4 * 1024;        // floats: dy boxes | x boxes | p, m, v, target tiles
+constexpr int RP_DW_SMEM = ((WSM_FLOATS + 255) & ~255) + RP_DW_STAGE;
+__device__ __forceinline__ bool rp_dw_tc_ok(const Op& op, const void* maps) {
+  return maps != nullptr && op.epi == EPI_DW && op.i[2] > 0 && op.i[3] > 0 && op.K <= RP_DW_MAXK && !(op.flags & DW_ATOMIC) && op.i[0] <= 1;
+}
+// swizzled position of element (k, col) of a [64][32] box: the 16-byte piece index is XORed with the row's low three bits
+__device__ __forceinline__ int rp_dw_sw(int k, int col) { return k * 32 + ((((col >> 2) ^ k) & 7) << 2) + (col & 3); }
+
+__device__ __noinline__ void rp_dw_tile_tc(const Op& op, const EpiCtx& ctx, int tile, float* __restrict__ stage, const void* maps,
+                                           uint64_t* bars, unsigned& parity) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int M = op.M, N = op.N, K = op.K;
+  const int tm = tile / op.tiles_n, tn = tile % op.tiles_n, m0 = tm * 32, n0 = tn * 32;
+  float* base = ctx.base;
+  float* As = stage;                                           // [chunk][64][32], swizzled
+  float* Bs = stage + RP_DW_MAXK * 32;
+  float* Es = stage + 2 * RP_DW_MAXK * 32;                     // [4][32][32]: p, m, v, target of this tile
+  const bool bias_tile = (tn == 0) && (op.pb >= 0);
+  const int nchunks = (K + RP_DW_CHUNK - 1) / RP_DW_CHUNK;
+  if (tid == 0) {
+    // the staging area was last written / read with ordinary accesses (previous tile's reduction, the row-parallel phase), all
+    // complete before the barrier in front of this tile: order them before the TMA unit's writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const char* ma = reinterpret_cast<const char*>(maps) + (size_t)(op.i[2] - 1) * 128;
+    const char* mb = reinterpret_cast<const char*>(maps) + (size_t)(op.i[3] - 1) * 128;
+    for (int c = 0; c < nchunks; ++c) {
+      rp_mbar_expect_tx(bars + c, 2u * RP_DW_BOX * 4u);
+      rp_tma_load(As + c * RP_DW_BOX, ma, bars + c, m0, c * RP_DW_CHUNK);
+      rp_tma_load(Bs + c * RP_DW_BOX, mb, bars + c, n0, c * RP_DW_CHUNK);
+    }
+  }
+  // epilogue operands: thread (row, c4) copies its own four float4
+  const int erow = tid >> 3, ec4 = (tid & 7) << 2;
+  const bool adam = (op.flags & DW_ADAM) != 0, polyak = (op.flags & DW_POLYAK) != 0;
+  const bool evec = adam && (m0 + erow < M) && epi_vec_ok(op, n0 + ec4);
+  if (evec) {
+    const i64 e = (i64)(m0 + erow) * N + n0 + ec4;
+    float* dst = Es + erow * 32 + ec4;
+    cp_async16(dst, base + op.p + e, 16);
+    cp_async16(dst + 1024, base + op.pm + e, 16);
+    cp_async16(dst + 2048, base + op.pv + e, 16);
+    if (polyak) cp_async16(dst + 3072, base + op.pt + e, 16);
+  }
+  cp_async_commit();
+  float ss = 0.f, bc = 0.f, tau = 0.f, omt = 0.f;
+  if (adam) {
+    ss = __ldcg(&ctx.scal->adam_step_size[op.opt]);
+    bc = __ldcg(&ctx.scal->adam_bc2_sqrt[op.opt]);
+    if (polyak) { tau = __ldcg(&ctx.scal->tau); omt = __ldcg(&ctx.scal->one_minus_tau); }
+  }
+  float bpre[8] = {0.f, 0.f, 0.f, 0.f, ss, bc, tau, omt};
+  if (bias_tile && adam && tid < 32 && m0 + tid < M) {
+    bpre[0] = __ldcg(base + op.pb + m0 + tid);
+    bpre[1] = __ldcg(base + op.pbm + m0 + tid);
+    bpre[2] = __ldcg(base + op.pbv + m0 + tid);
+    if (polyak) bpre[3] = __ldcg(base + op.pbt + m0 + tid);
+  }
+  float acc[2][4][4], small[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { acc[i][j][q] = 0.f; small[i][j][q] = 0.f; }
+  float bsum = 0.f;                                            // (warp, lane): this warp's k rows of dy column m0 + lane
+  // fragment position -> tile row / column. A rows: MMA block i, row g + 8h <-> tile row 16 (g >> 2) + 8 i + 4 h + (g & 3);
+  // B / C columns: block j, column cn <-> tile column 16 (cn >> 2) + 4 j + (cn & 3). Under the swizzle a fragment load of 32 lanes
+  // (g, t) then reads piece ((4 (g >> 2) + const) ^ t) at word g & 3: 32 distinct banks.
+  const int arow = 16 * (g >> 2) + (g & 3), kb = warp * 8;
+  for (int c = 0; c < nchunks; ++c) {
+    rp_mbar_wait(bars + c, (parity >> c) & 1u);
+    if (c * RP_DW_CHUNK + kb < K) {
+      const float* a = As + c * RP_DW_BOX;
+      const float* b = Bs + c * RP_DW_BOX;
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        rp_split(a[rp_dw_sw(kb + t, arow + 8 * i)], ah[i][0], al[i][0]);
+        rp_split(a[rp_dw_sw(kb + t, arow + 8 * i + 4)], ah[i][1], al[i][1]);
+        rp_split(a[rp_dw_sw(kb + t + 4, arow + 8 * i)], ah[i][2], al[i][2]);
+        rp_split(a[rp_dw_sw(kb + t + 4, arow + 8 * i + 4)], ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t bh[2], bl[2];
+        rp_split(b[rp_dw_sw(kb + t, arow + 4 * j)], bh[0], bl[0]);
+        rp_split(b[rp_dw_sw(kb + t + 4, arow + 4 * j)], bh[1], bl[1]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          rp_mma(small[i][j], al[i], bh);
+          rp_mma(small[i][j], ah[i], bl);
+          rp_mma(acc[i][j], ah[i], bh);
+        }
+      }
+      if (bias_tile) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bsum += a[rp_dw_sw(kb + k, lane)];
+      }
+    }
+  }
+  parity ^= (1u << nchunks) - 1u;
+  __syncthreads();                                             // all chunks consumed: the dy boxes become the reduction buffer
+  float* red = stage;                                          // [warp][32][33] (+ [warp][32] bias partials behind them)
+  float* bred = stage + 8 * 32 * 33;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = arow + 8 * i + 4 * (q >> 1), cn = 2 * t + (q & 1), col = 16 * (cn >> 2) + 4 * j + (cn & 3);
+        red[(warp * 32 + row) * 33 + col] = acc[i][j][q] + small[i][j][q];
+      }
+  if (bias_tile) bred[warp * 32 + lane] = bsum;
+  cp_async_wait<0>();                                          // this thread's epilogue operands
+  __syncthreads();
+  {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float* p = red + (w * 32 + erow) * 33 + ec4;
+      s.x += p[0]; s.y += p[1]; s.z += p[2]; s.w += p[3];
+    }
+    EpiPre pre;
+    pre.valid = evec;
+    if (evec) {
+      const float* src = Es + erow * 32 + ec4;
+      pre.a = *reinterpret_cast<const float4*>(src);
+      pre.b = *reinterpret_cast<const float4*>(src + 1024);
+      pre.c = *reinterpret_cast<const float4*>(src + 2048);
+      if (polyak) pre.d = *reinterpret_cast<const float4*>(src + 3072);
+      pre.ss = ss; pre.bc = bc; pre.tau = tau; pre.omt = omt;
+    } else if (!adam) {
+      pre.valid = (m0 + erow < M) && epi_vec_ok(op, n0 + ec4);          // gradient store only: nothing to prefetch
+    }
+    float4 outv;
+    epilogue_row4<2>(op, ctx, m0 + erow, n0 + ec4, s, pre, true, outv);
+  }
+  if (bias_tile && tid < 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += bred[w * 32 + tid];
+    epilogue_bias(op, ctx, m0 + tid, s, bpre);
+  }
+  __syncthreads();                                             // the staging area is reused by the next tile
+}
+
 // ---- the step interpreter ---------------------------------------------------------------------------------------------
 struct RpSync {            // barrier state that lives across phases and updates
   unsigned gepoch;         // group barrier epoch
@@ -906,11 +1067,13 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   __shared__ Phase sphase[2];
   __shared__ RpTrace trace;
   __shared__ __align__(8) uint64_t wbar[RP_NWSLOT];
+  __shared__ __align__(8) uint64_t dwbar[RP_DW_NBAR];
   __shared__ RpLaunch launch;
   __shared__ i64 row_slots[RP_RB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < RP_NWSLOT; ++i) rp_mbar_init(&wbar[i], 8);      // one arrival per warp and job
+    for (int i = 0; i < RP_DW_NBAR; ++i) rp_mbar_init(&dwbar[i], 1);    // one arrival (the issuing thread's expect_tx) per dW chunk
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (args.rp_maps && (((uint32_t)__cvta_generic_to_shared(smem_raw)) & 1023u)) __trap();   // swizzled tiles need 1024 B alignment
   }
@@ -945,6 +1108,8 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   // dW phases reuse the tile code of the tile-parallel kernel; their shared memory aliases the row-parallel buffers
   float* wsm = smem_raw;
   float* gsm = smem_raw + WSM_FLOATS;
+  float* dwstage = smem_raw + ((WSM_FLOATS + 255) & ~255);      // 1 KB aligned: swizzled TMA boxes
+  unsigned dwparity = 0u;
   RowCtx rc{base, scal, &args, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};      // (no OP_GATHER here: gcache stays null)
   EpiCtx ec{base, scal, &args.hp, nullptr, gsm + CfgSmall::SMEM_FLOATS};
   unsigned epoch = 0;
@@ -972,7 +1137,10 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
           while (oi + 1 < p.op0 + p.nops && t >= sops[oi + 1].tile0) ++oi;
           const Op& op = sops[oi];
           const int lt = t - op.tile0;
-          if (op.type == OP_GEMM) gemm_tile_impl<CfgSmall, 2>(op, ec, lt, gsm);      // only dW tiles live in these phases
+          if (op.type == OP_GEMM) {                 // only dW tiles live in these phases
+            if (!(args.barrier_mode & 8) && rp_dw_tc_ok(op, args.rp_maps)) rp_dw_tile_tc(op, ec, lt, dwstage, args.rp_maps, dwbar, dwparity);
+            else gemm_tile_impl<CfgSmall, 2>(op, ec, lt, gsm);
+          }
           else if (op.type == OP_FINAL) {
             if (warp == 0) {
               op_final(op, rc, lane);
