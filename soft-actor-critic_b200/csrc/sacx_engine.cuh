@@ -76,11 +76,13 @@ struct Engine {
   size_t dev_io_bytes = 0;
   struct IoSlot {
     void* pinned = nullptr; void* dev = nullptr; size_t bytes = 0, metrics_off = 0; cudaEvent_t done = nullptr; bool busy = false;
+    cudaEvent_t copied = nullptr;         // the slot's H2D copy (on copy_stream) has landed
     // the step (H2D of the index stream / normals -> barrier reset -> fused kernel -> metrics D2H) as an instantiated CUDA graph:
     // every address in it is fixed per slot, so one submission is ONE cudaGraphLaunch instead of four stream operations
     cudaGraphExec_t gexec = nullptr;
     unsigned long long gkey = 0;          // what the graph was built for (n_steps, which streams are given, payload, ring identity)
   };
+  cudaStream_t copy_stream = nullptr;     // host inputs of step t+1 travel here while the kernel of step t runs on `stream`
   cudaStream_t cap_stream = nullptr;      // private stream the graphs are captured on (the caller's may be the legacy default stream)
   int graph_mode = 1;                     // SACX_GRAPH=0 disables; set to 0 when capture / instantiation fails once
   IoSlot slots[2];
