@@ -52,6 +52,10 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
   float* gsm = wsm + WSM_FLOATS;
   __shared__ Phase sphase[MAX_PHASES];
   __shared__ uint32_t gcache[8 * GCACHE_WORDS];            // OP_GATHER: per-warp cache of the sampler keys / ring header
+  // the argument block the context structs point at is a SHARED copy: &args would put a 328-byte copy on every thread's
+  // local-memory stack, and the helpers' reads of it miss the small L1 that is left beside the shared-memory carve-out
+  __shared__ RunArgs sargs;
+  if (threadIdx.x == 0) sargs = args;
   if (threadIdx.x < 8 * GCACHE_WORDS) gcache[threadIdx.x] = 0xffffffffu;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -73,10 +77,10 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
   for (int agent = blockIdx.y; agent < args.n_agents; agent += gridDim.y) {
     float* base = args.arena + (i64)agent * args.agent_stride;
     AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
-    RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, C::SMEM_FLOATS, nullptr};
+    RowCtx rc{base, scal, &sargs, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, C::SMEM_FLOATS, nullptr};
     rc.gcache = gcache + warp * GCACHE_WORDS;
-    EpiCtx ec{base, scal, &args.hp, nullptr, gsm + C::SMEM_FLOATS};
-    const FusedCtx fcx{base, scal, &args.hp, gsm + C::SMEM_FLOATS};
+    EpiCtx ec{base, scal, &sargs.hp, nullptr, gsm + C::SMEM_FLOATS};
+    const FusedCtx fcx{base, scal, &sargs.hp, gsm + C::SMEM_FLOATS};
     const bool last_agent = (agent + (int)gridDim.y >= args.n_agents);
     for (int step = 0; step < args.n_steps; ++step) {
       rc.step = step;
@@ -266,6 +270,8 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
   __shared__ Op sops[ROWS_SMEM_OPS];
   __shared__ float fred[8];
   __shared__ uint32_t gcache[8 * GCACHE_WORDS];            // OP_GATHER: per-warp cache of the sampler keys / ring header
+  __shared__ RunArgs sargs;                                // (shared copy of the argument block: see sacx_run_kernel)
+  if (threadIdx.x == 0) sargs = args;
   if (threadIdx.x < 8 * GCACHE_WORDS) gcache[threadIdx.x] = 0xffffffffu;
   float* wsm = rows_raw;
   float* tsm = rows_raw + WSM_FLOATS;
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
   for (int agent = blockIdx.y; agent < args.n_agents; agent += gridDim.y) {
     float* base = args.arena + (i64)agent * args.agent_stride;
     AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
-    RowCtx rc{base, scal, &args, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, tsm, tsm_floats, nullptr};
+    RowCtx rc{base, scal, &sargs, agent, 0, wsm + warp * 4 * SACX_MAX_ACT, tsm, tsm_floats, nullptr};
     rc.gcache = gcache + warp * GCACHE_WORDS;
     int last_oi = -1;
     i64 sm_a = -1;                                  // input matrix / row block of the small-K tile staged last (uniform over the CTA)
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
             sm_a = op.a; sm_ld = op.a_sm; sm_k = op.K; sm_tm = tm_;
             last_oi = -3;                           // -3: the staging area holds a small-K input tile (any other op re-stages)
           }
-          else if (small_dw_ok(op)) { small_dw_tile(op, base, scal, args.hp, lt, tsm); last_oi = -2; }
+          else if (small_dw_ok(op)) { small_dw_tile(op, base, scal, sargs.hp, lt, tsm); last_oi = -2; }
           break;
         case OP_GATHER: op_gather(op, rc, lt * ROWS_PER_TILE + warp, lane); break;
         case OP_PI_HEAD: tile_pi_head<1>(op, rc, lt); break;

@@ -1104,14 +1104,26 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   float* base = args.arena;
   AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
   const int B = args.hp.B, nrb = (B + RP_RB - 1) / RP_RB;
-  RpCtx c{base, scal, &args, &sprog, &rows, args.rp_part + (i64)gid * sprog.part_stride, args.barrier + 64 * (1 + gid), rank, 0, 0, &trace, wbar, &launch, row_slots};
+  // A copy of the argument block (and the dW tiles' context) lives in SHARED memory: as a kernel-local copy -- forced by taking
+  // &args -- it sat on the local-memory stack (472 B per thread, 118 KB per CTA: more than the L1 left beside 192 KB of shared
+  // memory), and every `c.args->...` in a helper was a local load that regularly missed to L2: 600-800 cycles for a handful of
+  // instructions (profiles/r02c_rp_hot_lines.txt). The row-parallel context `c` (104 B) stays per thread: a shared copy whose
+  // fields point at the other shared objects made nvcc 12.9 drop those objects.
+  __shared__ RunArgs sargs;
+  __shared__ EpiCtx sec;
   // dW phases reuse the tile code of the tile-parallel kernel; their shared memory aliases the row-parallel buffers
   float* wsm = smem_raw;
   float* gsm = smem_raw + WSM_FLOATS;
   float* dwstage = smem_raw + ((WSM_FLOATS + 255) & ~255);      // 1 KB aligned: swizzled TMA boxes
   unsigned dwparity = 0u;
-  RowCtx rc{base, scal, &args, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};      // (no OP_GATHER here: gcache stays null)
-  EpiCtx ec{base, scal, &args.hp, nullptr, gsm + CfgSmall::SMEM_FLOATS};
+  if (tid == 0) {
+    sargs = args;                                               // (a plain struct copy: &args would bring the stack copy back)
+    sec = EpiCtx{base, scal, &sargs.hp, nullptr, gsm + CfgSmall::SMEM_FLOATS};
+  }
+  __syncthreads();
+  RpCtx c{base, scal, &sargs, &sprog, &rows, args.rp_part + (i64)gid * sprog.part_stride, args.barrier + 64 * (1 + gid), rank, 0, 0, &trace, wbar, &launch, row_slots};
+  const EpiCtx& ec = sec;
+  RowCtx rc{base, scal, &sargs, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};      // (no OP_GATHER here: gcache stays null)
   unsigned epoch = 0;
   RpSync sy{0u, 0u};
   unsigned* counter = args.barrier;
