@@ -538,7 +538,7 @@ def main():
         x["roofline"] = {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "hbm_view", "flop_per_update")}
         x["n_gpus"] = world
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # (the contract: timed on rank 0 at N=1 only)
         cpu = cpu_reference(w if w["n_agents"] == 1 else dict(w, fill=w["fill"]), 400, 10, budget_s=40.0)
     line = {"metric": "SAC updates/s", "value": res["value"], "unit": "updates/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": res["ms_per_step"], "repeats": res["repeats"], "ms_per_step_min": res["ms_per_step_min"],

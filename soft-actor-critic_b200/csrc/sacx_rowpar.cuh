@@ -166,6 +166,9 @@ __device__ __forceinline__ void rp_mma3(float (&c0)[4], float (&c1)[4], float (&
 // ---- group barrier: 8 CTAs, arrivals on one L2 line, release flag on another ----------------------------------------
 __device__ __forceinline__ void rp_group_barrier(unsigned* counter, unsigned& epoch, int mode) {
   __syncthreads();
+#ifdef SACX_DEBUG_HOOKS      // timing experiment (libsacx_debug.so only): what would the update cost without the group barriers? (results are garbage)
+  if (mode & 16) return;
+#endif
   if (threadIdx.x == 0) {
     epoch += RP_CS;
     unsigned old, v;
@@ -504,11 +507,14 @@ __device__ __noinline__ void rp_gather(const RpCtx& c, const RpLaunch& L, i64* _
     }
     slots[tid] = slot;
   } else if (tid >= 32) {
-    // normals: element i = (which, row of the block, action dim); lanes with dim >= A idle
-    for (int i = tid - 32; i < 2 * RP_RB * RP_MAXA; i += 224) {
-      const int which = i >> 7, mm = (i >> 3) & (RP_RB - 1), j = i & (RP_MAXA - 1), row = c.row0 + mm;
+    // normals: element i = (which, row of the block, action dim < A) -- 2 x 16 x A draws over 224 threads: ONE round up to A = 7
+    // (enumerating all RP_MAXA dims cost every update a second ~3.5 K-cycle Philox + Box-Muller round for 32 of the threads).
+    // Columns A.. of the eps rows are never read.
+    const int per = RP_RB * A;
+    for (int i = tid - 32; i < 2 * per; i += 224) {
+      const int which = i >= per ? 1 : 0, r = i - which * per, mm = r / A, j = r - mm * A, row = c.row0 + mm;
       float e = 0.f;
-      if (row < B && j < A) {
+      if (row < B) {
         const float* ext = which ? a.eps2_ext : a.eps1_ext;
         if (ext) e = ext[((i64)c.step * hp.B + row) * A + j];
         else e = philox_normal(L.rng_seed, upd, 1 + which, (uint32_t)(hp.row0_global + row), (uint32_t)j, L.rng_agent);
