@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256, 1) sacx_run_kernel(const Plan* __restrict
             case OP_Q_ROW: tile_q_row<0>(op, rc, lt); __syncthreads(); break;
             case OP_ACTOR_Q: tile_actor_q<0>(op, rc, lt); __syncthreads(); break;
             case OP_ACTOR_BWD: tile_actor_bwd<0>(op, rc, lt); __syncthreads(); break;
-            case OP_PROLOGUE: if (tid == 0) op_prologue(op, rc); break;
+            case OP_PROLOGUE: if (tid < 3) op_prologue(op, rc, tid); break;
             case OP_FINAL: if (warp == 0) op_final(op, rc, lane); break;
             case OP_DW_HEAD: tile_dw_head(op, fcx, lt, gsm); break;
             case OP_POLYAK: op_polyak(op, rc, lt); break;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256, 3) sacx_rows_kernel(const Plan* __restric
         case OP_Q_ROW: tile_q_row<1>(op, rc, lt); break;
         case OP_ACTOR_Q: tile_actor_q<1>(op, rc, lt); break;
         case OP_ACTOR_BWD: tile_actor_bwd<1>(op, rc, lt); break;
-        case OP_PROLOGUE: if (tid == 0) op_prologue(op, rc); break;
+        case OP_PROLOGUE: if (tid < 3) op_prologue(op, rc, tid); break;
         case OP_FINAL: op_final_impl<true>(op, rc, tid, fred); break;      // all 256 threads: B terms per mean
         case OP_POLYAK: op_polyak(op, rc, lt); break;
         case OP_ADAM_FLAT: op_adam_flat(op, rc, lt); break;

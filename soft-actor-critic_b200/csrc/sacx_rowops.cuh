@@ -671,19 +671,30 @@ __device__ __noinline__ void tile_actor_bwd(const Op& op, const RowCtx& c, int t
 
 // ---------------------------------------------------------------- OP_PROLOGUE (one thread)
 // mode = bitmask of optimisers (1 << OptId) whose step advances in this update
-__device__ __forceinline__ void op_prologue(const Op& op, const RowCtx& c) {
+// beta^t for Adam's bias corrections (torch: `1 - beta ** step` in Python doubles). exp(t ln beta) instead of pow(): the fp64 pow
+// was ~1.5 K cycles a call on this GPU, six calls per update on ONE thread that the rest of its 8-CTA group -- and at the phase
+// barrier everyone -- waited for (10 K cycles in front of phase A; tools/phase_profile.py, tag 101 -> 1000). The product
+// t ln(beta) carries |t ln beta| x 1.1e-16 <= 5e-15 of relative error into the result (beta^t < 4e-18 past |t ln beta| = 40 is
+// dropped: 1 - beta^t rounds to 1.0 either way), far below what the float32 step size / the 1e-12 temperature check resolve.
+__device__ __forceinline__ double adam_beta_pow(double ln_beta, i64 t) {
+  const double x = (double)t * ln_beta;
+  return x < -40.0 ? 0.0 : exp(x);
+}
+constexpr double LN_BETA1 = -0.10536051565782628;       // ln 0.9
+constexpr double LN_BETA2 = -0.0010005003335835335;     // ln 0.999
+
+// Adam step counters and bias-correction scalars of optimiser `o` (one lane each: the callers pass lanes 0-2)
+__device__ __forceinline__ void op_prologue(const Op& op, const RowCtx& c, int o) {
   AgentScalars* s = c.scal;
   const Hyper& hp = c.args->hp;
-  for (int o = 0; o < 3; ++o) {
-    if (!(op.mode & (1 << o))) continue;
-    const i64 t = s->step[o] + 1;
-    s->step[o] = t;
-    // python-double bias corrections of torch's _single_tensor_adam
-    const double bc1 = 1.0 - pow(0.9, (double)t);
-    const double bc2 = 1.0 - pow(0.999, (double)t);
-    s->adam_step_size[o] = (float)((s->lr[o] > 0.0 ? s->lr[o] : hp.lr[o]) / bc1);      // per-agent learning rate when set
-    s->adam_bc2_sqrt[o] = (float)sqrt(bc2);
-  }
+  if (o >= 3 || !(op.mode & (1 << o))) return;
+  const i64 t = s->step[o] + 1;
+  s->step[o] = t;
+  // python-double bias corrections of torch's _single_tensor_adam
+  const double bc1 = 1.0 - adam_beta_pow(LN_BETA1, t);
+  const double bc2 = 1.0 - adam_beta_pow(LN_BETA2, t);
+  s->adam_step_size[o] = (float)((s->lr[o] > 0.0 ? s->lr[o] : hp.lr[o]) / bc1);      // per-agent learning rate when set
+  s->adam_bc2_sqrt[o] = (float)sqrt(bc2);
 }
 
 // ---------------------------------------------------------------- OP_FINAL (one warp; CTA = true: the whole CTA, large batch)
@@ -792,7 +803,7 @@ __device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int
         s->step[OPT_ALPHA] = t;
         s->alpha_m = s->alpha_m + (1.0 - 0.9) * (g - s->alpha_m);
         s->alpha_v = s->alpha_v * 0.999 + (1.0 - 0.999) * g * g;
-        const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+        const double bc1 = 1.0 - adam_beta_pow(LN_BETA1, t), bc2 = 1.0 - adam_beta_pow(LN_BETA2, t);
         const double denom = sqrt(s->alpha_v) / sqrt(bc2) + 1e-8;
         const double alr = s->alpha_lr > 0.0 ? s->alpha_lr : hp.alpha_lr;      // per-agent override (Optuna trials as a population)
         s->log_alpha = s->log_alpha - (alr / bc1) * (s->alpha_m / denom);

@@ -1077,6 +1077,7 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   __shared__ RpLaunch launch;
   __shared__ i64 row_slots[RP_RB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long t_entry = clock64();
   if (tid == 0) {
     for (int i = 0; i < RP_NWSLOT; ++i) rp_mbar_init(&wbar[i], 8);      // one arrival per warp and job
     for (int i = 0; i < RP_DW_NBAR; ++i) rp_mbar_init(&dwbar[i], 1);    // one arrival (the issuing thread's expect_tx) per dW chunk
@@ -1136,13 +1137,17 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   const int sa = sprog.n_steps_a, sc = sprog.n_steps_c;
   for (int step = 0; step < args.n_steps; ++step) {
     c.step = step; rc.step = step;
-    if (tid == 0 && args.dbg2 && blockIdx.x == 0 && step + 1 == args.n_steps) { trace.buf = args.dbg2 + 1; trace.cap = 1000; trace.n = 0; }
+    if (tid == 0 && args.dbg2 && blockIdx.x == 0 && step + 1 == args.n_steps) {
+      trace.buf = args.dbg2 + 1; trace.cap = 1000; trace.n = 0;
+      if (step == 0) { trace.buf[0] = 100ull; trace.buf[1] = (unsigned long long)t_entry; trace.n = 1; }      // kernel entry (one-update launches)
+      RP_TRACE(101);
+    }
     // optional per-phase timestamps: [step][4 phases][CTA][arrive, release]
     unsigned long long* dbg = (args.dbg && tid == 0) ? args.dbg + ((size_t)step * 4 * gridDim.x + blockIdx.x) * 2 : nullptr;
     const size_t dstride = (size_t)gridDim.x * 2;
-    if (blockIdx.x == 0 && tid == 0) {
+    if (blockIdx.x == 0 && tid < 3) {
       Op po; po.mode = 7;
-      op_prologue(po, rc);
+      op_prologue(po, rc, tid);
     }
     for (int ph = 0; ph < 4; ++ph) {
       if ((ph & 1) == 0) {          // row-parallel phases: A (target, critics' forward/backward), C (actor)
@@ -1182,6 +1187,7 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
       if (dbg) dbg[ph * dstride + 1] = clock64();
     }
   }
+  RP_TRACE(9999);
   if (tid == 0 && trace.buf) args.dbg2[0] = (unsigned long long)trace.n;
 }
 

@@ -33,9 +33,10 @@ t = buf[: steps * P * G * 2].reshape(steps, P, G, 2).astype(np.int64)
 arrive, release = t[..., 0], t[..., 1]
 # per CTA: work(p) = arrive(p) - release(p-1); wait(p) = release(p) - arrive(p)
 prev_release = np.concatenate([release[:, -1:, :][:, :, :] * 0, release[:, :-1, :]], axis=1)
-work = (arrive - prev_release)[2:, 1:, :]          # skip first steps and phase 0 (no previous release in-step)
-wait = (release - arrive)[2:, :, :]
-span = (release[:, -2, :] - release[:, 0, :])[2:]   # phases 1..P-2 span per step (same SM clock)
+skip = min(2, steps - 1)
+work = (arrive - prev_release)[skip:, 1:, :]          # skip first steps and phase 0 (no previous release in-step)
+wait = (release - arrive)[skip:, :, :]
+span = (release[:, -2, :] - release[:, 0, :])[skip:]   # phases 1..P-2 span per step (same SM clock)
 print(f"workload={wl} grid={gx} phases={P} clock~1.965GHz; cycles (median over steps)")
 print("phase  work_max  work_med  work_min  wait_min  wait_med")
 for p in range(P):
