@@ -714,6 +714,39 @@ __device__ __forceinline__ float final_sum(float v, float* red) {
   for (int w = 0; w < 8; ++w) t += red[w];
   return t;
 }
+// scalar tail of OP_FINAL (one thread): temperature step from the entropy-gap means, update counter
+__device__ __forceinline__ void final_tail(const Op& op, const RowCtx& c) {
+  const Hyper& hp = c.args->hp;
+  float* base = c.base;
+  AgentScalars* s = c.scal;
+  if (op.mode & (4 | 32)) {
+    const float mean_t = (op.mode & 32) ? __ldcg(base + op.o[7]) : s->dp_mean_t;       // 32: the all-reduced shares
+    const float mean_lt = (op.mode & 32) ? __ldcg(base + op.o[7] + 1) : s->dp_mean_lt;
+    s->metrics[8] = mean_t - hp.target_entropy;
+    if (hp.auto_alpha) {
+      // alpha_loss = -(log_alpha * (logpi + H).detach()).mean();  d/dlog_alpha = -mean(logpi + H)
+      // alpha_lr < 0: temperature frozen -- what the reference does after load_agent, where the optimiser keeps stepping the
+      // pre-load tensor (agent.py:549-554); SAC.load_agent(..., reference_temperature_semantics=True) selects it
+      if (!(s->alpha_lr < 0.0)) {
+        const double g = -(double)mean_t;
+        const i64 t = s->step[OPT_ALPHA] + 1;
+        s->step[OPT_ALPHA] = t;
+        s->alpha_m = s->alpha_m + (1.0 - 0.9) * (g - s->alpha_m);
+        s->alpha_v = s->alpha_v * 0.999 + (1.0 - 0.999) * g * g;
+        const double bc1 = 1.0 - adam_beta_pow(LN_BETA1, t), bc2 = 1.0 - adam_beta_pow(LN_BETA2, t);
+        const double denom = sqrt(s->alpha_v) / sqrt(bc2) + 1e-8;
+        const double alr = s->alpha_lr > 0.0 ? s->alpha_lr : hp.alpha_lr;      // per-agent override (Optuna trials as a population)
+        s->log_alpha = s->log_alpha - (alr / bc1) * (s->alpha_m / denom);
+        s->alpha = exp(s->log_alpha);
+        s->alpha_f32 = (float)s->alpha;
+      }
+      s->metrics[3] = -mean_lt;
+    }
+    s->metrics[4] = (float)s->alpha;
+    s->metrics[5] = (float)s->log_alpha;
+  }
+  if (op.mode & 8) s->updates += 1;
+}
 template <bool CTA>
 __device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int lane, float* red) {
   const Hyper& hp = c.args->hp;
@@ -789,35 +822,61 @@ __device__ __forceinline__ void op_final_impl(const Op& op, const RowCtx& c, int
     }
     if (CTA) __syncthreads();
   }
-  if ((op.mode & (4 | 32)) && lane == 0) {
-    const float mean_t = (op.mode & 32) ? __ldcg(base + op.o[7]) : s->dp_mean_t;       // 32: the all-reduced shares
-    const float mean_lt = (op.mode & 32) ? __ldcg(base + op.o[7] + 1) : s->dp_mean_lt;
-    s->metrics[8] = mean_t - hp.target_entropy;
-    if (hp.auto_alpha) {
-      // alpha_loss = -(log_alpha * (logpi + H).detach()).mean();  d/dlog_alpha = -mean(logpi + H)
-      // alpha_lr < 0: temperature frozen -- what the reference does after load_agent, where the optimiser keeps stepping the
-      // pre-load tensor (agent.py:549-554); SAC.load_agent(..., reference_temperature_semantics=True) selects it
-      if (!(s->alpha_lr < 0.0)) {
-        const double g = -(double)mean_t;
-        const i64 t = s->step[OPT_ALPHA] + 1;
-        s->step[OPT_ALPHA] = t;
-        s->alpha_m = s->alpha_m + (1.0 - 0.9) * (g - s->alpha_m);
-        s->alpha_v = s->alpha_v * 0.999 + (1.0 - 0.999) * g * g;
-        const double bc1 = 1.0 - adam_beta_pow(LN_BETA1, t), bc2 = 1.0 - adam_beta_pow(LN_BETA2, t);
-        const double denom = sqrt(s->alpha_v) / sqrt(bc2) + 1e-8;
-        const double alr = s->alpha_lr > 0.0 ? s->alpha_lr : hp.alpha_lr;      // per-agent override (Optuna trials as a population)
-        s->log_alpha = s->log_alpha - (alr / bc1) * (s->alpha_m / denom);
-        s->alpha = exp(s->log_alpha);
-        s->alpha_f32 = (float)s->alpha;
-      }
-      s->metrics[3] = -mean_lt;
-    }
-    s->metrics[4] = (float)s->alpha;
-    s->metrics[5] = (float)s->log_alpha;
-  }
-  if ((op.mode & 8) && lane == 0) s->updates += 1;
+  if (lane == 0) final_tail(op, c);
 }
 __device__ __forceinline__ void op_final(const Op& op, const RowCtx& c, int lane) { op_final_impl<false>(op, c, lane, nullptr); }
+// Row-parallel kernel (batch <= 512): the whole CTA is called, warp k takes the k-th mean -- each with the summation order of
+// op_final_impl<false> (lane-strided, four loads in flight, butterfly) -- and thread 0 finishes. One warp doing the seven means
+// one after the other made this tile (17.6 K cycles) the longest of its phase, 6 K past the weight-gradient tiles.
+// red: 16 floats of shared memory.
+__device__ __forceinline__ void op_final_par(const Op& op, const RowCtx& c, float* red) {
+  const Hyper& hp = c.args->hp;
+  float* base = c.base;
+  AgentScalars* s = c.scal;
+  const int B = hp.B, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float invB = 1.f / (float)hp.B_global;
+  auto warp_mean = [&](const float* p) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int b = lane;
+    for (; b + 96 < B; b += 128) {
+      acc[0] += __ldcg(p + b); acc[1] += __ldcg(p + b + 32); acc[2] += __ldcg(p + b + 64); acc[3] += __ldcg(p + b + 96);
+    }
+    for (; b < B; b += 32) acc[0] += __ldcg(p + b);
+    return warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3])) * invB;
+  };
+  float r = 0.f, r2 = 0.f;
+  if (op.mode & 1) {
+    if (warp == 0) r = warp_mean(base + op.o[0]);
+    else if (warp == 1) r = warp_mean(base + op.o[1]);
+    else if (warp == 2) r = warp_mean(base + op.o[4]);
+    else if (warp == 3) r = warp_mean(base + op.o[5]);
+    else if (warp == 4) r = warp_mean(base + op.o[6]);
+  }
+  if ((op.mode & 2) && warp == 5) r = warp_mean(base + op.o[2]);
+  if ((op.mode & (4 | 16)) && warp == 6) {
+    const float* lp = c.args->lp_ext ? c.args->lp_ext : base + op.o[3];
+    float acc = 0.f, accl = 0.f;
+    const float la32 = (float)s->log_alpha;
+    for (int b = lane; b < B; b += 32) {
+      const float t = __ldcg(lp + b) + hp.target_entropy;
+      acc += t;
+      accl += la32 * t;
+    }
+    r = warp_sum(acc) * invB;             // f32 mean, as in the reference
+    r2 = warp_sum(accl) * invB;
+  }
+  if (lane == 0) { red[warp] = r; if (warp == 6) red[8] = r2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (op.mode & 1) { s->metrics[0] = red[0]; s->metrics[1] = red[1]; s->metrics[6] = red[2]; s->metrics[7] = red[3]; s->metrics[9] = red[4]; }
+    if (op.mode & 2) s->metrics[2] = red[5];
+    if (op.mode & (4 | 16)) {
+      s->dp_mean_t = red[6]; s->dp_mean_lt = red[8];
+      if (op.mode & 16) { base[op.o[7]] = red[6]; base[op.o[7] + 1] = red[8]; }      // travels with the policy gradients
+    }
+    final_tail(op, c);
+  }
+}
 
 // ---------------------------------------------------------------- OP_POLYAK / OP_ADAM_FLAT (elementwise tiles)
 constexpr int FLAT_TILE = 256 * 8;

@@ -1165,8 +1165,8 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
             else gemm_tile_impl<CfgSmall, 2>(op, ec, lt, gsm);
           }
           else if (op.type == OP_FINAL) {
+            op_final_par(op, rc, wsm);
             if (warp == 0) {
-              op_final(op, rc, lane);
               if (args.metrics_host && step + 1 == args.n_steps) {
                 // the step's result goes straight into pinned host memory (visible to the host once the kernel has completed):
                 // no device-to-host copy operation behind the launch

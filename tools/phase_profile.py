@@ -47,6 +47,12 @@ for p in range(P):
 tot = np.median(release[2:, -2, 0] - release[1:-1, -2, 0]) if steps > 3 else 0
 print("cycles per update (CTA0, release-to-release of phase P-2):", int(tot), "=", tot / 1.965e3, "us")
 
+if len(sys.argv) > 3:
+    for p in [int(x) for x in sys.argv[3].split(",")]:
+        wk = np.median(work[:, p - 1, :], axis=0).astype(int)
+        print(f"phase {p} work per CTA (cycles), CTA index = first tile index:")
+        print(" ".join(f"{i}:{v}" for i, v in enumerate(wk)))
+
 if eng.path()[0] == "rowpar":
     tr = buf[steps * P * G * 2:]
     n = int(tr[0])
@@ -70,8 +76,3 @@ for p in range(P):
         extra = f"   gen: pre {dg(5,0)} prologue {dg(6,5)} sync {dg(7,6)} first-wait {dg(1,7)}"
     print(f"{p:5d} {d(1,0):7d} {d(2,1):7d} {d(3,2):7d} {d(4,3):7d} {d(4,0):7d}{extra}")
 
-if len(sys.argv) > 3:
-    for p in [int(x) for x in sys.argv[3].split(",")]:
-        wk = np.median(work[:, p - 1, :], axis=0).astype(int)
-        print(f"phase {p} work per CTA (cycles), CTA index = first tile index:")
-        print(" ".join(f"{i}:{v}" for i, v in enumerate(wk)))
