@@ -1063,19 +1063,47 @@ __device__ __forceinline__ void rp_run_steps(const RpCtx& c, int s0, int s1, RpS
   __syncthreads();
 }
 
+// program and dW ops -> shared memory: 16-byte loads, all of a thread's loads in flight before its first store (with 4-byte
+// loads in two dependent loops this was 4 K of the 7 K cycles a launch spends before its first step). Out of line: its
+// registers are its own.
+__device__ __noinline__ void rp_stage_program(const Plan* __restrict__ gplan, const RpProgram* __restrict__ gprog, RpProgram* sprog, Op* sops) {
+  const int tid = threadIdx.x;
+  constexpr int PW = (int)(sizeof(RpProgram) / 16), OW = (int)(RP_MAX_DW_OPS * sizeof(Op) / 16);
+  static_assert(sizeof(RpProgram) % 4 == 0 && (RP_MAX_DW_OPS * sizeof(Op)) % 16 == 0 && sizeof(Plan) % 16 == 0 && offsetof(Plan, ops) % 16 == 0,
+                "16-byte copies of the program / the dW ops");
+  const int4* src = reinterpret_cast<const int4*>(gprog);
+  int4* dst = reinterpret_cast<int4*>(sprog);
+  const int4* osrc = reinterpret_cast<const int4*>(gplan->ops);
+  int4* odst = reinterpret_cast<int4*>(sops);
+  constexpr int NP = (PW + 255) / 256, NO = (OW + 255) / 256;
+  int4 vp[NP], vo[NO];
+#pragma unroll
+  for (int u = 0; u < NP; ++u) if (tid + 256 * u < PW) vp[u] = __ldg(src + tid + 256 * u);
+#pragma unroll
+  for (int u = 0; u < NO; ++u) if (tid + 256 * u < OW) vo[u] = __ldg(osrc + tid + 256 * u);
+  if (tid < (int)(sizeof(RpProgram) % 16) / 4)      // tail words of the program
+    reinterpret_cast<int*>(sprog)[PW * 4 + tid] = __ldg(reinterpret_cast<const int*>(gprog) + PW * 4 + tid);
+#pragma unroll
+  for (int u = 0; u < NP; ++u) if (tid + 256 * u < PW) dst[tid + 256 * u] = vp[u];
+#pragma unroll
+  for (int u = 0; u < NO; ++u) if (tid + 256 * u < OW) odst[tid + 256 * u] = vo[u];
+}
+
 // grid = n_groups x 8 CTAs (cooperative launch: all co-resident). gplan: phase 0 = critics' dW + Adam + Polyak tiles,
 // phase 1 = policy dW + Adam tiles and the final op (loss means, temperature step, update counter).
 __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict__ gplan, const RpProgram* __restrict__ gprog, const RunArgs args) {
   RP_SMEM;
-  __shared__ RpProgram sprog;
+  __shared__ __align__(16) RpProgram sprog;
   __shared__ RpRows rows;
-  __shared__ Op sops[RP_MAX_DW_OPS];
+  __shared__ __align__(16) Op sops[RP_MAX_DW_OPS];
   __shared__ Phase sphase[2];
   __shared__ RpTrace trace;
   __shared__ __align__(8) uint64_t wbar[RP_NWSLOT];
   __shared__ __align__(8) uint64_t dwbar[RP_DW_NBAR];
   __shared__ RpLaunch launch;
   __shared__ i64 row_slots[RP_RB];
+  __shared__ RunArgs sargs;       // the argument block and the dW tiles' context, read by the helpers (see below)
+  __shared__ EpiCtx sec;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long t_entry = clock64();
   if (tid == 0) {
@@ -1084,14 +1112,8 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (args.rp_maps && (((uint32_t)__cvta_generic_to_shared(smem_raw)) & 1023u)) __trap();   // swizzled tiles need 1024 B alignment
   }
+  rp_stage_program(gplan, gprog, &sprog, sops);
   {
-    const int* src = reinterpret_cast<const int*>(gprog);
-    int* dst = reinterpret_cast<int*>(&sprog);
-    for (int i = tid; i < (int)(sizeof(RpProgram) / 4); i += 256) dst[i] = src[i];
-    const int nops = min(gplan->n_ops, RP_MAX_DW_OPS);
-    const int* osrc = reinterpret_cast<const int*>(gplan->ops);
-    int* odst = reinterpret_cast<int*>(sops);
-    for (int i = tid; i < nops * (int)(sizeof(Op) / 4); i += 256) odst[i] = osrc[i];
     if (tid < 2) sphase[tid] = gplan->phases[tid];
     if (tid == 0) {
       trace.buf = nullptr; trace.n = 0; trace.cap = 0;
@@ -1106,6 +1128,11 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
     if (blockIdx.x == 0 && args.barrier_next)
       for (int i = tid; i < 64 * (1 + RP_MAX_GROUPS); i += 256) args.barrier_next[i] = 0u;
   }
+  if (tid == 32) {            // (another warp than the launch constants' thread)
+    sargs = args;             // a plain struct copy: &args would bring the stack copy back
+    float* b0 = args.arena;
+    sec = EpiCtx{b0, reinterpret_cast<AgentScalars*>(b0 + args.scal_off), &sargs.hp, nullptr, rp_dyn_smem + WSM_FLOATS + CfgSmall::SMEM_FLOATS};
+  }
   __syncthreads();
   const int rank = blockIdx.x % RP_CS, gid = blockIdx.x / RP_CS, ngr = gridDim.x / RP_CS;
   float* base = args.arena;
@@ -1116,18 +1143,11 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   // memory), and every `c.args->...` in a helper was a local load that regularly missed to L2: 600-800 cycles for a handful of
   // instructions (profiles/r02c_rp_hot_lines.txt). The row-parallel context `c` (104 B) stays per thread: a shared copy whose
   // fields point at the other shared objects made nvcc 12.9 drop those objects.
-  __shared__ RunArgs sargs;
-  __shared__ EpiCtx sec;
   // dW phases reuse the tile code of the tile-parallel kernel; their shared memory aliases the row-parallel buffers
   float* wsm = smem_raw;
   float* gsm = smem_raw + WSM_FLOATS;
   float* dwstage = smem_raw + ((WSM_FLOATS + 255) & ~255);      // 1 KB aligned: swizzled TMA boxes
   unsigned dwparity = 0u;
-  if (tid == 0) {
-    sargs = args;                                               // (a plain struct copy: &args would bring the stack copy back)
-    sec = EpiCtx{base, scal, &sargs.hp, nullptr, gsm + CfgSmall::SMEM_FLOATS};
-  }
-  __syncthreads();
   RpCtx c{base, scal, &sargs, &sprog, &rows, args.rp_part + (i64)gid * sprog.part_stride, args.barrier + 64 * (1 + gid), rank, 0, 0, &trace, wbar, &launch, row_slots};
   const EpiCtx& ec = sec;
   RowCtx rc{base, scal, &sargs, 0, 0, wsm + warp * 4 * SACX_MAX_ACT, gsm, CfgSmall::SMEM_FLOATS, nullptr};      // (no OP_GATHER here: gcache stays null)
