@@ -133,3 +133,35 @@ def test_rowpar_teacher_forced_bipedal_vs_reference(monkeypatch):
     assert_close("q1", eng.view("out.q1").cpu().numpy().ravel(), g["step0/q1"], 2e-5)
     assert abs(m["q1_loss"] - float(g["step0/q1_loss"])) <= 2e-5 * abs(float(g["step0/q1_loss"])) + 1e-7
     assert abs(m["log_alpha"] - float(g["step0/log_alpha"])) < 1e-6
+
+
+@pytest.mark.parametrize("obs,act,hp,hq,B,actfn", [CASES[0], CASES[2], CASES[4]])
+def test_rowpar_weight_gradient_tiles_tma_vs_ffma(obs, act, hp, hq, B, actfn, monkeypatch):
+    """The weight-gradient tiles of the two tile-parallel phases have two implementations: 3xTF32 tensor-core tiles with
+    TMA-staged operands (default) and the FFMA / cp.async tile the kernel falls back to when a tensor map cannot be encoded
+    (SACX_RP_DW_TMA=0 forces it). Same gradients, same Adam / Polyak arithmetic: parameters, moments and targets agree to
+    summation-order tolerance after two updates, everything in front of the dW phases bit for bit."""
+    rng = np.random.default_rng(5)
+    K = 2
+    idx = np.stack([rng.choice(1500, B, replace=False) for _ in range(K)]).astype(np.int64)
+    e1 = rng.standard_normal((K, B, act)).astype(np.float32)
+    e2 = rng.standard_normal((K, B, act)).astype(np.float32)
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("SACX_RP_DW_TMA", tma)
+        eng = _engine(obs, act, hp, hq, B, actfn, monkeypatch, True)
+        assert eng.path()[0] == "rowpar"
+        snaps = []
+        for k in range(K):
+            m = eng.update_host(idx[k], e1[k], e2[k], 1)
+            assert m["nonfinite"] == 0
+            snaps.append({n: eng.view(n).cpu().numpy().copy() for n in ("out.y", "out.q1", "out.tq1", "block.params", "block.targets",
+                                                                         "block.m", "block.v")})
+        out[tma] = snaps
+    monkeypatch.delenv("SACX_RP_DW_TMA")
+    for n in ("out.y", "out.q1", "out.tq1"):
+        assert np.array_equal(out["1"][0][n], out["0"][0][n]), n            # first update, phase A: in front of any dW tile
+    for k in range(K):
+        for n in ("block.params", "block.targets"):
+            assert_close(f"step{k} {n}", out["1"][k][n], out["0"][k][n], 2e-6 * (4 ** k))
+        assert_close(f"step{k} block.m", out["1"][k]["block.m"], out["0"][k]["block.m"], 2e-5 * (4 ** k))
