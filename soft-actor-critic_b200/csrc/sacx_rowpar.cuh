@@ -481,16 +481,63 @@ __device__ __forceinline__ float rp_sum8(float v) {     // sum over the 8 lanes 
 // before the first is used. Per-launch constants (push count, stream keys, update counter at launch) come from RpLaunch.
 struct RpLaunch { i64 pushes, upd0, oldest_slot; unsigned long long rng_seed; unsigned rng_agent, pad; };
 
-__device__ __noinline__ void rp_gather(const RpCtx& c, const RpLaunch& L, i64* __restrict__ slots) {
+template <int MAXE>
+__device__ __forceinline__ void rp_gather_rows(const RpCtx& c, const i64* __restrict__ slots, const float* __restrict__ ring) {
   RP_SMEM;
+  const RunArgs& a = *c.args;
+  const RpProgram& P = *c.P;
+  RpRows& R = *c.R;
+  const int tid = threadIdx.x, O = P.O, A = P.A, ldx = P.ldx;
+  float* xsa = smem_raw + P.sm_xbuf, *xs2 = xsa + RP_RB * ldx, *xpi = xs2 + RP_RB * ldx;
+  const bool w0 = c.rank == 0;
+  const int W = 2 * O + A + 2, mm = tid >> 4, c0 = tid & 15, row = c.row0 + mm;
+  const i64 slot = slots[mm];
+  const float* __restrict__ rec = ring + a.ring_s + (slot >= 0 ? slot : 0) * a.ring_rs;      // record = [s | s2 | a | r | d]: ring_s is its first field
+  float v[MAXE];
+#pragma unroll
+  for (int u = 0; u < MAXE; ++u) {
+    const int col = c0 + 16 * u;
+    v[u] = (col < W && slot >= 0) ? __ldcs(rec + col) : 0.f;
+  }
+  // padding columns (finite zeros: they meet zero-padded weights in the K loop)
+  for (int col = O + c0; col < ldx; col += 16) {
+    if (col >= O + A) xsa[mm * ldx + col] = 0.f;
+    xs2[mm * ldx + col] = 0.f; xpi[mm * ldx + col] = 0.f;
+  }
+  const bool ok = w0 && slot >= 0;
+#pragma unroll
+  for (int u = 0; u < MAXE; ++u) {
+    const int col = c0 + 16 * u;
+    if (col < W) {
+      const float x = v[u];
+      if (col < O) {
+        xsa[mm * ldx + col] = x; xpi[mm * ldx + col] = x;
+        if (ok) { c.base[P.x_sa + (i64)row * P.gldx + col] = x; c.base[P.x_pi + (i64)row * P.gldx + col] = x; }
+      } else if (col < 2 * O) {
+        xs2[mm * ldx + col - O] = x;
+        if (ok) c.base[P.x_s2 + (i64)row * P.gldx + col - O] = x;
+      } else if (col < 2 * O + A) {
+        xsa[mm * ldx + col - O] = x;                       // action columns sit behind the state in X_sa
+        if (ok) c.base[P.x_sa + (i64)row * P.gldx + col - O] = x;
+      } else if (col == 2 * O + A) {
+        R.r[mm] = x;
+        if (ok) c.base[P.b_r + row] = x;
+      } else {
+        R.d[mm] = x;
+        if (ok) c.base[P.b_d + row] = x;
+      }
+    }
+  }
+}
+
+__device__ __noinline__ void rp_gather(const RpCtx& c, const RpLaunch& L, i64* __restrict__ slots) {
   const RunArgs& a = *c.args;
   const Hyper& hp = a.hp;
   const RpProgram& P = *c.P;
   RpRows& R = *c.R;
-  const int tid = threadIdx.x, O = P.O, A = P.A, ldx = P.ldx, B = hp.B;
+  const int tid = threadIdx.x, O = P.O, A = P.A, B = hp.B;
   const float* __restrict__ ring = a.ring;
   const i64 cap = a.ring_capacity;
-  float* xsa = smem_raw + P.sm_xbuf, *xs2 = xsa + RP_RB * ldx, *xpi = xs2 + RP_RB * ldx;
   const bool w0 = c.rank == 0;
   const unsigned long long upd = (unsigned long long)(L.upd0 + c.step);
   if (tid < RP_RB) {
@@ -526,48 +573,13 @@ __device__ __noinline__ void rp_gather(const RpCtx& c, const RpLaunch& L, i64* _
   RP_TRACE(2100);
   __syncthreads();
   // the 16 records: 16 threads per record, thread (mm, c0) takes columns c0, c0 + 16, ... of record mm (W = 2O + A + 2 <= 256
-  // -> at most 16 per thread; 4 at BipedalWalker shape); all loads of a thread are in flight before the first is used
-  const int W = 2 * O + A + 2, mm = tid >> 4, c0 = tid & 15, row = c.row0 + mm;
-  const i64 slot = slots[mm];
-  const float* __restrict__ rec = ring + a.ring_s + (slot >= 0 ? slot : 0) * a.ring_rs;      // record = [s | s2 | a | r | d]: ring_s is its first field
-  constexpr int MAXE = 16;
-  float v[MAXE];
-#pragma unroll
-  for (int u = 0; u < MAXE; ++u) {
-    const int col = c0 + 16 * u;
-    v[u] = (col < W && slot >= 0) ? __ldcs(rec + col) : 0.f;
-  }
-  RP_TRACE(2101);
-  // padding columns (finite zeros: they meet zero-padded weights in the K loop)
-  for (int col = O + c0; col < ldx; col += 16) {
-    if (col >= O + A) xsa[mm * ldx + col] = 0.f;
-    xs2[mm * ldx + col] = 0.f; xpi[mm * ldx + col] = 0.f;
-  }
-  RP_TRACE(2102);
-  const bool ok = w0 && slot >= 0;
-#pragma unroll
-  for (int u = 0; u < MAXE; ++u) {
-    const int col = c0 + 16 * u;
-    if (col < W) {
-      const float x = v[u];
-      if (col < O) {
-        xsa[mm * ldx + col] = x; xpi[mm * ldx + col] = x;
-        if (ok) { c.base[P.x_sa + (i64)row * P.gldx + col] = x; c.base[P.x_pi + (i64)row * P.gldx + col] = x; }
-      } else if (col < 2 * O) {
-        xs2[mm * ldx + col - O] = x;
-        if (ok) c.base[P.x_s2 + (i64)row * P.gldx + col - O] = x;
-      } else if (col < 2 * O + A) {
-        xsa[mm * ldx + col - O] = x;                       // action columns sit behind the state in X_sa
-        if (ok) c.base[P.x_sa + (i64)row * P.gldx + col - O] = x;
-      } else if (col == 2 * O + A) {
-        R.r[mm] = x;
-        if (ok) c.base[P.b_r + row] = x;
-      } else {
-        R.d[mm] = x;
-        if (ok) c.base[P.b_d + row] = x;
-      }
-    }
-  }
+  // -> at most 16 per thread; 4 at BipedalWalker shape); all loads of a thread are in flight before the first is used. The
+  // body is instantiated for 4 / 8 / 16 columns per thread: with one 16-column body every update walked twelve predicated-off
+  // copies of the scatter at BipedalWalker shape, all instruction-cache misses (`no_instruction` at this line in the ncu source view)
+  const int W = 2 * O + A + 2;
+  if (W <= 64) rp_gather_rows<4>(c, slots, ring);
+  else if (W <= 128) rp_gather_rows<8>(c, slots, ring);
+  else rp_gather_rows<16>(c, slots, ring);
   RP_TRACE(2103);
   __syncthreads();
 }
@@ -702,14 +714,15 @@ __device__ __noinline__ void rp_target_critic(const RpCtx& c) {
 }
 
 // phase C entry: the row block's (s, a~pi) rows and the saved head quantities come back from the arena
-__device__ __noinline__ void rp_reload(const RpCtx& c) {
+// (instantiated for 2 / 4 / 9 columns per lane: see rp_gather_rows)
+template <int MAXC>
+__device__ __forceinline__ void rp_reload_impl(const RpCtx& c) {
   RP_SMEM;
   const RpProgram& P = *c.P;
   RpRows& R = *c.R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, O = P.O, A = P.A, ldx = P.ldx, B = c.args->hp.B;
   float* xpi = smem_raw + P.sm_xbuf + 2 * RP_RB * ldx;
   // warp w: rows 2w, 2w+1 of x_pi; loads first
-  constexpr int MAXC = 9;                 // columns per lane (ldx <= 260)
   float v[2][MAXC];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -749,6 +762,12 @@ __device__ __noinline__ void rp_reload(const RpCtx& c) {
     R.lp[tid - 128] = lpv;
   }
   __syncthreads();
+}
+__device__ __noinline__ void rp_reload(const RpCtx& c) {
+  const int ldx = c.P->ldx;               // columns per lane = ceil(ldx / 32), ldx <= 260
+  if (ldx <= 64) rp_reload_impl<2>(c);
+  else if (ldx <= 128) rp_reload_impl<4>(c);
+  else rp_reload_impl<9>(c);
 }
 
 // critics on (s, a~pi): min, policy loss rows, routed dQ (agent.py:238-260)
