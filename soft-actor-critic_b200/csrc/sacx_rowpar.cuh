@@ -802,7 +802,9 @@ __device__ __noinline__ void rp_actor_q(const RpCtx& c) {
 }
 
 // dQ/da from the layer-0 partials, closed-form head backward, delta of the policy's last hidden layer
-__device__ __noinline__ void rp_pi_bwd(const RpCtx& c) {
+// (instantiated for 2A <= 4 / 8 / 16 head columns: see rp_gather_rows)
+template <int JM>
+__device__ __forceinline__ void rp_pi_bwd_impl(const RpCtx& c) {
   RP_SMEM;
   const Hyper& hp = c.args->hp;
   const RpProgram& P = *c.P;
@@ -811,9 +813,9 @@ __device__ __noinline__ void rp_pi_bwd(const RpCtx& c) {
   const int H = P.Hpi, NS = H / RP_CS, n0g = c.rank * NS, cpr = H >> 2;
   const int k = (tid % cpr) << 2, m0 = tid / cpr, mstep = 256 / cpr;
   // this thread's 4 columns of the policy's output layer W_L [2A][H], in flight while the head backward runs
-  float4 wl[2 * RP_MAXA];
+  float4 wl[JM];
 #pragma unroll
-  for (int j = 0; j < 2 * RP_MAXA; ++j)
+  for (int j = 0; j < JM; ++j)
     wl[j] = (j < J) ? __ldcg(reinterpret_cast<const float4*>(c.base + P.pi_WL + (i64)j * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid < RP_RB * RP_MAXA) {
     const int mm = tid >> 3, j = tid & 7, row = c.row0 + mm;
@@ -843,7 +845,7 @@ __device__ __noinline__ void rp_pi_bwd(const RpCtx& c) {
   for (int mm = m0; mm < RP_RB; mm += mstep) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 2 * RP_MAXA; ++j) {
+    for (int j = 0; j < JM; ++j) {
       if (j < J) {
         const float gj = R.dh[mm][j];
         s.x = fmaf(gj, wl[j].x, s.x); s.y = fmaf(gj, wl[j].y, s.y); s.z = fmaf(gj, wl[j].z, s.z); s.w = fmaf(gj, wl[j].w, s.w);
@@ -856,6 +858,12 @@ __device__ __noinline__ void rp_pi_bwd(const RpCtx& c) {
     if (mine && c.row0 + mm < B) *reinterpret_cast<float4*>(c.base + P.dp_last + (i64)(c.row0 + mm) * P.ld_hpi + k) = dv;
   }
   __syncthreads();
+}
+__device__ __noinline__ void rp_pi_bwd(const RpCtx& c) {
+  const int J = 2 * c.P->A;
+  if (J <= 4) rp_pi_bwd_impl<4>(c);
+  else if (J <= 8) rp_pi_bwd_impl<8>(c);
+  else rp_pi_bwd_impl<2 * RP_MAXA>(c);
 }
 
 // ---- weight-gradient tile on the tensor cores (phases B and D) ------------------------------------------------------------
