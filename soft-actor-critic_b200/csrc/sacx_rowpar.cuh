@@ -82,8 +82,14 @@ struct RpRows {            // per-row state of the current row block (every CTA 
 // optional event trace of CTA 0 (profiling aid): (tag, clock64) pairs of the launch's last update
 struct RpTrace { unsigned long long* buf; int n, cap; };
 
+// (compiled into libsacx_debug.so only: ~180 trace points per update, each a load + branch in every warp, are not free in a
+//  kernel whose every instruction costs latency; tools/phase_profile.py loads the debug library for the event trace)
+#ifdef SACX_DEBUG_HOOKS
 #define RP_TRACE(tag) do { if (c.tr->buf && threadIdx.x == 0 && c.tr->n < c.tr->cap) { \
   c.tr->buf[2 * c.tr->n] = (unsigned long long)(tag); c.tr->buf[2 * c.tr->n + 1] = clock64(); c.tr->n++; } } while (0)
+#else
+#define RP_TRACE(tag) do { } while (0)
+#endif
 
 struct RpCtx {
   float* base;
@@ -1132,7 +1138,9 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   __shared__ RunArgs sargs;       // the argument block and the dW tiles' context, read by the helpers (see below)
   __shared__ EpiCtx sec;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef SACX_DEBUG_HOOKS
   const long long t_entry = clock64();
+#endif
   if (tid == 0) {
     for (int i = 0; i < RP_NWSLOT; ++i) rp_mbar_init(&wbar[i], 8);      // one arrival per warp and job
     for (int i = 0; i < RP_DW_NBAR; ++i) rp_mbar_init(&dwbar[i], 1);    // one arrival (the issuing thread's expect_tx) per dW chunk
@@ -1184,11 +1192,13 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
   const int sa = sprog.n_steps_a, sc = sprog.n_steps_c;
   for (int step = 0; step < args.n_steps; ++step) {
     c.step = step; rc.step = step;
+#ifdef SACX_DEBUG_HOOKS
     if (tid == 0 && args.dbg2 && blockIdx.x == 0 && step + 1 == args.n_steps) {
       trace.buf = args.dbg2 + 1; trace.cap = 1000; trace.n = 0;
       if (step == 0) { trace.buf[0] = 100ull; trace.buf[1] = (unsigned long long)t_entry; trace.n = 1; }      // kernel entry (one-update launches)
       RP_TRACE(101);
     }
+#endif
     // optional per-phase timestamps: [step][4 phases][CTA][arrive, release]
     unsigned long long* dbg = (args.dbg && tid == 0) ? args.dbg + ((size_t)step * 4 * gridDim.x + blockIdx.x) * 2 : nullptr;
     const size_t dstride = (size_t)gridDim.x * 2;
@@ -1235,7 +1245,9 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
     }
   }
   RP_TRACE(9999);
+#ifdef SACX_DEBUG_HOOKS
   if (tid == 0 && trace.buf) args.dbg2[0] = (unsigned long long)trace.n;
+#endif
 }
 
 }  // namespace sacx

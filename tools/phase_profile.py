@@ -7,6 +7,8 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the event trace of the row-parallel kernel is compiled into the debug library only
+os.environ.setdefault("SACX_LIB", os.path.join(ROOT, "soft-actor-critic_b200", "lib", "libsacx_debug.so"))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "soft-actor-critic_b200")]
 import bench  # noqa: E402
 import torch  # noqa: E402
