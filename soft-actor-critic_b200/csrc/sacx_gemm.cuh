@@ -60,7 +60,12 @@ struct EpiCtx {
   unsigned long long* t;        // optional intra-tile timestamps (profiling aid), 8 slots
   float* xsm;                   // extra shared memory of the fused paths (XSM_FLOATS)
 };
+// (intra-tile timestamps for tools/phase_profile.py: debug library only, like the row-parallel kernel's event trace)
+#ifdef SACX_DEBUG_HOOKS
 #define SACX_TSTAMP(i) do { if (ctx.t && threadIdx.x == 0) ctx.t[i] = clock64(); } while (0)
+#else
+#define SACX_TSTAMP(i) do { } while (0)
+#endif
 
 // ---- cp.async helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {

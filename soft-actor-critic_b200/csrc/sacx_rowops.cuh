@@ -36,7 +36,11 @@ struct RowCtx {
   uint32_t* gcache = nullptr;
 };
 constexpr int GCACHE_WORDS = 12;
+#ifdef SACX_DEBUG_HOOKS
 #define SACX_RSTAMP(i) do { if (c.t && threadIdx.x == 0) c.t[i] = clock64(); } while (0)
+#else
+#define SACX_RSTAMP(i) do { } while (0)
+#endif
 
 // ---- staging helpers -------------------------------------------------------------------------------
 // copy n floats global -> shared by the whole CTA (cp.async when 16B-aligned, scalar otherwise)
