@@ -274,6 +274,7 @@ static int engine_setup_rp(Engine* e) {
   const int rounds = (nrb + n_groups - 1) / n_groups;
   n_groups = (nrb + rounds - 1) / rounds;
   e->rp_grid = n_groups * RP_CS;
+  e->h_prog.n_row_groups = n_groups;
   if (e->d_rp_part) { cudaFree(e->d_rp_part); e->d_rp_part = nullptr; }       // (second call: plans rebuilt after a failed tensor-core setup)
   if (e->d_prog) { cudaFree(e->d_prog); e->d_prog = nullptr; }
   SACX_CUDA(cudaMalloc((void**)&e->d_rp_part, sizeof(float) * (size_t)RP_MAX_GROUPS * e->h_prog.part_stride));
@@ -484,6 +485,27 @@ static int engine_setup_rp_tma(Engine* e) {
     if (ok_dw) { o.i[2] = P.n_jobs + 2 * k + 1; o.i[3] = P.n_jobs + 2 * k + 2; }
   }
   if (!ok_dw) { for (int k = 0; k < plan.n_ops; ++k) { plan.ops[k].i[2] = 0; plan.ops[k].i[3] = 0; } cudaGetLastError(); }
+  // one-row output layers (the critics' heads) as 128-column vector tiles (rp_dw_vec_tile) instead of 32 x 32 tiles with one valid
+  // row each; then the tile offsets of the two dW phases are recomputed and the grid grows to the widest phase (up to one CTA per
+  // SM): the extra CTAs own no row block and only work in the tile-parallel phases.
+  const char* vec_env = getenv("SACX_RP_DW_VEC");
+  if (ok_dw && !(vec_env && atoi(vec_env) == 0)) {
+    for (int k = 0; k < plan.n_ops; ++k) {
+      Op& o = plan.ops[k];
+      o.i[5] = 0;
+      if (o.type == OP_GEMM && o.epi == EPI_DW && o.i[3] > 0 && o.M == 1 && o.K <= RP_DWV_MAXK && o.N >= 64 && !(o.flags & DW_ATOMIC) && o.i[0] <= 1) {
+        o.i[5] = 1; o.tiles_n = (o.N + RP_DWV_COLS - 1) / RP_DWV_COLS; o.ntiles = o.tiles_n;
+      }
+    }
+    int widest = 0;
+    for (int ph = 0; ph < plan.n_phases; ++ph) {
+      Phase& p = plan.phases[ph];
+      p.ntiles = 0;
+      for (int k = p.op0; k < p.op0 + p.nops; ++k) { plan.ops[k].tile0 = p.ntiles; p.ntiles += plan.ops[k].ntiles; }
+      widest = std::max(widest, p.ntiles);
+    }
+    e->rp_grid = std::min(e->n_sms, std::max(e->rp_grid, widest));
+  }
   if (e->d_rp_maps) { cudaFree(e->d_rp_maps); e->d_rp_maps = nullptr; }
   bool up = cudaMalloc(&e->d_rp_maps, sizeof(CUtensorMap) * maps.size()) == cudaSuccess;
   up = up && cudaMemcpy(e->d_rp_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice) == cudaSuccess;

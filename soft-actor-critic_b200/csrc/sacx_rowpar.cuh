@@ -56,6 +56,7 @@ struct RpStep { int row_op, job0, njobs, load0, nloads, pad0, pad1, pad2; };
 
 struct RpProgram {
   int n_steps_a, n_steps_c, n_jobs, n_loads;
+  int n_row_groups, pad_g;                     // groups that own row blocks (CTAs past 8 x n_row_groups only work in the tile-parallel phases)
   // shared-memory layout (float offsets into the dynamic region)
   int sm_abuf, sm_xbuf, ldx, sm_wslot, sm_red, sm_otile, sm_pw, sm_total;
   int lda, abuf_floats, wslot_floats, gldx;     // gldx: row stride of the batch buffers in the arena
@@ -1033,6 +1034,81 @@ __device__ __noinline__ void rp_dw_tile_tc(const Op& op, const EpiCtx& ctx, int 
   __syncthreads();                                             // the staging area is reused by the next tile
 }
 
+// ---- weight gradient of a one-row output layer (the critics' heads: dW_L[n] = sum_k dout[k] h[k][n]) --------------------------
+// As 32 x 32 tiles this layer was eight tiles per critic with one valid row each -- sixteen more tiles than the 128-CTA grid
+// has CTAs, i.e. a second wave for the whole phase (every tile costs ~10 K cycles whatever it computes: operand delivery).
+// Here ONE tile covers 128 columns: the x boxes [64 rows x 32 columns] of four column blocks arrive by TMA (same tensor map as
+// the square tiles), thread (n, half) runs down half of the batch for column n, the halves meet in shared memory, and the
+// Adam / Polyak epilogue is the square tiles'. Two tiles per critic; with the grid sized to the phase (148 tiles on 148 CTAs at
+// BipedalWalker shape) the critics' dW phase is one wave.
+constexpr int RP_DWV_COLS = 128, RP_DWV_MAXK = 256;
+__device__ __noinline__ void rp_dw_vec_tile(const Op& op, const EpiCtx& ctx, int tile, float* __restrict__ stage, const void* maps,
+                                            uint64_t* bars, unsigned& parity) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = op.N, K = op.K, n0 = tile * RP_DWV_COLS;
+  float* base = ctx.base;
+  const int nchunks = (K + RP_DW_CHUNK - 1) / RP_DW_CHUNK;          // <= 4
+  float* xs = stage;                                                // [col block q][chunk c][64][32], swizzled
+  float* dsm = stage + 4 * RP_DWV_MAXK * 32;                        // dout[k], then the two halves' partial sums
+  float* red = dsm + RP_DWV_MAXK;
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int c = 0; c < nchunks; ++c) rp_mbar_expect_tx(bars + c, 4u * RP_DW_BOX * 4u);      // four column blocks per chunk
+  }
+  if (lane == 0) {
+    const char* mb = reinterpret_cast<const char*>(maps) + (size_t)(op.i[3] - 1) * 128;
+    if (tid != 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int b = warp; b < 4 * nchunks; b += 8) {                    // box b = (chunk, column block): chunk-major, so chunk 0 is complete first
+      const int c = b >> 2, q = b & 3;
+      rp_tma_load(xs + (q * nchunks + c) * RP_DW_BOX, mb, bars + c, n0 + 32 * q, c * RP_DW_CHUNK);
+    }
+  }
+  for (int k = tid; k < RP_DWV_MAXK; k += 256) dsm[k] = (k < K) ? __ldcg(base + op.a + (i64)k * op.a_sk) : 0.f;
+  const bool adam = (op.flags & DW_ADAM) != 0, polyak = (op.flags & DW_POLYAK) != 0;
+  __syncthreads();                                                   // dout staged
+  {
+    const int n = tid & (RP_DWV_COLS - 1), half = tid >> 7, q = n >> 5, col = n & 31;
+    const int cpt = (nchunks + 1) >> 1;                              // chunks per half
+    float acc = 0.f;
+    for (int c = half * cpt; c < min(nchunks, (half + 1) * cpt); ++c) {
+      rp_mbar_wait(bars + c, (parity >> c) & 1u);
+      const float* xb = xs + (q * nchunks + c) * RP_DW_BOX;
+      const float* dk = dsm + c * RP_DW_CHUNK;
+#pragma unroll 8
+      for (int kk = 0; kk < RP_DW_CHUNK; ++kk) acc = fmaf(dk[kk], xb[rp_dw_sw(kk, col)], acc);
+    }
+    // every thread has to have seen every chunk barrier's phase before the next tile re-arms them
+    for (int c = 0; c < nchunks; ++c) rp_mbar_wait(bars + c, (parity >> c) & 1u);
+    red[tid] = acc;
+  }
+  parity ^= (1u << nchunks) - 1u;
+  __syncthreads();
+  if (tid < RP_DWV_COLS / 4) {                                       // 32 threads, four columns each: the square tiles' epilogue
+    const float4 g = make_float4(red[4 * tid] + red[128 + 4 * tid], red[4 * tid + 1] + red[128 + 4 * tid + 1], red[4 * tid + 2] + red[128 + 4 * tid + 2],
+                                 red[4 * tid + 3] + red[128 + 4 * tid + 3]);
+    EpiPre pre;
+    pre.valid = false;
+    float4 outv;
+    if (n0 + 4 * tid < N) epilogue_row4<2>(op, ctx, 0, n0 + 4 * tid, g, pre, false, outv);
+  }
+  if (tile == 0 && op.pb >= 0 && warp == 1) {                        // bias gradient = sum of dout (lane-strided, then butterfly)
+    float sacc = 0.f;
+    for (int k = lane; k < K; k += 32) sacc += dsm[k];
+    sacc = warp_sum(sacc);
+    if (lane == 0) {
+      float bpre[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (adam) {
+        bpre[0] = __ldcg(base + op.pb); bpre[1] = __ldcg(base + op.pbm); bpre[2] = __ldcg(base + op.pbv);
+        if (polyak) bpre[3] = __ldcg(base + op.pbt);
+        bpre[4] = __ldcg(&ctx.scal->adam_step_size[op.opt]); bpre[5] = __ldcg(&ctx.scal->adam_bc2_sqrt[op.opt]);
+        if (polyak) { bpre[6] = __ldcg(&ctx.scal->tau); bpre[7] = __ldcg(&ctx.scal->one_minus_tau); }
+      }
+      epilogue_bias(op, ctx, 0, sacc, bpre);
+    }
+  }
+  __syncthreads();                                                   // the staging area is reused by the next tile
+}
+
 // ---- the step interpreter ---------------------------------------------------------------------------------------------
 struct RpSync {            // barrier state that lives across phases and updates
   unsigned gepoch;         // group barrier epoch
@@ -1169,7 +1245,7 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
     sec = EpiCtx{b0, reinterpret_cast<AgentScalars*>(b0 + args.scal_off), &sargs.hp, nullptr, rp_dyn_smem + WSM_FLOATS + CfgSmall::SMEM_FLOATS};
   }
   __syncthreads();
-  const int rank = blockIdx.x % RP_CS, gid = blockIdx.x / RP_CS, ngr = gridDim.x / RP_CS;
+  const int rank = blockIdx.x % RP_CS, gid = blockIdx.x / RP_CS, ngr = sprog.n_row_groups;
   float* base = args.arena;
   AgentScalars* scal = reinterpret_cast<AgentScalars*>(base + args.scal_off);
   const int B = args.hp.B, nrb = (B + RP_RB - 1) / RP_RB;
@@ -1209,7 +1285,8 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
     for (int ph = 0; ph < 4; ++ph) {
       if ((ph & 1) == 0) {          // row-parallel phases: A (target, critics' forward/backward), C (actor)
         const int s0 = ph ? sa : 0, s1 = ph ? sa + sc : sa;
-        for (int rb = gid; rb < nrb; rb += ngr) { c.row0 = rb * RP_RB; rp_run_steps(c, s0, s1, sy); }
+        if (gid < ngr)                  // (the extra CTAs of a grid sized for the dW phases wait at the phase barrier)
+          for (int rb = gid; rb < nrb; rb += ngr) { c.row0 = rb * RP_RB; rp_run_steps(c, s0, s1, sy); }
       } else {                      // tile-parallel phases: dW + Adam (+ Polyak) of the critics (B) / the policy (D)
         const Phase p = sphase[ph >> 1];
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -1218,7 +1295,8 @@ __global__ void __launch_bounds__(256, 1) sacx_rp_kernel(const Plan* __restrict_
           const Op& op = sops[oi];
           const int lt = t - op.tile0;
           if (op.type == OP_GEMM) {                 // only dW tiles live in these phases
-            if (!(args.barrier_mode & 8) && rp_dw_tc_ok(op, args.rp_maps)) rp_dw_tile_tc(op, ec, lt, dwstage, args.rp_maps, dwbar, dwparity);
+            if (op.i[5] == 1) rp_dw_vec_tile(op, ec, lt, dwstage, args.rp_maps, dwbar, dwparity);      // one-row layer: 128 columns per tile
+            else if (!(args.barrier_mode & 8) && rp_dw_tc_ok(op, args.rp_maps)) rp_dw_tile_tc(op, ec, lt, dwstage, args.rp_maps, dwbar, dwparity);
             else gemm_tile_impl<CfgSmall, 2>(op, ec, lt, gsm);
           }
           else if (op.type == OP_FINAL) {

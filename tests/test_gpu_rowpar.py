@@ -36,7 +36,7 @@ def test_rowpar_is_the_default_single_agent_path(monkeypatch):
     eng = engine_from_golden(g)
     assert eng.path()[0] == "rowpar"
     gx, gy, smem = eng.grid()
-    assert gx % 8 == 0 and gy == 1 and smem <= 227 * 1024
+    assert gx >= 8 and gy == 1 and smem <= 227 * 1024        # 8 CTAs per row group (+ CTAs that only serve the dW phases)
     tiny = engine_from_golden(Golden("tiny_auto"))
     kind, why = tiny.path()
     assert kind == "tiles" and why                                # narrow nets keep the generic tile-parallel kernel
