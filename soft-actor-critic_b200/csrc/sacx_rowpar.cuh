@@ -17,9 +17,10 @@
 // GPC, and only 15 such clusters are co-resident on a B200 at this shared-memory footprint (tools/cluster_probe.cu),
 // one short of the 16 row blocks of a 256-row batch -- the unbalanced second round cost more than the ~1K cycles a
 // software barrier adds over barrier.cluster. Any 128 of the 148 SMs can form 16 groups.
-// Only the weight gradients need all rows: dW + Adam (+ Polyak) stay tile-parallel (the EPI_DW tiles of
-// sacx_gemm.cuh) in two grid-wide phases. One update = 4 grid barriers + 7 group barriers instead of 16 grid
-// barriers. Reference semantics: sac/agent.py:195-327, sac/models.py:73-87.
+// Only the weight gradients need all rows: dW + Adam (+ Polyak) stay tile-parallel in two grid-wide phases -- 3xTF32 tiles
+// with TMA-staged operands (rp_dw_tile_tc), 128-column vector tiles for one-row layers (rp_dw_vec_tile), the FFMA tiles of
+// sacx_gemm.cuh as the fallback -- on a grid sized to the widest of them (CTAs past the row groups only work there).
+// One update = 4 grid barriers + 7 group barriers instead of 16 grid barriers. Reference semantics: sac/agent.py:195-327, sac/models.py:73-87.
 #pragma once
 #include "sacx_kernels.cuh"
 
